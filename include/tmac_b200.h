@@ -1,0 +1,163 @@
+/*
+ * tmac_b200.h -- C ABI of libtmac_b200.so: the B200-native (sm_100a) drop-in for the
+ * preprocessor + qgemm_lut operator pair of microsoft/T-MAC.
+ *
+ * Plain C: pointers and sizes only, no torch / C++ types.  Every entry point cites the
+ * reference interface it replaces (paths relative to the T-MAC tree).
+ *
+ * Pointer domain: every data pointer may be a DEVICE pointer (native use: benchmarks, a
+ * GPU-resident host program) or a HOST pointer (the reference's callers: ggml passes host
+ * memory).  The library classifies each pointer (cudaPointerGetAttributes); host activations /
+ * outputs are staged through pinned buffers, host weights must be registered once
+ * (tmac_b200_upload_weights / ggml_tmac_b200_transform_tensor) so that they stay resident in HBM.
+ *
+ * Errors: the reference's convention -- 0 = ok, -1 = failure (deploy/tuned/<preset>/kernels.h:27,37).
+ * tmac_b200_last_error() returns a static message for the calling thread.  There is NO CPU
+ * fallback: without a usable CUDA device every compute entry point returns -1.
+ */
+#ifndef TMAC_B200_H_
+#define TMAC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TMAC_B200_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------------------------
+ * Kernel configuration = the reference's per-shape `kcfg.ini` section
+ * (TMAC::TMACGeMMConfig, include/t-mac/tmac_gemm_wrapper.h:26-35; written by
+ * deploy/compile.py:156-165) plus the compile-time options the reference bakes into each
+ * generated kernel (deploy/compile.py:207-229: bits, group_size, act_group_size, zero_point,
+ * m_groups).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct tmac_b200_kcfg {
+    int M;               /* output features (rows of the weight matrix), NOT multiplied by bits */
+    int K;               /* input features */
+    int bits;            /* 1..4 */
+    int bm;              /* reference tile of bit-plane rows (kcfg `bm`) -- needed to decode A */
+    int kfactor;         /* kcfg `kfactor` */
+    int simd_n_in;       /* kcfg `simd_n_in`  (16) */
+    int simd_n_out;      /* kcfg `simd_n_out` (8) */
+    int group_size;      /* weight quantisation group along K (kcfg `group_size`) */
+    int act_group_size;  /* LUT-scale group along K; -1 or K = one scale per activation row */
+    int zero_point;      /* scales carry interleaved zero points (GPTQ-like) */
+    int one_scale;       /* m_groups == 1: one unified weight scale (BitNet-like) */
+} tmac_b200_kcfg;
+
+/* dtype codes for activations / outputs (`T` of the reference: float on x86, fp16 on ARM) */
+enum { TMAC_B200_F32 = 0, TMAC_B200_F16 = 1 };
+
+/* ---- library ---------------------------------------------------------------------------- */
+TMAC_B200_API int tmac_b200_init(int device);          /* picks the device, creates streams */
+TMAC_B200_API void tmac_b200_shutdown(void);
+TMAC_B200_API const char *tmac_b200_last_error(void);
+TMAC_B200_API int tmac_b200_version(void);
+/* All launches go to `stream` (a cudaStream_t passed as void*); NULL = the library's own stream. */
+TMAC_B200_API int tmac_b200_set_stream(void *stream);
+TMAC_B200_API int tmac_b200_set_float_type(int dtype); /* TMAC_B200_F32 (default) or _F16 */
+/* LUT handling in qgemm_lut: 0 = auto (device QLUTs written by tmac_b200_preprocessor and host
+ * QLUTs that pass the odd-symmetry check LUT[15-i] == -LUT[i] take the 8-entry fast path, any
+ * other QLUT the general 16-entry path), 1 = always general, 2 = always symmetric. */
+TMAC_B200_API int tmac_b200_set_lut_mode(int mode);
+
+/* ---- configuration (replaces kcfg.ini lookup, tmac_gemm_wrapper.h:230-255) -------------- */
+TMAC_B200_API int tmac_b200_register_kcfg(const tmac_b200_kcfg *cfg);
+/* Parses a reference kcfg.ini (sections qgemm_lut_t{T}_int8_m{M*bits}_k{K}_n{N}_b{bits}).
+ * act_group_size / zero_point / one_scale are derived from lut_scales_size / scales_size unless
+ * the (extension) keys `act_group_size`, `zero_point`, `m_groups` are present. Returns #sections or -1. */
+TMAC_B200_API int tmac_b200_load_kcfg_file(const char *path);
+TMAC_B200_API int tmac_b200_find_kcfg(int m_times_bits, int k, int bits, tmac_b200_kcfg *out);
+TMAC_B200_API void tmac_b200_clear_kcfg(void);
+
+/* ---- weights ---------------------------------------------------------------------------- *
+ * Replaces the load-time re-permutation ggml_tmac_transform_tensor
+ * (3rdparty/llama.cpp/ggml/src/ggml-tmac.cpp:290-501): takes the reference run-time layout
+ *   A      uint8 [M*bits/bm][K/4][bm/2]                     (python/t_mac/weights.py:57-73)
+ *   Scales T     [M*bits/bm][K/group_size][bm/bits (*2)] or [1]   (weights.py:75-88)
+ * (host pointers), re-permutes once into the B200 stream layout, uploads it and registers the
+ * host pointer range [A, A+M*K*bits/8) as an alias of the resident copy, so that later
+ * qgemm_lut_int8 / ggml_tmac_mul_mat_task_compute calls that pass `A + tile_offset` find it.
+ * Returns an opaque handle (>0) or -1. */
+TMAC_B200_API int64_t tmac_b200_upload_weights(const tmac_b200_kcfg *cfg, const void *A,
+                                               const void *scales, int scales_dtype);
+/* Same, from un-permuted quantised weights w uint8 [M][K] in [0,2^bits), scales/zeros fp32
+ * [M][K/group_size] (zeros already in the (z - 2^(bits-1))*s convention, weights.py:28-30). */
+TMAC_B200_API int64_t tmac_b200_upload_plain(const tmac_b200_kcfg *cfg, const uint8_t *w,
+                                             const float *scales, const float *zeros);
+/* Host-only layout transform (no GPU needed): writes the stream layout of tmac_b200_upload_weights
+ * into dst (dst == NULL: size query); layout_out[12] = {pb, rows/lane, rows/super-block,
+ * #super-blocks, K/chunk, quads/chunk, #chunks, scale bytes, zp, one_scale, block bytes, weight bytes}. */
+TMAC_B200_API int64_t tmac_b200_debug_encode(const tmac_b200_kcfg *cfg, const void *A, const void *scales,
+                                             void *dst, size_t cap, int *layout_out);
+TMAC_B200_API int tmac_b200_free_weights(int64_t handle);
+TMAC_B200_API size_t tmac_b200_weights_nbytes(int64_t handle); /* resident bytes in HBM */
+/* Row-shard view for multi-GPU: keep only rows [row0,row0+rows) resident. */
+TMAC_B200_API int64_t tmac_b200_upload_plain_rows(const tmac_b200_kcfg *cfg, const uint8_t *w,
+                                                  const float *scales, const float *zeros,
+                                                  int row0, int rows);
+
+/* ---- native operators (explicit configuration, device or host pointers) ------------------ */
+/* preprocessor: B [N][K] T -> LUT_Scales [N][K/ags] T, LUT_Biases [N][K/ags] T,
+ * QLUT [N][K/4][16] int8.  Bit-exact with lut_ctor_g4_int8_impl / partial_max_g4_int8_k8
+ * (python/t_mac/intrins/lut_ctor.cc:38-260) in the generated loop order
+ * (deploy/tuned/kernels.cc:1002-1040). */
+TMAC_B200_API int tmac_b200_preprocessor(int K, int N, int act_group_size, int dtype, const void *B,
+                                         void *LUT_Scales, void *LUT_Biases, void *QLUT);
+/* qgemm_lut over rows [row0,row0+rows) of a resident tensor: C [N][rows] T.
+ * Same arithmetic as tbl_g4_int8_{float,int32}_update + the generated recombine
+ * (python/t_mac/intrins/tbl.cc:323-630; aarch64-llama-2-7b-2bit/kernels.cc:1059-1075). */
+TMAC_B200_API int tmac_b200_qgemm_lut(int64_t handle, int row0, int rows, int N, int dtype,
+                                      const void *QLUT, const void *LUT_Scales,
+                                      const void *LUT_Biases, void *C);
+/* Fused convenience (llama_cpp_init + llama_cpp_compute of the whole tensor in one call,
+ * workspaces owned by the library): C [N][M] = qgemm_lut(preprocessor(B)). */
+TMAC_B200_API int tmac_b200_gemv(int64_t handle, int N, int dtype, const void *B, void *C);
+/* Debug / parity gate G2: integer bit-plane sums CBits int32 [N][M*bits] in the reference
+ * plane layout ([M/8][bits][8] per tensor), act-group sums folded over K. */
+TMAC_B200_API int tmac_b200_cbits(int64_t handle, int N, const void *QLUT, int32_t *CBits);
+
+/* ---- the reference's generated dispatchers (deploy/compile.py:60-67; instance
+ *      deploy/tuned/aarch64-llama-2-7b-2bit/kernels.h:21-37).  Identical signature and
+ *      argument meaning: m = (rows of this call) * bits, b = bits.  The configuration comes
+ *      from the registered kcfg for (k, b); A must lie inside a range registered with
+ *      tmac_b200_upload_weights (any tile offset), or be a device pointer returned by it. */
+TMAC_B200_API int qgemm_lut_int8(int m, int k, int n, int b, void *A, void *LUT, void *Scales,
+                                 void *LUT_Scales, void *LUT_Biases, void *C);
+TMAC_B200_API int preprocessor_int8(int m, int k, int n, int b, void *B, void *LUT_Scales,
+                                    void *LUT_Biases, void *QLUT);
+
+/* ---- ggml hook (3rdparty/llama.cpp/ggml/include/ggml-tmac.h:25-38).  The four entry points
+ *      that take raw buffers keep their exact signatures; the four that take `ggml_tensor *`
+ *      are offered ggml-free (shape arguments) -- INTEGRATION.md shows the 6-line shim. */
+TMAC_B200_API void ggml_tmac_init(void);
+TMAC_B200_API void ggml_tmac_free(void);
+TMAC_B200_API void ggml_tmac_mul_mat_task_init(void *src1, void *qlut, void *lut_scales,
+                                               void *lut_biases, int n, int k, int m, int bits);
+TMAC_B200_API void ggml_tmac_mul_mat_task_compute(void *src0, void *scales, void *qlut,
+                                                  void *lut_scales, void *lut_biases, void *dst,
+                                                  int n, int k, int m, int bits);
+TMAC_B200_API void ggml_tmac_set_n_threads(int n_threads);
+TMAC_B200_API int ggml_tmac_get_type_bits(int ggml_type);           /* ggml-tmac.cpp:503-526 */
+/* ggml-free forms of can_mul_mat / get_wsize / get_nbytes / transform_tensor */
+TMAC_B200_API int ggml_tmac_b200_can_mul_mat(int src0_type, int src1_is_f32, int dst_is_f32,
+                                             const char *src0_name);
+TMAC_B200_API size_t ggml_tmac_b200_mul_mat_get_wsize(int ne01, int ne10, int ne11, int bits);
+TMAC_B200_API size_t ggml_tmac_b200_get_nbytes(int ne00, int ne01, int bits);
+struct tmac_tensor_extra_b200 {  /* mirrors struct tmac_tensor_extra, ggml-tmac.h:17-23 */
+    int lut_scales_size;
+    int scales_size;
+    int n_tile_num;
+    uint8_t *qweights;  /* host alias key: pass qweights + tile offset to task_compute */
+    float *scales;
+};
+TMAC_B200_API int ggml_tmac_b200_transform_tensor(void *data, int ne00, int ne01, int bits,
+                                                  struct tmac_tensor_extra_b200 *extra);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TMAC_B200_H_ */

@@ -1,0 +1,794 @@
+// tmac_b200.cu -- host side of libtmac_b200.so: context, resident-weight registry, kcfg registry,
+// pointer-domain handling and the C ABI declared in include/tmac_b200.h.
+//
+// Mirrors, for the hot path only:
+//   * the generated dispatchers qgemm_lut_int8 / preprocessor_int8 (deploy/compile.py:60-67),
+//   * TMAC::TMACGeMMWrapper::{llama_cpp_init, llama_cpp_compute, get_kcfg}
+//     (include/t-mac/tmac_gemm_wrapper.h:173-255),
+//   * the ggml hook (3rdparty/llama.cpp/ggml/src/ggml-tmac.cpp).
+// There is no CPU fallback anywhere in this file: every compute entry point launches CUDA
+// kernels or fails with -1.
+#include "../../include/tmac_b200.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "tmac_kernels.cuh"
+#include "tmac_layout.h"
+
+using namespace tmac_b200;
+
+namespace {
+
+thread_local std::string t_err;
+int fail(const std::string &m) { t_err = m; return -1; }
+#define CUDA_OK(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess) return fail(std::string(#expr) + ": " + cudaGetErrorString(e_));    \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = std::max(n, (size_t)4096);
+        if (cudaMalloc(&p, want) != cudaSuccess) return -1;
+        cap = want;
+        return 0;
+    }
+};
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = std::max(n, (size_t)65536);
+        if (cudaMallocHost(&p, want) != cudaSuccess) return -1;
+        cap = want;
+        return 0;
+    }
+};
+
+struct Resident {
+    tmac_b200_kcfg cfg{};
+    StreamLayout L{};
+    unsigned char *d = nullptr;          // stream layout in HBM
+    const unsigned char *host_a = nullptr;  // alias key: reference-layout host range
+    size_t host_a_bytes = 0;
+    int row0 = 0;                        // first row of the full tensor held here (row shards)
+};
+
+struct Context {
+    bool inited = false;
+    int device = 0, sms = 148;
+    cudaStream_t own = nullptr, user = nullptr;
+    bool use_user = false;
+    int float_type = TMAC_B200_F32;
+    int lut_mode = 0;                    // 0 auto, 1 general, 2 symmetric
+    int ks_override = 0;
+    std::map<int64_t, Resident> res;
+    int64_t next_handle = 1;
+    std::vector<tmac_b200_kcfg> kcfgs;
+    std::set<const void *> sym_qluts;    // device QLUT buffers last written by our preprocessor
+    // workspaces
+    DevBuf d_b, d_qlut, d_ls, d_lb, d_c, d_part, d_cnt, d_cbits;
+    PinBuf h_in, h_out;
+    cudaEvent_t stage_ev = nullptr;      // last H2D that read h_in
+    bool stage_pending = false;
+    size_t cnt_zeroed = 0;
+    cudaStream_t stream() const { return use_user ? user : own; }
+};
+
+Context g;
+std::mutex g_mu;
+
+bool is_device_ptr(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int ensure_init() {
+    if (g.inited) return 0;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return fail("no CUDA device: libtmac_b200 has no CPU fallback"); }
+    int dev = 0;
+    if (const char *e = getenv("TMAC_B200_DEVICE")) dev = atoi(e);
+    else { int cur = 0; if (cudaGetDevice(&cur) == cudaSuccess) dev = cur; }
+    CUDA_OK(cudaSetDevice(dev));
+    g.device = dev;
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) return fail("libtmac_b200 is built for sm_100a only (found sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+    g.sms = prop.multiProcessorCount;
+    CUDA_OK(cudaStreamCreateWithFlags(&g.own, cudaStreamNonBlocking));
+    if (const char *e = getenv("TMAC_B200_KS")) g.ks_override = atoi(e);
+    if (const char *e = getenv("TMAC_B200_LUT_MODE")) g.lut_mode = atoi(e);
+    g.inited = true;
+    return 0;
+}
+
+// ---- kernel dispatch ---------------------------------------------------------------------
+typedef void (*gemv_fn)(const GemvParams, const uint32_t, const uint32_t);
+
+template <int PB, bool SYM> gemv_fn pick_qch(int qch) {
+    switch (qch) {
+        case 2: return gemv_kernel<PB, SYM, 2>;
+        case 4: return gemv_kernel<PB, SYM, 4>;
+        case 8: return gemv_kernel<PB, SYM, 8>;
+    }
+    return nullptr;
+}
+gemv_fn pick_gemv(int pb, bool sym, int qch) {
+    if (pb == 4) return sym ? pick_qch<4, true>(qch) : pick_qch<4, false>(qch);
+    if (pb == 2) return sym ? pick_qch<2, true>(qch) : pick_qch<2, false>(qch);
+    if (pb == 1) return sym ? pick_qch<1, true>(qch) : pick_qch<1, false>(qch);
+    return nullptr;
+}
+
+int choose_ks(const StreamLayout &L, int nrsb, int N) {
+    if (g.ks_override > 0) return std::max(1, std::min(g.ks_override, L.nchunk));
+    const int target = 2 * g.sms;
+    int ks = (target + nrsb * N - 1) / (nrsb * N);
+    const int max_ks = std::max(1, L.nchunk / 8);      // >= one chunk per warp per split
+    ks = std::max(1, std::min(ks, std::min(max_ks, 16)));
+    return ks;
+}
+
+// Launch qgemm_lut over rows [row_begin,row_end) (relative to the resident tensor).
+// All pointers are device pointers; C is [N][ldc] with C[n][row - c_row0].
+int launch_gemv(const Resident &R, int row_begin, int row_end, int N, const int8_t *qlut, const float *ls,
+                const float *lb, void *C, int ldc, int c_row0, int out_f16, bool sym, int32_t *cbits_unused) {
+    (void)cbits_unused;
+    const StreamLayout &L = R.L;
+    if (row_begin < 0 || row_end > L.Mout || row_begin >= row_end) return fail("qgemm_lut: bad row range");
+    const int rsb0 = row_begin / L.rsb, rsb1 = (row_end + L.rsb - 1) / L.rsb, nrsb = rsb1 - rsb0;
+    const bool int_path = L.one_scale && L.act_group_size == L.K;
+    GemvParams p{};
+    p.W = R.d + (size_t)rsb0 * L.rsb_stride;
+    p.qlut = qlut; p.lut_scales = ls; p.lut_biases = lb; p.C = C;
+    p.K = L.K; p.N = N; p.ldc = ldc;
+    p.row_begin = row_begin; p.row_end = row_end; p.c_row0 = c_row0;
+    p.bits = L.bits; p.nrsb = nrsb; p.rsb0 = rsb0;
+    p.nchunk = L.nchunk; p.ags = L.act_group_size; p.ck = L.ck;
+    p.zp = L.zp; p.one_scale = L.one_scale; p.int_path = int_path ? 1 : 0; p.sd = L.sd; p.out_f16 = out_f16;
+    p.rsb_stride = L.rsb_stride; p.blk_stride = L.blk; p.scale0 = L.scale0;
+    p.ks = choose_ks(L, nrsb, N);
+    if (p.ks > 1) {
+        const size_t part_bytes = (size_t)N * p.ks * nrsb * L.rsb * sizeof(float);
+        const size_t cnt_bytes = (size_t)N * nrsb * sizeof(int);
+        if (g.d_part.ensure(part_bytes)) return fail("out of device memory (split-K scratch)");
+        if (cnt_bytes > g.d_cnt.cap || g.cnt_zeroed < cnt_bytes) {
+            if (g.d_cnt.ensure(cnt_bytes)) return fail("out of device memory (counters)");
+            CUDA_OK(cudaMemsetAsync(g.d_cnt.p, 0, g.d_cnt.cap, g.stream()));
+            g.cnt_zeroed = g.d_cnt.cap;
+        }
+        p.partial = (float *)g.d_part.p;
+        p.counters = (int *)g.d_cnt.p;
+    }
+    gemv_fn fn = pick_gemv(L.pb, sym, L.qch);
+    if (!fn) return fail("qgemm_lut: unsupported chunking (qch=" + std::to_string(L.qch) + ")");
+    // shared memory: tables + lut scales + chunk biases + cross-warp reduction
+    const int cmax = (L.nchunk + p.ks - 1) / p.ks + 1;
+    const size_t smem = (size_t)cmax * L.qch * 4 * (sym ? 8 : 16) + (size_t)(cmax * L.ck / std::min(L.ck, L.act_group_size) + 2) * 4 +
+                        (size_t)cmax * 4 + (size_t)kGemvWarps * L.rsb * 4 + 64;
+    if (smem > 48 * 1024) {
+        if (smem > 227 * 1024) return fail("qgemm_lut: K too large for the shared-memory LUT (" + std::to_string(smem) + " B)");
+        CUDA_OK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    uint32_t wtx, wty;
+    plane_weight_regs(L.bits, sym, &wtx, &wty);
+    dim3 grid(nrsb, p.ks, N);
+    fn<<<grid, kGemvThreads, smem, g.stream()>>>(p, wtx, wty);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_preprocessor(int K, int N, int ags, int dtype, const void *B, float *ls, float *lb, int8_t *qlut) {
+    if (ags <= 0 || ags > K) ags = K;
+    if (K % 32 || ags % 32 || K % ags) return fail("preprocessor: K and act_group_size must be multiples of 32, K % act_group_size == 0");
+    const int nag = K / ags;
+    int agb = (ags == K) ? 1 : std::max(1, 1024 / ags);
+    const int gx = (nag + agb - 1) / agb;
+    const int ng = agb * (ags / 4);
+    const size_t smem = (size_t)agb * 4 + (size_t)ng * 4 + (size_t)(ng / 8 + 1) * 4;
+    if (smem > 200 * 1024) return fail("preprocessor: activation group too large");
+    dim3 grid(gx, N);
+    if (dtype == TMAC_B200_F16) {
+        if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute((const void *)preprocessor_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        preprocessor_kernel<__half><<<grid, kPreThreads, smem, g.stream()>>>((const __half *)B, ls, lb, qlut, K, ags, agb);
+    } else {
+        if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute((const void *)preprocessor_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        preprocessor_kernel<float><<<grid, kPreThreads, smem, g.stream()>>>((const float *)B, ls, lb, qlut, K, ags, agb);
+    }
+    CUDA_OK(cudaGetLastError());
+    if (g.sym_qluts.size() > 4096) g.sym_qluts.clear();
+    g.sym_qluts.insert(qlut);
+    return 0;
+}
+
+bool host_lut_symmetric(const int8_t *q, size_t groups) {
+    for (size_t g2 = 0; g2 < groups; ++g2) {
+        const int8_t *t = q + g2 * 16;
+        for (int i = 0; i < 8; ++i)
+            if ((int)t[15 - i] != -(int)t[i]) return false;
+    }
+    return true;
+}
+
+int validate_cfg(const tmac_b200_kcfg &c) {
+    if (c.bits < 1 || c.bits > 4) return fail("kcfg: bits must be 1..4");
+    if (c.M <= 0 || c.K <= 0 || c.K % 32) return fail("kcfg: bad M/K");
+    if (c.bm <= 0 || (c.M * c.bits) % c.bm || c.bm % 32 || c.bm % c.bits) return fail("kcfg: bm must divide M*bits and be a multiple of 32 and of bits");
+    if (c.kfactor <= 0 || (c.K / 4) % c.kfactor) return fail("kcfg: kfactor must divide K/4");
+    if (c.simd_n_in != 16 || c.simd_n_out != 8) return fail("kcfg: only simd_n_in=16, simd_n_out=8 (the reference's only instantiation)");
+    return 0;
+}
+
+int64_t register_resident(const tmac_b200_kcfg &cfg, const PlainWeights &P, const void *host_alias, size_t alias_bytes, int row0) {
+    StreamLayout L;
+    bool fp16_ok = true;
+    if (!cfg.one_scale) {
+        fp16_ok = all_fp16_exact(P.scales.data(), P.scales.size()) && (P.zeros.empty() || all_fp16_exact(P.zeros.data(), P.zeros.size()));
+        if (getenv("TMAC_B200_SCALES_F32")) fp16_ok = false;
+    }
+    if (!make_layout(P.Mout, cfg.K, cfg.bits, cfg.group_size, cfg.act_group_size, cfg.zero_point, cfg.one_scale, fp16_ok ? 2 : 4, &L))
+        return fail("unsupported shape / grouping for the stream layout");
+    if (cfg.one_scale) L.scale0 = P.scales.empty() ? 0.f : P.scales[0];
+    std::vector<uint8_t> host(L.total);
+    encode_stream(P, L, host.data());
+    Resident R;
+    R.cfg = cfg; R.L = L; R.row0 = row0;
+    if (cudaMalloc((void **)&R.d, L.total) != cudaSuccess) { cudaGetLastError(); return fail("out of device memory for resident weights"); }
+    if (cudaMemcpy(R.d, host.data(), L.total, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(R.d); return fail("weight upload failed"); }
+    R.host_a = (const unsigned char *)host_alias;
+    R.host_a_bytes = alias_bytes;
+    const int64_t h = g.next_handle++;
+    g.res[h] = R;
+    return h;
+}
+
+Resident *find_by_alias(const void *A, size_t *offset) {
+    const unsigned char *a = (const unsigned char *)A;
+    for (auto &kv : g.res) {
+        Resident &R = kv.second;
+        if (R.host_a && a >= R.host_a && a < R.host_a + R.host_a_bytes) { *offset = (size_t)(a - R.host_a); return &R; }
+        if (a == R.d) { *offset = 0; return &R; }
+    }
+    return nullptr;
+}
+
+const tmac_b200_kcfg *find_kcfg_locked(int m_times_bits, int k, int bits) {
+    const tmac_b200_kcfg *tile_match = nullptr;
+    for (const auto &c : g.kcfgs) {
+        if (c.K != k || c.bits != bits) continue;
+        if (c.M * c.bits == m_times_bits) return &c;
+        if (m_times_bits % c.bm == 0 && m_times_bits < c.M * c.bits && !tile_match) tile_match = &c;
+    }
+    return tile_match;
+}
+
+// Stage helpers for host pointers ---------------------------------------------------------
+// h_in is written by the host at call time and read by an async H2D: before reusing it wait for
+// the previous call's copy; after enqueuing this call's copies record the event again.
+void stage_wait() {
+    if (g.stage_pending) { cudaEventSynchronize(g.stage_ev); g.stage_pending = false; }
+}
+void stage_mark() {
+    if (!g.stage_ev) cudaEventCreateWithFlags(&g.stage_ev, cudaEventDisableTiming);
+    cudaEventRecord(g.stage_ev, g.stream());
+    g.stage_pending = true;
+}
+int h2d(DevBuf &dst, PinBuf &pin, size_t pin_off, const void *src, size_t bytes) {
+    if (dst.ensure(bytes)) return fail("out of device memory");
+    std::memcpy((char *)pin.p + pin_off, src, bytes);
+    CUDA_OK(cudaMemcpyAsync(dst.p, (char *)pin.p + pin_off, bytes, cudaMemcpyHostToDevice, g.stream()));
+    return 0;
+}
+
+size_t esize(int dtype) { return dtype == TMAC_B200_F16 ? 2 : 4; }
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int tmac_b200_init(int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g.inited && device >= 0) {
+        if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return fail("cudaSetDevice failed"); }
+    }
+    return ensure_init();
+}
+
+void tmac_b200_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g.inited) return;
+    cudaStreamSynchronize(g.stream());
+    for (auto &kv : g.res) cudaFree(kv.second.d);
+    g.res.clear();
+    for (DevBuf *b : {&g.d_b, &g.d_qlut, &g.d_ls, &g.d_lb, &g.d_c, &g.d_part, &g.d_cnt, &g.d_cbits}) { if (b->p) cudaFree(b->p); b->p = nullptr; b->cap = 0; }
+    for (PinBuf *b : {&g.h_in, &g.h_out}) { if (b->p) cudaFreeHost(b->p); b->p = nullptr; b->cap = 0; }
+    if (g.stage_ev) cudaEventDestroy(g.stage_ev);
+    g.stage_ev = nullptr; g.stage_pending = false;
+    if (g.own) cudaStreamDestroy(g.own);
+    g.own = nullptr; g.cnt_zeroed = 0; g.sym_qluts.clear();
+    g.inited = false;
+}
+
+const char *tmac_b200_last_error(void) { return t_err.c_str(); }
+int tmac_b200_version(void) { return 100; }
+
+int tmac_b200_set_stream(void *stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    g.user = (cudaStream_t)stream;
+    g.use_user = stream != nullptr;
+    return 0;
+}
+
+int tmac_b200_set_float_type(int dtype) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (dtype != TMAC_B200_F32 && dtype != TMAC_B200_F16) return fail("bad dtype");
+    g.float_type = dtype;
+    return 0;
+}
+
+int tmac_b200_register_kcfg(const tmac_b200_kcfg *cfg) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!cfg) return fail("null kcfg");
+    tmac_b200_kcfg c = *cfg;
+    if (c.simd_n_in == 0) c.simd_n_in = 16;
+    if (c.simd_n_out == 0) c.simd_n_out = 8;
+    if (c.act_group_size <= 0 || c.act_group_size > c.K) c.act_group_size = c.K;
+    if (validate_cfg(c)) return -1;
+    for (auto &o : g.kcfgs)
+        if (o.M == c.M && o.K == c.K && o.bits == c.bits) { o = c; return 0; }
+    g.kcfgs.push_back(c);
+    return 0;
+}
+
+void tmac_b200_clear_kcfg(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g.kcfgs.clear();
+}
+
+int tmac_b200_find_kcfg(int m_times_bits, int k, int bits, tmac_b200_kcfg *out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    const tmac_b200_kcfg *c = find_kcfg_locked(m_times_bits, k, bits);
+    if (!c) return fail("no kcfg for m=" + std::to_string(m_times_bits) + " k=" + std::to_string(k) + " b=" + std::to_string(bits));
+    if (out) *out = *c;
+    return 0;
+}
+
+// Minimal INI reader for the reference's kcfg.ini (deploy/compile.py:156-165,203-204).
+int tmac_b200_load_kcfg_file(const char *path) {
+    FILE *f = path ? fopen(path, "r") : nullptr;
+    if (!f) return fail(std::string("cannot open kcfg file ") + (path ? path : "(null)"));
+    struct Sec { std::string name; std::map<std::string, long> kv; };
+    std::vector<Sec> secs;
+    char line[512];
+    while (fgets(line, sizeof line, f)) {
+        std::string s(line);
+        size_t a = s.find_first_not_of(" \t\r\n");
+        if (a == std::string::npos || s[a] == ';' || s[a] == '#') continue;
+        size_t b = s.find_last_not_of(" \t\r\n");
+        s = s.substr(a, b - a + 1);
+        if (s.front() == '[' && s.back() == ']') { secs.push_back({s.substr(1, s.size() - 2), {}}); continue; }
+        size_t eq = s.find('=');
+        if (eq == std::string::npos || secs.empty()) continue;
+        std::string k = s.substr(0, eq), v = s.substr(eq + 1);
+        k.erase(k.find_last_not_of(" \t") + 1);
+        v.erase(0, v.find_first_not_of(" \t"));
+        secs.back().kv[k] = atol(v.c_str());
+    }
+    fclose(f);
+    int count = 0;
+    for (auto &s : secs) {
+        int t, m, k, n, b;
+        if (sscanf(s.name.c_str(), "qgemm_lut_t%d_int8_m%d_k%d_n%d_b%d", &t, &m, &k, &n, &b) != 5) continue;
+        auto get = [&](const char *key, long dflt) { auto it = s.kv.find(key); return it == s.kv.end() ? dflt : it->second; };
+        tmac_b200_kcfg c{};
+        c.M = m / b; c.K = k; c.bits = b;
+        c.bm = (int)get("bm", 0); c.kfactor = (int)get("kfactor", 16);
+        c.simd_n_in = (int)get("simd_n_in", 16); c.simd_n_out = (int)get("simd_n_out", 8);
+        c.group_size = (int)get("group_size", 128);
+        const long lss = get("lut_scales_size", 0), ss = get("scales_size", 0);
+        c.act_group_size = (int)get("act_group_size", lss > 0 ? (long)k * n / lss : 64);
+        const long per_group = (long)c.M * (k / std::max(1, c.group_size));
+        c.one_scale = (int)get("m_groups", ss > 0 && ss < c.M ? 1 : -1) > 0 ? 1 : 0;
+        c.zero_point = (int)get("zero_point", (!c.one_scale && ss == 2 * per_group) ? 1 : 0);
+        if (tmac_b200_register_kcfg(&c) == 0) ++count;
+    }
+    return count;
+}
+
+int64_t tmac_b200_upload_weights(const tmac_b200_kcfg *cfg_in, const void *A, const void *scales, int scales_dtype) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    if (!cfg_in || !A || !scales) return fail("upload_weights: null argument");
+    if (is_device_ptr(A)) return fail("upload_weights: A must be a host pointer (reference layout)");
+    tmac_b200_kcfg cfg = *cfg_in;
+    if (cfg.simd_n_in == 0) cfg.simd_n_in = 16;
+    if (cfg.simd_n_out == 0) cfg.simd_n_out = 8;
+    if (cfg.act_group_size <= 0 || cfg.act_group_size > cfg.K) cfg.act_group_size = cfg.K;
+    if (validate_cfg(cfg)) return -1;
+    const size_t nsc = cfg.one_scale ? 1 : (size_t)cfg.M * (cfg.K / cfg.group_size) * (cfg.zero_point ? 2 : 1);
+    std::vector<float> s32(nsc);
+    if (scales_dtype == TMAC_B200_F16) {
+        const uint16_t *h = (const uint16_t *)scales;
+        for (size_t i = 0; i < nsc; ++i) s32[i] = f16_bits_to_f32(h[i]);
+    } else
+        std::memcpy(s32.data(), scales, nsc * 4);
+    PlainWeights P;
+    plain_from_reference((const uint8_t *)A, s32.data(), cfg.M, cfg.K, cfg.bits, cfg.bm, cfg.kfactor, cfg.group_size,
+                         cfg.zero_point, cfg.one_scale, &P);
+    return register_resident(cfg, P, A, (size_t)cfg.M * cfg.K * cfg.bits / 8, 0);
+}
+
+int64_t tmac_b200_upload_plain_rows(const tmac_b200_kcfg *cfg_in, const uint8_t *w, const float *scales, const float *zeros,
+                                    int row0, int rows) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    if (!cfg_in || !w || !scales) return fail("upload_plain: null argument");
+    tmac_b200_kcfg cfg = *cfg_in;
+    if (cfg.simd_n_in == 0) cfg.simd_n_in = 16;
+    if (cfg.simd_n_out == 0) cfg.simd_n_out = 8;
+    if (cfg.act_group_size <= 0 || cfg.act_group_size > cfg.K) cfg.act_group_size = cfg.K;
+    if (cfg.bits < 1 || cfg.bits > 4 || cfg.M <= 0 || cfg.K % 32) return fail("upload_plain: bad shape");
+    if (row0 < 0 || rows <= 0 || row0 + rows > cfg.M) return fail("upload_plain: bad row range");
+    if (cfg.zero_point && !zeros && !cfg.one_scale) return fail("upload_plain: zero_point set but zeros == NULL");
+    PlainWeights P;
+    plain_from_w(w, cfg.M, cfg.K, cfg.bits, row0, rows, &P);
+    if (cfg.one_scale) P.scales.assign(1, scales[0]);
+    else {
+        const int NG = cfg.K / cfg.group_size;
+        P.scales.assign(scales + (size_t)row0 * NG, scales + (size_t)(row0 + rows) * NG);
+        if (cfg.zero_point) P.zeros.assign(zeros + (size_t)row0 * NG, zeros + (size_t)(row0 + rows) * NG);
+    }
+    return register_resident(cfg, P, nullptr, 0, row0);
+}
+
+int64_t tmac_b200_upload_plain(const tmac_b200_kcfg *cfg, const uint8_t *w, const float *scales, const float *zeros) {
+    if (!cfg) return fail("upload_plain: null kcfg");
+    return tmac_b200_upload_plain_rows(cfg, w, scales, zeros, 0, cfg->M);
+}
+
+// Host-only: run the reference-layout -> stream-layout transform without touching the GPU and
+// return the stream bytes (used by the CPU test-suite to pin the layout).  dst may be NULL to
+// query the size.  Returns the byte count or -1.
+int64_t tmac_b200_debug_encode(const tmac_b200_kcfg *cfg_in, const void *A, const void *scales, void *dst, size_t cap,
+                               int *layout_out /* int[12] */) {
+    if (!cfg_in || !A || !scales) return fail("debug_encode: null argument");
+    tmac_b200_kcfg cfg = *cfg_in;
+    if (cfg.simd_n_in == 0) cfg.simd_n_in = 16;
+    if (cfg.simd_n_out == 0) cfg.simd_n_out = 8;
+    if (cfg.act_group_size <= 0 || cfg.act_group_size > cfg.K) cfg.act_group_size = cfg.K;
+    if (validate_cfg(cfg)) return -1;
+    PlainWeights P;
+    plain_from_reference((const uint8_t *)A, (const float *)scales, cfg.M, cfg.K, cfg.bits, cfg.bm, cfg.kfactor, cfg.group_size,
+                         cfg.zero_point, cfg.one_scale, &P);
+    bool fp16_ok = true;
+    if (!cfg.one_scale) fp16_ok = all_fp16_exact(P.scales.data(), P.scales.size()) && (P.zeros.empty() || all_fp16_exact(P.zeros.data(), P.zeros.size()));
+    StreamLayout L;
+    if (!make_layout(P.Mout, cfg.K, cfg.bits, cfg.group_size, cfg.act_group_size, cfg.zero_point, cfg.one_scale, fp16_ok ? 2 : 4, &L))
+        return fail("unsupported shape / grouping for the stream layout");
+    if (layout_out) {
+        const int v[12] = {L.pb, L.rw, L.rsb, L.nrsb, L.ck, L.qch, L.nchunk, L.sd, L.zp, L.one_scale, (int)L.blk, (int)L.wbytes};
+        std::memcpy(layout_out, v, sizeof v);
+    }
+    if (dst) {
+        if (cap < L.total) return fail("debug_encode: destination too small");
+        encode_stream(P, L, (uint8_t *)dst);
+    }
+    return (int64_t)L.total;
+}
+
+int tmac_b200_free_weights(int64_t handle) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g.res.find(handle);
+    if (it == g.res.end()) return fail("bad handle");
+    cudaStreamSynchronize(g.stream());
+    cudaFree(it->second.d);
+    g.res.erase(it);
+    return 0;
+}
+
+size_t tmac_b200_weights_nbytes(int64_t handle) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g.res.find(handle);
+    return it == g.res.end() ? 0 : it->second.L.total;
+}
+
+int tmac_b200_set_lut_mode(int mode) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g.lut_mode = mode;
+    return 0;
+}
+
+int tmac_b200_preprocessor(int K, int N, int act_group_size, int dtype, const void *B, void *LUT_Scales, void *LUT_Biases, void *QLUT) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    if (!B || !LUT_Scales || !LUT_Biases || !QLUT || N <= 0) return fail("preprocessor: null/empty argument");
+    const int ags = (act_group_size <= 0 || act_group_size > K) ? K : act_group_size;
+    if (K % 32 || ags % 32 || K % ags) return fail("preprocessor: bad K / act_group_size");
+    const int nag = K / ags;
+    const bool dev_in = is_device_ptr(B), dev_out = is_device_ptr(QLUT);
+    if (dev_out != is_device_ptr(LUT_Scales) || dev_out != is_device_ptr(LUT_Biases)) return fail("preprocessor: outputs must live in one memory domain");
+    const void *dB = B;
+    if (!dev_in) {
+        const size_t bytes = (size_t)N * K * esize(dtype);
+        stage_wait();
+        if (g.h_in.ensure(bytes)) return fail("out of pinned memory");
+        if (h2d(g.d_b, g.h_in, 0, B, bytes)) return -1;
+        stage_mark();
+        dB = g.d_b.p;
+    }
+    float *dls = (float *)LUT_Scales, *dlb = (float *)LUT_Biases;
+    int8_t *dq = (int8_t *)QLUT;
+    const size_t qb = (size_t)N * K * 4, sb = (size_t)N * nag * 4;
+    if (!dev_out) {
+        if (g.d_qlut.ensure(qb) || g.d_ls.ensure(sb) || g.d_lb.ensure(sb)) return fail("out of device memory");
+        dls = (float *)g.d_ls.p; dlb = (float *)g.d_lb.p; dq = (int8_t *)g.d_qlut.p;
+    }
+    if (launch_preprocessor(K, N, ags, dtype, dB, dls, dlb, dq)) return -1;
+    if (!dev_out) {
+        if (g.h_out.ensure(qb + 2 * sb)) return fail("out of pinned memory");
+        char *ho = (char *)g.h_out.p;
+        CUDA_OK(cudaMemcpyAsync(ho, dq, qb, cudaMemcpyDeviceToHost, g.stream()));
+        CUDA_OK(cudaMemcpyAsync(ho + qb, dls, sb, cudaMemcpyDeviceToHost, g.stream()));
+        CUDA_OK(cudaMemcpyAsync(ho + qb + sb, dlb, sb, cudaMemcpyDeviceToHost, g.stream()));
+        CUDA_OK(cudaStreamSynchronize(g.stream()));
+        std::memcpy(QLUT, ho, qb);
+        std::memcpy(LUT_Scales, ho + qb, sb);
+        std::memcpy(LUT_Biases, ho + qb + sb, sb);
+    }
+    return 0;
+}
+
+static int qgemm_impl(Resident &R, int row0, int rows, int N, int dtype, const void *QLUT, const void *LUT_Scales,
+                      const void *LUT_Biases, void *C) {
+    const StreamLayout &L = R.L;
+    if (N <= 0 || rows <= 0) return fail("qgemm_lut: empty problem");
+    if (!QLUT || !LUT_Scales || !LUT_Biases || !C) return fail("qgemm_lut: null argument");
+    const int nag = L.K / L.act_group_size;
+    const size_t qb = (size_t)N * L.K * 4, sb = (size_t)N * nag * 4;
+    const bool dev_lut = is_device_ptr(QLUT);
+    if (dev_lut != is_device_ptr(LUT_Scales) || dev_lut != is_device_ptr(LUT_Biases)) return fail("qgemm_lut: LUT inputs must live in one memory domain");
+    const bool dev_c = is_device_ptr(C);
+    const int8_t *dq = (const int8_t *)QLUT;
+    const float *dls = (const float *)LUT_Scales, *dlb = (const float *)LUT_Biases;
+    bool sym;
+    if (!dev_lut) {
+        sym = host_lut_symmetric((const int8_t *)QLUT, (size_t)N * L.K / 4);
+        stage_wait();
+        if (g.h_in.ensure(qb + 2 * sb)) return fail("out of pinned memory");
+        if (h2d(g.d_qlut, g.h_in, 0, QLUT, qb) || h2d(g.d_ls, g.h_in, qb, LUT_Scales, sb) || h2d(g.d_lb, g.h_in, qb + sb, LUT_Biases, sb)) return -1;
+        stage_mark();
+        dq = (const int8_t *)g.d_qlut.p; dls = (const float *)g.d_ls.p; dlb = (const float *)g.d_lb.p;
+    } else
+        sym = g.sym_qluts.count(QLUT) != 0;
+    if (g.lut_mode == 1) sym = false;
+    if (g.lut_mode == 2) sym = true;
+    void *dC = C;
+    const size_t cb = (size_t)N * rows * esize(dtype);
+    if (!dev_c) {
+        if (g.d_c.ensure(cb)) return fail("out of device memory");
+        dC = g.d_c.p;
+    }
+    if (launch_gemv(R, row0, row0 + rows, N, dq, dls, dlb, dC, rows, row0, dtype == TMAC_B200_F16, sym, nullptr)) return -1;
+    if (!dev_c) {
+        if (g.h_out.ensure(cb)) return fail("out of pinned memory");
+        CUDA_OK(cudaMemcpyAsync(g.h_out.p, dC, cb, cudaMemcpyDeviceToHost, g.stream()));
+        CUDA_OK(cudaStreamSynchronize(g.stream()));
+        std::memcpy(C, g.h_out.p, cb);
+    }
+    return 0;
+}
+
+int tmac_b200_qgemm_lut(int64_t handle, int row0, int rows, int N, int dtype, const void *QLUT, const void *LUT_Scales,
+                        const void *LUT_Biases, void *C) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    auto it = g.res.find(handle);
+    if (it == g.res.end()) return fail("qgemm_lut: bad weight handle");
+    return qgemm_impl(it->second, row0, rows, N, dtype, QLUT, LUT_Scales, LUT_Biases, C);
+}
+
+int tmac_b200_gemv(int64_t handle, int N, int dtype, const void *B, void *C) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    auto it = g.res.find(handle);
+    if (it == g.res.end()) return fail("gemv: bad weight handle");
+    Resident &R = it->second;
+    const StreamLayout &L = R.L;
+    if (!B || !C || N <= 0) return fail("gemv: null/empty argument");
+    const int nag = L.K / L.act_group_size;
+    const size_t qb = (size_t)N * L.K * 4, sb = (size_t)N * nag * 4;
+    const size_t bb = (size_t)N * L.K * esize(dtype), cb = (size_t)N * L.Mout * esize(dtype);
+    const bool dev_b = is_device_ptr(B), dev_c = is_device_ptr(C);
+    const void *dB = B;
+    if (!dev_b) {
+        stage_wait();
+        if (g.h_in.ensure(bb)) return fail("out of pinned memory");
+        if (h2d(g.d_b, g.h_in, 0, B, bb)) return -1;
+        stage_mark();
+        dB = g.d_b.p;
+    }
+    if (g.d_qlut.ensure(qb) || g.d_ls.ensure(sb) || g.d_lb.ensure(sb)) return fail("out of device memory");
+    if (launch_preprocessor(L.K, N, L.act_group_size, dtype, dB, (float *)g.d_ls.p, (float *)g.d_lb.p, (int8_t *)g.d_qlut.p)) return -1;
+    void *dC = C;
+    if (!dev_c) {
+        if (g.d_c.ensure(cb)) return fail("out of device memory");
+        dC = g.d_c.p;
+    }
+    const bool sym = g.lut_mode != 1;
+    if (launch_gemv(R, 0, L.Mout, N, (const int8_t *)g.d_qlut.p, (const float *)g.d_ls.p, (const float *)g.d_lb.p, dC, L.Mout, 0,
+                    dtype == TMAC_B200_F16, sym, nullptr)) return -1;
+    if (!dev_c) {
+        if (g.h_out.ensure(cb)) return fail("out of pinned memory");
+        CUDA_OK(cudaMemcpyAsync(g.h_out.p, dC, cb, cudaMemcpyDeviceToHost, g.stream()));
+        CUDA_OK(cudaStreamSynchronize(g.stream()));
+        std::memcpy(C, g.h_out.p, cb);
+    }
+    return 0;
+}
+
+int tmac_b200_cbits(int64_t handle, int N, const void *QLUT, int32_t *CBits) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    auto it = g.res.find(handle);
+    if (it == g.res.end()) return fail("cbits: bad weight handle");
+    Resident &R = it->second;
+    const StreamLayout &L = R.L;
+    if (!QLUT || !CBits || N <= 0) return fail("cbits: null/empty argument");
+    const size_t qb = (size_t)N * L.K * 4, ob = (size_t)N * L.Mout * L.bits * 4;
+    const int8_t *dq = (const int8_t *)QLUT;
+    if (!is_device_ptr(QLUT)) {
+        stage_wait();
+        if (g.h_in.ensure(qb)) return fail("out of pinned memory");
+        if (h2d(g.d_qlut, g.h_in, 0, QLUT, qb)) return -1;
+        stage_mark();
+        dq = (const int8_t *)g.d_qlut.p;
+    }
+    const bool dev_o = is_device_ptr(CBits);
+    int32_t *dout = CBits;
+    if (!dev_o) {
+        if (g.d_cbits.ensure(ob)) return fail("out of device memory");
+        dout = (int32_t *)g.d_cbits.p;
+    }
+    const long long total = (long long)N * L.Mout * L.bits;
+    cbits_kernel<<<(unsigned)((total + 255) / 256), 256, 0, g.stream()>>>(R.d, dq, dout, L.Mout, L.K, L.bits, L.pb, L.qch, L.nchunk,
+                                                                         L.rsb_stride, L.blk, N);
+    CUDA_OK(cudaGetLastError());
+    if (!dev_o) {
+        CUDA_OK(cudaMemcpyAsync(CBits, dout, ob, cudaMemcpyDeviceToHost, g.stream()));
+        CUDA_OK(cudaStreamSynchronize(g.stream()));
+    }
+    return 0;
+}
+
+// ---- reference dispatchers ---------------------------------------------------------------
+int preprocessor_int8(int m, int k, int n, int b, void *B, void *LUT_Scales, void *LUT_Biases, void *QLUT) {
+    int ags, dtype;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        const tmac_b200_kcfg *c = find_kcfg_locked(m, k, b);
+        if (!c) return fail("preprocessor_int8: shape not configured (m=" + std::to_string(m) + ", k=" + std::to_string(k) + ", b=" + std::to_string(b) + ")");
+        ags = c->act_group_size;
+        dtype = g.float_type;
+    }
+    return tmac_b200_preprocessor(k, n, ags, dtype, B, LUT_Scales, LUT_Biases, QLUT);
+}
+
+int qgemm_lut_int8(int m, int k, int n, int b, void *A, void *LUT, void *Scales, void *LUT_Scales, void *LUT_Biases, void *C) {
+    (void)Scales;  // the resident copy carries the scales that were uploaded together with A
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    if (b < 1 || b > 4 || m <= 0 || m % b) return fail("qgemm_lut_int8: bad m/b");
+    size_t off = 0;
+    Resident *R = find_by_alias(A, &off);
+    if (!R) return fail("qgemm_lut_int8: A is not a registered weight tensor (call tmac_b200_upload_weights / ggml_tmac_b200_transform_tensor at load time)");
+    if (R->cfg.K != k || R->cfg.bits != b) return fail("qgemm_lut_int8: (k, b) do not match the registered tensor");
+    const size_t tile_bytes = (size_t)(k / 4) * R->cfg.bm / 2;
+    if (off % tile_bytes) return fail("qgemm_lut_int8: A is not at a tile boundary");
+    const int row0 = (int)(off / tile_bytes) * (R->cfg.bm / b);
+    const int rows = m / b;
+    if (row0 + rows > R->L.Mout) return fail("qgemm_lut_int8: tile range exceeds the tensor");
+    return qgemm_impl(*R, row0, rows, n, g.float_type, LUT, LUT_Scales, LUT_Biases, C);
+}
+
+// ---- ggml hook -----------------------------------------------------------------------------
+void ggml_tmac_init(void) {
+    if (tmac_b200_init(-1) != 0) { fprintf(stderr, "ggml_tmac_init: %s\n", tmac_b200_last_error()); return; }
+    if (const char *f = getenv("TMAC_KCFG_FILE")) {   // tmac_gemm_wrapper.h:40-56
+        if (tmac_b200_load_kcfg_file(f) < 0) fprintf(stderr, "ggml_tmac_init: %s\n", tmac_b200_last_error());
+    }
+}
+void ggml_tmac_free(void) { tmac_b200_shutdown(); }
+
+// ggml-tmac.cpp:267-275: ggml's n (output dim) / m (batch) are swapped relative to T-MAC.
+void ggml_tmac_mul_mat_task_init(void *src1, void *qlut, void *lut_scales, void *lut_biases, int n, int k, int m, int bits) {
+    if (preprocessor_int8(n * bits, k, m, bits, src1, lut_scales, lut_biases, qlut) != 0)
+        fprintf(stderr, "ggml_tmac_mul_mat_task_init: %s\n", tmac_b200_last_error());
+}
+void ggml_tmac_mul_mat_task_compute(void *src0, void *scales, void *qlut, void *lut_scales, void *lut_biases, void *dst, int n, int k,
+                                    int m, int bits) {
+    if (qgemm_lut_int8(n * bits, k, m, bits, src0, qlut, scales, lut_scales, lut_biases, dst) != 0)
+        fprintf(stderr, "ggml_tmac_mul_mat_task_compute: %s\n", tmac_b200_last_error());
+}
+void ggml_tmac_set_n_threads(int n_threads) { (void)n_threads; /* CPU thread pool size is irrelevant on the GPU */ }
+
+int ggml_tmac_get_type_bits(int type) {  // ggml-tmac.cpp:503-522; ids from ggml.h:359,391-396
+    switch (type) {
+        case 36: return 1;   // GGML_TYPE_I1
+        case 37: return 2;   // GGML_TYPE_I2
+        case 38: return 3;   // GGML_TYPE_I3
+        case 39: return 4;   // GGML_TYPE_I4
+        case 2: return 4;    // GGML_TYPE_Q4_0
+        case 34: return 2;   // GGML_TYPE_TQ1_0
+        case 35: return 2;   // GGML_TYPE_TQ2_0
+        default: return 0;
+    }
+}
+
+int ggml_tmac_b200_can_mul_mat(int src0_type, int src1_is_f32, int dst_is_f32, const char *src0_name) {
+    // ggml-tmac.cpp:238-248 minus the backend check (weights live in HBM here).  Only the
+    // pre-permuted I1..I4 types are accepted by this build (Q4_0 / TQ repacking: INTEGRATION.md).
+    const bool supported = src0_type >= 36 && src0_type <= 39;
+    if (!supported || !src1_is_f32 || !dst_is_f32) return 0;
+    if (src0_name && (!strcmp(src0_name, "token_embd.weight") || !strcmp(src0_name, "output.weight"))) return 0;
+    return 1;
+}
+
+size_t ggml_tmac_b200_mul_mat_get_wsize(int ne01, int ne10, int ne11, int bits) {  // ggml-tmac.cpp:250-265
+    tmac_b200_kcfg c;
+    if (tmac_b200_find_kcfg(ne01 * bits, ne10, bits, &c)) return 0;
+    const size_t lss = (size_t)ne10 / c.act_group_size;
+    size_t wsize = (size_t)ne10 * ne11 * 4 + lss * ne11 * 2 * sizeof(float);
+    return ((wsize - 1) / 64 + 1) * 64;
+}
+
+size_t ggml_tmac_b200_get_nbytes(int ne00, int ne01, int bits) {  // ggml-tmac.cpp:277-288
+    tmac_b200_kcfg c;
+    if (tmac_b200_find_kcfg(ne01 * bits, ne00, bits, &c)) return 0;
+    const size_t ss = c.one_scale ? 1 : (size_t)c.M * (c.K / c.group_size) * (c.zero_point ? 2 : 1);
+    return (size_t)ne00 * ne01 / 8 * bits + ss * sizeof(float);
+}
+
+int ggml_tmac_b200_transform_tensor(void *data, int ne00, int ne01, int bits, struct tmac_tensor_extra_b200 *extra) {
+    // ggml-tmac.cpp:290-354, I1..I4 branch (:336-345): the blob is `permuted weights || fp32 scales`.
+    tmac_b200_kcfg c;
+    if (tmac_b200_find_kcfg(ne01 * bits, ne00, bits, &c)) return -1;
+    if (c.M != ne01) return fail("transform_tensor: kcfg is for a different M");
+    uint8_t *qweights = (uint8_t *)data;
+    float *scales = (float *)(qweights + (size_t)ne00 * ne01 * bits / 8);
+    const int64_t h = tmac_b200_upload_weights(&c, qweights, scales, TMAC_B200_F32);
+    if (h < 0) return -1;
+    if (extra) {
+        extra->lut_scales_size = ne00 / c.act_group_size;
+        extra->scales_size = c.one_scale ? 1 : c.M * (c.K / c.group_size) * (c.zero_point ? 2 : 1);
+        extra->n_tile_num = c.M * c.bits / c.bm;
+        extra->qweights = qweights;
+        extra->scales = scales;
+    }
+    return (int)h;
+}
+
+}  // extern "C"

@@ -1,0 +1,496 @@
+// tmac_kernels.cuh -- hand-written sm_100a kernels of the T-MAC hot path.
+//
+//   preprocessor_kernel : activation row -> per-act-group LUT scale, LUT bias, int8 LUT
+//                         (python/t_mac/intrins/lut_ctor.cc:38-260; loop nest
+//                          deploy/tuned/kernels.cc:1002-1040).  Bit-exact with the x86 reference.
+//   gemv_kernel         : table-lookup GEMV over the stream layout (tmac_layout.h)
+//                         (python/t_mac/intrins/tbl.cc:323-630 + generated recombine
+//                          deploy/tuned/aarch64-llama-2-7b-2bit/kernels.cc:1059-1075).
+//
+// Lookup primitive.  The reference does 16 (NEON) / 32 (AVX2) byte lookups per `tbl`/`pshufb`
+// in a 16-entry int8 table.  On B200 the register-file analogue is PRMT: 4 byte lookups in an
+// 8-byte table held in two registers.  The LUT is odd-symmetric (LUT[15-i] = -LUT[i],
+// lut_ctor.cc:153-155), so 8 entries + a sign bit are enough; the sign is applied by DP4A, whose
+// second operand (+-plane weights 2*alpha_b = 1,2,4,8) is itself fetched with one PRMT from an
+// 8-byte constant table indexed by the sign bits.  One DP4A therefore does "negate, scale by
+// the bit-plane weight, add the 4 lookups" = the int16 adder tree + alpha recombination of the
+// reference, exactly, in int32.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tmac_b200 {
+
+struct GemvParams {
+    const unsigned char *W;        // stream layout (already offset to the first row super-block)
+    const int8_t *qlut;            // [N][K/4][16]
+    const float *lut_scales;       // [N][K/ags]
+    const float *lut_biases;       // [N][K/ags]
+    void *C;                       // [N][ldc] f32 or f16
+    float *partial;                // split-K scratch [N][ks][nrsb*rsb] (float or int32 bits)
+    int *counters;                 // [N][nrsb] arrival counters (zero on entry, reset on exit)
+    int32_t *cbits;                // optional debug output [N][M*bits] (int path only), else null
+    int K, N, ldc;
+    int row_begin, row_end;        // rows (relative to the resident tensor's first row) that are stored
+    int c_row0;                    // C[n][row - c_row0]
+    int bits, nrsb, rsb0;          // rsb0: first super-block index (for row numbering)
+    int nchunk, ags, ck;
+    int zp, one_scale, int_path, sd, out_f16, ks;
+    size_t rsb_stride, blk_stride;
+    float scale0;
+};
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(s));
+    return r;
+}
+__device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// process_quad: 4 K-groups x the lane's RW rows.  acc[r] += sum_{k<4} sum_b 2*alpha_b * sgn * T_k[j]
+// ------------------------------------------------------------------------------------------
+template <int PB, bool SYM> struct Quad;
+
+// sign/plane-weight tables (bytes): index = plane-position | neg << 2
+//   PB 4: {1,2,4,8 | -1,-2,-4,-8}   (bits 3: plane 3 weight 0)
+//   PB 2: {1,2,1,2 | -1,-2,-1,-2}
+//   PB 1: {1,1,1,1 | -1,-1,-1,-1}
+template <bool SYM> struct Quad<4, SYM> {
+    static __device__ __forceinline__ void run(const uint4 w, const uint32_t *tab /* 4 tables */, int *acc,
+                                               uint32_t wtx, uint32_t wty) {
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t wj = ww[k] & 0x77777777u;
+            const uint32_t ws = ((ww[k] >> 1) & 0x44444444u) | 0x32103210u;
+            uint32_t v0, v1;
+            if (SYM) {
+                v0 = prmt(tab[2 * k], tab[2 * k + 1], wj);
+                v1 = prmt(tab[2 * k], tab[2 * k + 1], wj >> 16);
+                acc[0] = __dp4a((int)v0, (int)prmt(wtx, wty, ws), acc[0]);
+                acc[1] = __dp4a((int)v1, (int)prmt(wtx, wty, ws >> 16), acc[1]);
+            } else {
+                const uint32_t *g = tab + 4 * k;
+                v0 = prmt(prmt(g[0], g[1], wj), prmt(g[2], g[3], wj), ws);
+                v1 = prmt(prmt(g[0], g[1], wj >> 16), prmt(g[2], g[3], wj >> 16), ws >> 16);
+                acc[0] = __dp4a((int)v0, (int)wtx, acc[0]);
+                acc[1] = __dp4a((int)v1, (int)wtx, acc[1]);
+            }
+        }
+    }
+};
+
+template <bool SYM> struct Quad<2, SYM> {
+    static __device__ __forceinline__ void run(const uint4 w, const uint32_t *tab, int *acc, uint32_t wtx,
+                                               uint32_t wty) {
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int pr = 0; pr < 2; ++pr) {
+            const uint32_t we = ww[2 * pr], wo = ww[2 * pr + 1];
+            const uint32_t je = we & 0x77777777u, jo = wo & 0x77777777u;
+            const uint32_t se = ((we >> 1) & 0x44444444u) | 0x32103210u;
+            const uint32_t so = ((wo >> 1) & 0x44444444u) | 0x32103210u;
+            if (SYM) {
+                const uint32_t *te = tab + 4 * pr, *to = tab + 4 * pr + 2;
+                const uint32_t v0a = prmt(te[0], te[1], je), v0b = prmt(te[0], te[1], je >> 16);
+                const uint32_t v1a = prmt(to[0], to[1], jo), v1b = prmt(to[0], to[1], jo >> 16);
+                acc[0] = __dp4a((int)prmt(v0a, v1a, 0x5410), (int)prmt(wtx, wty, se), acc[0]);
+                acc[1] = __dp4a((int)prmt(v0a, v1a, 0x7632), (int)prmt(wtx, wty, se >> 16), acc[1]);
+                acc[2] = __dp4a((int)prmt(v0b, v1b, 0x5410), (int)prmt(wtx, wty, so), acc[2]);
+                acc[3] = __dp4a((int)prmt(v0b, v1b, 0x7632), (int)prmt(wtx, wty, so >> 16), acc[3]);
+            } else {
+                const uint32_t *ge = tab + 8 * pr, *go = tab + 8 * pr + 4;
+                const uint32_t l0a = prmt(ge[0], ge[1], je), l0b = prmt(ge[0], ge[1], je >> 16);
+                const uint32_t h0a = prmt(ge[2], ge[3], je), h0b = prmt(ge[2], ge[3], je >> 16);
+                const uint32_t l1a = prmt(go[0], go[1], jo), l1b = prmt(go[0], go[1], jo >> 16);
+                const uint32_t h1a = prmt(go[2], go[3], jo), h1b = prmt(go[2], go[3], jo >> 16);
+                // transpose lo and hi candidates, then pick by the (row-ordered) sign bits
+                acc[0] = __dp4a((int)prmt(prmt(l0a, l1a, 0x5410), prmt(h0a, h1a, 0x5410), se), (int)wtx, acc[0]);
+                acc[1] = __dp4a((int)prmt(prmt(l0a, l1a, 0x7632), prmt(h0a, h1a, 0x7632), se >> 16), (int)wtx, acc[1]);
+                acc[2] = __dp4a((int)prmt(prmt(l0b, l1b, 0x5410), prmt(h0b, h1b, 0x5410), so), (int)wtx, acc[2]);
+                acc[3] = __dp4a((int)prmt(prmt(l0b, l1b, 0x7632), prmt(h0b, h1b, 0x7632), so >> 16), (int)wtx, acc[3]);
+            }
+        }
+    }
+};
+
+__device__ __forceinline__ void transpose4(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t *x) {
+    const uint32_t t01 = prmt(v0, v1, 0x5140), t23 = prmt(v2, v3, 0x5140);
+    const uint32_t u01 = prmt(v0, v1, 0x7362), u23 = prmt(v2, v3, 0x7362);
+    x[0] = prmt(t01, t23, 0x5410);
+    x[1] = prmt(t01, t23, 0x7632);
+    x[2] = prmt(u01, u23, 0x5410);
+    x[3] = prmt(u01, u23, 0x7632);
+}
+
+template <bool SYM> struct Quad<1, SYM> {
+    static __device__ __forceinline__ void run(const uint4 w, const uint32_t *tab, int *acc, uint32_t wtx,
+                                               uint32_t wty) {
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+        uint32_t s[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s[k] = ((ww[k] >> 1) & 0x44444444u) | 0x32103210u;
+        uint32_t xa[4], xb[4];
+        if (SYM) {
+            uint32_t va[4], vb[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t j = ww[k] & 0x77777777u;
+                va[k] = prmt(tab[2 * k], tab[2 * k + 1], j);
+                vb[k] = prmt(tab[2 * k], tab[2 * k + 1], j >> 16);
+            }
+            transpose4(va[0], va[1], va[2], va[3], xa);
+            transpose4(vb[0], vb[1], vb[2], vb[3], xb);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const uint32_t sa = (r & 1) ? (s[r >> 1] >> 16) : s[r >> 1];           // rows 0..3: words 0,0,1,1
+                const uint32_t sb = (r & 1) ? (s[2 + (r >> 1)] >> 16) : s[2 + (r >> 1)]; // rows 4..7: words 2,2,3,3
+                acc[r] = __dp4a((int)xa[r], (int)prmt(wtx, wty, sa), acc[r]);
+                acc[4 + r] = __dp4a((int)xb[r], (int)prmt(wtx, wty, sb), acc[4 + r]);
+            }
+        } else {
+            uint32_t la[4], lb[4], ha[4], hb[4], xla[4], xlb[4], xha[4], xhb[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t j = ww[k] & 0x77777777u;
+                const uint32_t *g = tab + 4 * k;
+                la[k] = prmt(g[0], g[1], j); lb[k] = prmt(g[0], g[1], j >> 16);
+                ha[k] = prmt(g[2], g[3], j); hb[k] = prmt(g[2], g[3], j >> 16);
+            }
+            transpose4(la[0], la[1], la[2], la[3], xla);
+            transpose4(ha[0], ha[1], ha[2], ha[3], xha);
+            transpose4(lb[0], lb[1], lb[2], lb[3], xlb);
+            transpose4(hb[0], hb[1], hb[2], hb[3], xhb);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const uint32_t sa = (r & 1) ? (s[r >> 1] >> 16) : s[r >> 1];
+                const uint32_t sb = (r & 1) ? (s[2 + (r >> 1)] >> 16) : s[2 + (r >> 1)];
+                acc[r] = __dp4a((int)prmt(xla[r], xha[r], sa), (int)wtx, acc[r]);
+                acc[4 + r] = __dp4a((int)prmt(xlb[r], xhb[r], sb), (int)wtx, acc[4 + r]);
+            }
+        }
+        (void)xa; (void)xb;
+    }
+};
+
+// Host helper: the two constant registers handed to Quad<>::run.
+//  SYM : (wtx, wty) = byte table {+w0,+w1,+w2,+w3 | -w0,-w1,-w2,-w3}
+//  !SYM: wtx = constant plane weights (w0..w3), wty unused
+__host__ __device__ inline void plane_weight_regs(int bits, bool sym, uint32_t *wtx, uint32_t *wty) {
+    int w[4];
+    if (bits >= 3) { w[0] = 1; w[1] = 2; w[2] = 4; w[3] = (bits == 4) ? 8 : 0; }
+    else if (bits == 2) { w[0] = 1; w[1] = 2; w[2] = 1; w[3] = 2; }
+    else { w[0] = w[1] = w[2] = w[3] = 1; }
+    uint32_t p = 0, n = 0;
+    for (int i = 0; i < 4; ++i) { p |= (uint32_t)(w[i] & 0xff) << (8 * i); n |= (uint32_t)((-w[i]) & 0xff) << (8 * i); }
+    *wtx = p; *wty = n;
+    (void)sym;
+}
+
+__device__ __forceinline__ float load_scale(const unsigned char *p, int sd, int i) {
+    return sd == 2 ? __half2float(reinterpret_cast<const __half *>(p)[i]) : reinterpret_cast<const float *>(p)[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// gemv_kernel.  grid = (nrsb, ks, N), block = 256 (8 warps).
+//   CTA (rsb, ks, n): rows of one super-block, K chunks [c0,c1).  warp w takes chunks
+//   c0+w, c0+w+8, ...; every lane owns RW rows, so there is no cross-lane reduction; warps are
+//   reduced through shared memory in fixed order; K splits through a global scratch + arrival
+//   counter, the last CTA summing the splits in fixed order (deterministic).
+// ------------------------------------------------------------------------------------------
+constexpr int kGemvThreads = 256;
+constexpr int kGemvWarps = kGemvThreads / 32;
+
+template <int PB, bool SYM, int QCH>
+__global__ void __launch_bounds__(kGemvThreads) gemv_kernel(const GemvParams p, const uint32_t wtx, const uint32_t wty) {
+    constexpr int RW = 8 / PB;
+    constexpr int RSB = 32 * RW;
+    constexpr int TW = SYM ? 2 : 4;               // 32-bit words per group table
+    extern __shared__ __align__(16) unsigned char smem[];
+
+    const int rsb = blockIdx.x, ks = blockIdx.y, n = blockIdx.z;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c0 = (int)((long long)p.nchunk * ks / p.ks);
+    const int c1 = (int)((long long)p.nchunk * (ks + 1) / p.ks);
+    const int ngroups = (c1 - c0) * QCH * 4;
+    const int agq = p.ags / 16;                    // quads per activation group
+    const int ag0 = (c0 * p.ck) / p.ags;
+    const int ag1 = (c1 * p.ck + p.ags - 1) / p.ags;
+
+    uint32_t *tab = reinterpret_cast<uint32_t *>(smem);                       // [ngroups][TW]
+    float *ls_s = reinterpret_cast<float *>(smem + (size_t)ngroups * TW * 4);  // [ag1-ag0]
+    float *lbc_s = ls_s + (ag1 - ag0);                                         // [c1-c0] bias sum per chunk
+    float *red = lbc_s + (c1 - c0);                                            // [8][RSB]
+
+    // ---- prologue: stage the activation tables of this K range -----------------------------
+    {
+        const uint4 *q4 = reinterpret_cast<const uint4 *>(p.qlut + (size_t)n * p.K * 4) + (size_t)c0 * QCH * 4;
+        for (int g = tid; g < ngroups; g += kGemvThreads) {
+            const uint4 L = __ldg(q4 + g);
+            if (SYM) reinterpret_cast<uint2 *>(tab)[g] = make_uint2(L.x, L.y);
+            else     reinterpret_cast<uint4 *>(tab)[g] = make_uint4(L.x, L.y, __byte_perm(L.w, 0, 0x0123), __byte_perm(L.z, 0, 0x0123));
+        }
+        const int nag = p.K / p.ags;
+        const float *lsg = p.lut_scales + (size_t)n * nag, *lbg = p.lut_biases + (size_t)n * nag;
+        for (int a = tid; a < ag1 - ag0; a += kGemvThreads) ls_s[a] = lsg[ag0 + a];
+        if (!p.int_path)
+            for (int c = tid; c < c1 - c0; c += kGemvThreads) {
+                const int a0 = ((c0 + c) * p.ck) / p.ags, a1 = ((c0 + c + 1) * p.ck) / p.ags;
+                float s = 0.f;
+                for (int a = a0; a < a1; ++a) s += lbg[a];
+                lbc_s[c] = s;
+            }
+    }
+    __syncthreads();
+
+    float cacc[RW];
+    int iacc[RW];
+#pragma unroll
+    for (int i = 0; i < RW; ++i) { cacc[i] = 0.f; iacc[i] = 0; }
+
+    const unsigned char *rsb_base = p.W + (size_t)rsb * p.rsb_stride;
+    for (int c = c0 + warp; c < c1; c += kGemvWarps) {
+        const unsigned char *blk = rsb_base + (size_t)c * p.blk_stride;
+        const uint4 *wp = reinterpret_cast<const uint4 *>(blk) + lane;
+        uint4 wv[QCH];
+#pragma unroll
+        for (int q = 0; q < QCH; ++q) wv[q] = ldg_stream(wp + q * 32);
+        float sc[RW], zr[RW];
+        if (!p.one_scale) {
+            const unsigned char *sp = blk + (size_t)QCH * 512;
+#pragma unroll
+            for (int i = 0; i < RW; ++i) {
+                sc[i] = load_scale(sp, p.sd, lane * RW + i);
+                zr[i] = p.zp ? load_scale(sp + (size_t)RSB * p.sd, p.sd, lane * RW + i) : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < RW; ++i) { sc[i] = p.scale0; zr[i] = 0.f; }
+        }
+        const uint32_t *tb = tab + (size_t)(c - c0) * QCH * 4 * TW;
+        float facc[RW];
+#pragma unroll
+        for (int i = 0; i < RW; ++i) facc[i] = 0.f;
+#pragma unroll
+        for (int q = 0; q < QCH; ++q) {
+            uint32_t t[4 * TW];
+#pragma unroll
+            for (int j = 0; j < TW; ++j) {
+                const uint4 tv = reinterpret_cast<const uint4 *>(tb + q * 4 * TW)[j];
+                t[4 * j] = tv.x; t[4 * j + 1] = tv.y; t[4 * j + 2] = tv.z; t[4 * j + 3] = tv.w;
+            }
+            Quad<PB, SYM>::run(wv[q], t, iacc, wtx, wty);
+            if (!p.int_path && ((q + 1) % agq == 0 || q == QCH - 1)) {
+                const float lsv = ls_s[(c * QCH + q) / agq - ag0];
+#pragma unroll
+                for (int i = 0; i < RW; ++i) { facc[i] = fmaf(lsv, (float)iacc[i], facc[i]); iacc[i] = 0; }
+            }
+        }
+        if (!p.int_path) {
+            const float lb = lbc_s[c - c0];
+#pragma unroll
+            for (int i = 0; i < RW; ++i) {
+                float v = fmaf(0.5f * sc[i], facc[i] + lb, cacc[i]);
+                if (p.zp) v = fmaf(zr[i], lb, v);
+                cacc[i] = v;
+            }
+        }
+    }
+
+    // ---- cross-warp reduction (fixed order) --------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < RW; ++i)
+        red[warp * RSB + lane * RW + i] = p.int_path ? __int_as_float(iacc[i]) : cacc[i];
+    __syncthreads();
+
+    const int row_local = tid;                          // RSB <= 256 = blockDim
+    const int row = (p.rsb0 + rsb) * RSB + row_local;   // row relative to the resident tensor
+    float fsum = 0.f;
+    int isum = 0;
+    if (row_local < RSB) {
+#pragma unroll
+        for (int w = 0; w < kGemvWarps; ++w) {
+            const float v = red[w * RSB + row_local];
+            if (p.int_path) isum += __float_as_int(v); else fsum += v;
+        }
+    }
+    const int padded = p.nrsb * RSB;
+    if (p.ks > 1) {
+        float *part = p.partial + ((size_t)n * p.ks + ks) * padded + (size_t)rsb * RSB;
+        if (row_local < RSB) part[row_local] = p.int_path ? __int_as_float(isum) : fsum;
+        __threadfence();
+        __shared__ int s_last;
+        __syncthreads();
+        if (tid == 0) {
+            const int t = atomicAdd(p.counters + (size_t)n * p.nrsb + rsb, 1);
+            s_last = (t == p.ks - 1);
+            if (s_last) p.counters[(size_t)n * p.nrsb + rsb] = 0;   // self-reset for the next launch
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        fsum = 0.f; isum = 0;
+        if (row_local < RSB)
+            for (int k2 = 0; k2 < p.ks; ++k2) {
+                const float v = __ldcg(p.partial + ((size_t)n * p.ks + k2) * padded + (size_t)rsb * RSB + row_local);
+                if (p.int_path) isum += __float_as_int(v); else fsum += v;
+            }
+    }
+    if (row_local >= RSB || row < p.row_begin || row >= p.row_end) return;
+    float out;
+    if (p.int_path) {
+        // C = ((sum_b alpha_b*CBits_b) * LUT_Scales[0] + LUT_Biases[0]*alpha_0) * Scales[0]
+        // (python/t_mac/ops/qgemm.py:160,171-174); isum = sum_b 2*alpha_b*CBits_b exactly.
+        const float cb = __fmul_rn((float)isum, 0.5f);
+        const float t1 = __fmul_rn(cb, ls_s[0]);
+        const float t2 = __fmul_rn(p.lut_biases[(size_t)n * (p.K / p.ags)], 0.5f);
+        out = __fmul_rn(__fadd_rn(t1, t2), p.scale0);
+    } else
+        out = fsum;
+    const size_t o = (size_t)n * p.ldc + (size_t)(row - p.c_row0);
+    if (p.out_f16) reinterpret_cast<__half *>(p.C)[o] = __float2half_rn(out);
+    else reinterpret_cast<float *>(p.C)[o] = out;
+}
+
+// ------------------------------------------------------------------------------------------
+// cbits_kernel (debug / parity gate G2): per-plane int32 sums in the reference plane layout.
+// One thread per (row, plane); straightforward lookups in the full 16-entry table, decoding the
+// stream layout nibble by nibble.  Not a performance path.
+// ------------------------------------------------------------------------------------------
+__global__ void cbits_kernel(const unsigned char *W, const int8_t *qlut, int32_t *cbits, int Mout, int K, int bits,
+                             int pb, int qch, int nchunk, size_t rsb_stride, size_t blk_stride, int N) {
+    const int rw = 8 / pb, rsbsz = 32 * rw;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)N * Mout * bits;
+    if (t >= total) return;
+    const int n = (int)(t / ((long long)Mout * bits));
+    const int rem = (int)(t % ((long long)Mout * bits));
+    const int row = rem / bits, b = rem % bits;
+    const int rsb = row / rsbsz, lane = (row % rsbsz) / rw, i = (row % rsbsz) % rw;
+    const int8_t *lut = qlut + (size_t)n * K * 4;
+    int sum = 0;
+    for (int c = 0; c < nchunk; ++c) {
+        const uint32_t *wq = reinterpret_cast<const uint32_t *>(W + (size_t)rsb * rsb_stride + (size_t)c * blk_stride);
+        for (int q = 0; q < qch; ++q) {
+            const uint32_t *w4 = wq + ((size_t)q * 32 + lane) * 4;
+            for (int k = 0; k < 4; ++k) {
+                const int g = (c * qch + q) * 4 + k;
+                uint32_t j, neg;
+                if (pb == 4) { const uint32_t nb = (w4[k] >> (4 * (4 * i + b))) & 15u; j = nb & 7u; neg = nb >> 3; }
+                else if (pb == 2) {
+                    j = (w4[k] >> (4 * (2 * i + b))) & 7u;
+                    const int pair = k >> 1, nn = b + 2 * (k & 1);
+                    neg = (w4[2 * pair + i / 2] >> (16 * (i % 2) + 4 * nn + 3)) & 1u;
+                } else {
+                    j = (w4[k] >> (4 * i)) & 7u;
+                    neg = (w4[i / 2] >> (16 * (i % 2) + 4 * k + 3)) & 1u;
+                }
+                const uint32_t idx = neg ? (8u | (j ^ 7u)) : j;
+                sum += lut[(size_t)g * 16 + idx];
+            }
+        }
+    }
+    const int p = (row / 8) * 8 * bits + b * 8 + row % 8;
+    cbits[(size_t)n * Mout * bits + p] = sum;
+}
+
+// ------------------------------------------------------------------------------------------
+// preprocessor_kernel.  grid = (ceil(nag / agb), N); block = 256.
+// Each CTA handles `agb` consecutive activation groups of one activation row (agb == nag when
+// act_group_size == K, i.e. a single CTA per row).  fp32 op order identical to the AVX2 branch of
+// lut_ctor.cc (no FMA: only adds, one IEEE division, one IEEE reciprocal, one multiply per entry).
+// ------------------------------------------------------------------------------------------
+constexpr int kPreThreads = 256;
+
+template <typename TIn>
+__device__ __forceinline__ float ld_act(const TIn *p, size_t i);
+template <> __device__ __forceinline__ float ld_act<float>(const float *p, size_t i) { return p[i]; }
+template <> __device__ __forceinline__ float ld_act<__half>(const __half *p, size_t i) { return __half2float(p[i]); }
+
+template <typename TIn>
+__global__ void __launch_bounds__(kPreThreads) preprocessor_kernel(const TIn *B, float *lut_scales, float *lut_biases,
+                                                                    int8_t *qlut, int K, int ags, int agb) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int n = blockIdx.y;
+    const int nag = K / ags;
+    const int a_begin = blockIdx.x * agb;
+    const int a_end = min(nag, a_begin + agb);
+    const int gpa = ags / 4;                              // groups per act group
+    const int g_begin = a_begin * gpa, g_end = a_end * gpa;
+    const int ng = g_end - g_begin;
+    int *smax = reinterpret_cast<int *>(smem);            // [agb] max abs-sum (float bits, >= 0)
+    float *l0 = reinterpret_cast<float *>(smax + agb);    // [ng] LUT[0] of every group
+    float *blk = l0 + ng;                                 // [ng/8] addv8 of every 32-activation block
+    const TIn *b = B + (size_t)n * K;
+    const int tid = threadIdx.x;
+
+    for (int a = tid; a < a_end - a_begin; a += kPreThreads) smax[a] = 0;
+    __syncthreads();
+    // pass 1: abs-sum max per act group (lut_ctor.cc:242-256; association (a0+a1)+(a2+a3) :251)
+    for (int g = tid; g < ng; g += kPreThreads) {
+        const size_t k0 = (size_t)(g_begin + g) * 4;
+        const float a0 = fabsf(ld_act(b, k0)), a1 = fabsf(ld_act(b, k0 + 1));
+        const float a2 = fabsf(ld_act(b, k0 + 2)), a3 = fabsf(ld_act(b, k0 + 3));
+        const float s = __fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3));
+        atomicMax(&smax[g / gpa], __float_as_int(s));
+    }
+    __syncthreads();
+    // pass 2: tables
+    for (int g = tid; g < ng; g += kPreThreads) {
+        const size_t k0 = (size_t)(g_begin + g) * 4;
+        const float b0 = ld_act(b, k0), b1 = ld_act(b, k0 + 1), b2 = ld_act(b, k0 + 2), b3 = ld_act(b, k0 + 3);
+        const float scale = __fdiv_rn(__int_as_float(smax[g / gpa]), 127.0f);      // :256
+        const float ts = (scale != 0.0f) ? __fdiv_rn(1.0f, scale) : 0.0f;          // :124
+        float lut[16];
+#pragma unroll
+        for (int e = 1; e < 16; e += 2) {                                          // :133-151
+            float v = b0;
+            v = (e & 2) ? __fadd_rn(v, b1) : __fsub_rn(v, b1);
+            v = (e & 4) ? __fadd_rn(v, b2) : __fsub_rn(v, b2);
+            v = (e & 8) ? __fadd_rn(v, b3) : __fsub_rn(v, b3);
+            lut[e] = v;
+        }
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) lut[e] = -lut[15 - e];                     // :153-155
+        l0[g] = lut[0];
+        uint32_t packed[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                int q = __float2int_rn(__fmul_rn(lut[4 * w + e], ts));             // :160-171 (rne)
+                q = max(-128, min(127, q));                                       // packs saturation :173-176
+                acc |= (uint32_t)(q & 0xff) << (8 * e);
+            }
+            packed[w] = acc;
+        }
+        reinterpret_cast<uint4 *>(qlut + (size_t)n * K * 4)[g_begin + g] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
+    __syncthreads();
+    // biases: per 32-activation block the _mm256_addv_ps tree (:24-31), then a serial sum over
+    // the blocks of the act group (:157), starting from 0.
+    for (int bi = tid; bi < ng / 8; bi += kPreThreads) {
+        const float *v = l0 + bi * 8;
+        const float r0 = __fadd_rn(v[4], v[0]), r1 = __fadd_rn(v[5], v[1]);
+        const float r2 = __fadd_rn(v[6], v[2]), r3 = __fadd_rn(v[7], v[3]);
+        blk[bi] = __fadd_rn(__fadd_rn(r0, r2), __fadd_rn(r1, r3));
+    }
+    __syncthreads();
+    const int bpa = ags / 32;                              // blocks per act group
+    for (int a = tid; a < a_end - a_begin; a += kPreThreads) {
+        float bias = 0.0f;
+        for (int k = 0; k < bpa; ++k) bias = __fadd_rn(bias, blk[a * bpa + k]);
+        lut_biases[(size_t)n * nag + a_begin + a] = bias;
+        lut_scales[(size_t)n * nag + a_begin + a] = __fdiv_rn(__int_as_float(smax[a]), 127.0f);
+    }
+}
+
+}  // namespace tmac_b200

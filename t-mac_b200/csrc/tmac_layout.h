@@ -1,0 +1,262 @@
+// tmac_layout.h -- the B200 "stream layout" of a quantised weight tensor and the host code that
+// builds it from (a) the reference run-time layout produced by python/t_mac/weights.py:5-88 /
+// ggml_tmac_transform_tensor (3rdparty/llama.cpp/ggml/src/ggml-tmac.cpp:356-490) or (b) plain
+// quantised weights.  Header-only, host side, no CUDA types.
+//
+// Why a new layout: the reference interleaves bit planes / rows for 128-bit NEON/AVX2 `tbl`
+// lookups of one tile (bm plane rows x kfactor groups).  On B200 the lookup primitive is PRMT
+// (4 byte lookups in an 8-byte register table per instruction) followed by DP4A, so the stream
+// is organised as:
+//
+//   tensor   = [row super-block rsb][K chunk c] blocks, contiguous, 16-byte aligned
+//   block    = weights  [quad q < QCH][lane l < 32][word k < 4]   (32-bit words, 512 B per quad)
+//              scales   [lane][RW] (fp16 when every scale is fp16-representable, else fp32)
+//              zeros    [lane][RW] (only with zero points)
+//   word     = the 8 LUT indices of ONE K-group (4 consecutive K positions of one bit plane each)
+//              for the RW = 8/PB rows owned by that lane, PB = bit planes per row in the word
+//              (bits 1 -> PB 1, bits 2 -> PB 2, bits 3/4 -> PB 4; bits 3 pads a zero-weight plane)
+//   nibble   = code: low 3 bits j select one of the 8 stored LUT entries, bit 3 = negate.
+//              LUT[idx] = -LUT[15-idx] (lut_ctor.cc:153-155), so idx<8 -> (j=idx, neg=0) and
+//              idx>=8 -> (j=(15-idx), neg=1), i.e. code = idx < 8 ? idx : idx ^ 7.
+//   K chunk  = one weight-quantisation group (group_size K positions) so that a block carries the
+//              scales it needs; one lane-word quad = 4 consecutive K-groups = 16 K positions.
+//
+// The j bits of nibble n of word k always describe (row i, plane b, group 4q+k) with
+//   PB 4: n = 4i + b            (i < 2)
+//   PB 2: n = 2i + b            (i < 4)
+//   PB 1: n = i                 (i < 8)
+// The neg bits are permuted inside a group pair (PB 2) / quad (PB 1) so that the four sign bits
+// that belong to one DP4A land in one 16-bit half (see pack_quad below and the kernel).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+namespace tmac_b200 {
+
+struct StreamLayout {
+    int Mout = 0, K = 0, bits = 0;
+    int pb = 0, rw = 0, rsb = 0, nrsb = 0;   // planes/word, rows/lane, rows/super-block, #super-blocks
+    int ck = 0, qch = 0, nchunk = 0;         // K per chunk, quads per chunk, chunks
+    int sd = 0;                              // bytes per scale (2 = fp16, 4 = fp32); 0 = no per-row scales
+    int zp = 0, one_scale = 0;
+    int group_size = 0, act_group_size = 0;
+    size_t wbytes = 0, sbytes = 0, blk = 0, rsb_stride = 0, total = 0;
+    float scale0 = 0.f;                      // the unified scale (one_scale)
+};
+
+inline int planes_per_word(int bits) { return bits == 1 ? 1 : (bits == 2 ? 2 : 4); }
+
+// Chunking rule (see header comment).  Returns false when the shape cannot be chunked.
+inline bool make_layout(int Mout, int K, int bits, int group_size, int act_group_size, int zero_point,
+                        int one_scale, int scale_bytes, StreamLayout *L) {
+    if (bits < 1 || bits > 4 || Mout <= 0 || K <= 0 || K % 32) return false;
+    int ags = (act_group_size <= 0 || act_group_size > K) ? K : act_group_size;
+    if (ags % 32 || K % ags) return false;
+    int ck;
+    if (!one_scale) {
+        if (group_size <= 0 || K % group_size || group_size % 32) return false;
+        ck = group_size;
+        if (ck > 128) {                                       // keep blocks small: split big groups
+            ck = 128;
+            if (group_size % 128) return false;
+        }
+        if (ck % ags) return false;                           // act group inside weight group, qgemm.py:112-113
+    } else {
+        ck = 0;
+        const int cands[3] = {128, 64, 32};
+        for (int c : cands)
+            if (K % c == 0 && (ags == K || c % ags == 0)) { ck = c; break; }
+        if (!ck) return false;
+    }
+    L->Mout = Mout; L->K = K; L->bits = bits;
+    L->pb = planes_per_word(bits);
+    L->rw = 8 / L->pb;
+    L->rsb = 32 * L->rw;
+    L->nrsb = (Mout + L->rsb - 1) / L->rsb;
+    L->ck = ck; L->qch = ck / 16; L->nchunk = K / ck;
+    L->zp = (zero_point && !one_scale) ? 1 : 0;
+    L->one_scale = one_scale ? 1 : 0;
+    L->sd = one_scale ? 0 : scale_bytes;
+    L->group_size = one_scale ? K : group_size;
+    L->act_group_size = ags;
+    L->wbytes = (size_t)L->qch * 512;
+    L->sbytes = one_scale ? 0 : (size_t)L->rsb * L->sd * (L->zp ? 2 : 1);
+    L->blk = L->wbytes + L->sbytes;
+    L->rsb_stride = L->blk * L->nchunk;
+    L->total = L->rsb_stride * L->nrsb;
+    return true;
+}
+
+inline uint32_t idx_to_code(uint32_t idx) { return idx < 8 ? idx : (idx ^ 7u); }
+
+// fp32 -> fp16 bits (round-to-nearest-even) and back; used to decide whether scales are
+// losslessly storable as fp16.
+inline uint16_t f32_to_f16_bits(float f) {
+    uint32_t x; std::memcpy(&x, &f, 4);
+    uint32_t sign = (x >> 16) & 0x8000u;
+    int32_t exp = (int32_t)((x >> 23) & 0xff) - 127 + 15;
+    uint32_t man = x & 0x7fffffu;
+    if (((x >> 23) & 0xff) == 0xff) return (uint16_t)(sign | 0x7c00u | (man ? 0x200u : 0));
+    if (exp >= 31) return (uint16_t)(sign | 0x7c00u);
+    if (exp <= 0) {
+        if (exp < -10) return (uint16_t)sign;
+        man |= 0x800000u;
+        uint32_t shift = (uint32_t)(14 - exp);
+        uint32_t half = man >> shift;
+        uint32_t rem = man & ((1u << shift) - 1), mid = 1u << (shift - 1);
+        if (rem > mid || (rem == mid && (half & 1))) ++half;
+        return (uint16_t)(sign | half);
+    }
+    uint32_t half = ((uint32_t)exp << 10) | (man >> 13);
+    uint32_t rem = man & 0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (half & 1))) ++half;
+    return (uint16_t)(sign | half);
+}
+inline float f16_bits_to_f32(uint16_t h) {
+    uint32_t sign = (uint32_t)(h & 0x8000u) << 16, exp = (h >> 10) & 0x1f, man = h & 0x3ffu, x;
+    if (exp == 0) {
+        if (!man) x = sign;
+        else {
+            int e = -1;
+            do { ++e; man <<= 1; } while (!(man & 0x400u));
+            x = sign | ((uint32_t)(127 - 15 - e) << 23) | ((man & 0x3ffu) << 13);
+        }
+    } else if (exp == 31) x = sign | 0x7f800000u | (man << 13);
+    else x = sign | ((exp - 15 + 127) << 23) | (man << 13);
+    float f; std::memcpy(&f, &x, 4);
+    return f;
+}
+inline bool all_fp16_exact(const float *v, size_t n) {
+    for (size_t i = 0; i < n; ++i)
+        if (f16_bits_to_f32(f32_to_f16_bits(v[i])) != v[i]) return false;
+    return true;
+}
+
+// Plain representation used between "decode reference layout" and "encode stream layout":
+// idx [Mout][bits][K/4] 4-bit LUT indices (bit j = bit `b` of w[row][4g+j], weights.py:57-60),
+// scales/zeros [Mout][K/group_size] fp32.
+struct PlainWeights {
+    int Mout = 0, K = 0, bits = 0;
+    std::vector<uint8_t> idx;
+    std::vector<float> scales, zeros;
+    uint8_t at(int row, int b, int g) const { return idx[((size_t)row * bits + b) * (K / 4) + g]; }
+};
+
+inline void plain_from_w(const uint8_t *w, int Mout, int K, int bits, int row0, int rows, PlainWeights *P) {
+    P->Mout = rows; P->K = K; P->bits = bits;
+    const int KG = K / 4;
+    P->idx.assign((size_t)rows * bits * KG, 0);
+    for (int r = 0; r < rows; ++r) {
+        const uint8_t *wr = w + (size_t)(row0 + r) * K;
+        for (int g = 0; g < KG; ++g)
+            for (int b = 0; b < bits; ++b) {
+                uint32_t v = 0;
+                for (int j = 0; j < 4; ++j) v |= ((wr[4 * g + j] >> b) & 1u) << j;
+                P->idx[((size_t)r * bits + b) * KG + g] = (uint8_t)v;
+            }
+    }
+    (void)Mout;
+}
+
+// Inverse of the reference permutation (python/t_mac/weights.py:57-73): bit-plane row p of the
+// tensor, K-group kg -> byte / nibble in A [M/bm][K/4][bm/2].
+inline uint8_t ref_layout_idx(const uint8_t *A, int KG, int bm, int kf, int p, int kg) {
+    const int tile = p / bm, pin = p % bm, slab = pin / 32, s = pin % 16, half = (pin % 32) / 16;
+    const size_t byte = (((size_t)tile * (KG / kf) + kg / kf) * (bm / 32) + slab) * kf * 16 + (size_t)(kg % kf) * 16 + s;
+    return (uint8_t)((A[byte] >> (4 * half)) & 15);
+}
+
+inline void plain_from_reference(const uint8_t *A, const float *S, int Mout, int K, int bits, int bm, int kf,
+                                 int group_size, int zero_point, int one_scale, PlainWeights *P) {
+    P->Mout = Mout; P->K = K; P->bits = bits;
+    const int KG = K / 4;
+    P->idx.assign((size_t)Mout * bits * KG, 0);
+    for (int row = 0; row < Mout; ++row)
+        for (int b = 0; b < bits; ++b) {
+            const int p = (row / 8) * 8 * bits + b * 8 + row % 8;   // weights.py:65
+            uint8_t *dst = &P->idx[((size_t)row * bits + b) * KG];
+            for (int g = 0; g < KG; ++g) dst[g] = ref_layout_idx(A, KG, bm, kf, p, g);
+        }
+    if (one_scale) { P->scales.assign(1, S[0]); P->zeros.clear(); return; }
+    const int NG = K / group_size, rows = bm / bits;
+    P->scales.assign((size_t)Mout * NG, 0.f);
+    if (zero_point) P->zeros.assign((size_t)Mout * NG, 0.f); else P->zeros.clear();
+    for (int row = 0; row < Mout; ++row) {
+        const int tile = row / rows, rin = row % rows;
+        for (int wg = 0; wg < NG; ++wg) {                           // weights.py:75-84
+            const size_t base = ((size_t)tile * NG + wg) * rows * (zero_point ? 2 : 1);
+            if (zero_point) {
+                P->scales[(size_t)row * NG + wg] = S[base + (size_t)(rin / 8) * 16 + rin % 8];
+                P->zeros[(size_t)row * NG + wg] = S[base + (size_t)(rin / 8) * 16 + 8 + rin % 8];
+            } else
+                P->scales[(size_t)row * NG + wg] = S[base + rin];
+        }
+    }
+}
+
+// Encode the four words (groups 4q..4q+3 of the chunk) of one lane.
+inline void pack_quad(const PlainWeights &P, int pb, int row_base, int g_base, uint32_t w[4]) {
+    const int bits = P.bits, rw = 8 / pb;
+    uint32_t code[8][4][4];  // [row i][plane b][k]
+    for (int i = 0; i < rw; ++i)
+        for (int b = 0; b < pb; ++b)
+            for (int k = 0; k < 4; ++k) {
+                const int row = row_base + i;
+                uint32_t idx = (row < P.Mout && b < bits) ? P.at(row, b, g_base + k) : 0u;
+                code[i][b][k] = idx_to_code(idx);
+            }
+    for (int k = 0; k < 4; ++k) w[k] = 0;
+    if (pb == 4) {
+        for (int k = 0; k < 4; ++k)
+            for (int i = 0; i < 2; ++i)
+                for (int b = 0; b < 4; ++b) w[k] |= code[i][b][k] << (4 * (4 * i + b));
+    } else if (pb == 2) {
+        for (int k = 0; k < 4; ++k)
+            for (int i = 0; i < 4; ++i)
+                for (int b = 0; b < 2; ++b) w[k] |= (code[i][b][k] & 7u) << (4 * (2 * i + b));
+        for (int pair = 0; pair < 2; ++pair)          // words (2pair, 2pair+1)
+            for (int r = 0; r < 4; ++r) {             // row r -> word 2pair + r/2, half r%2
+                const int wi = 2 * pair + r / 2, half = r % 2;
+                for (int n = 0; n < 4; ++n) {         // (ge p0, ge p1, go p0, go p1)
+                    const uint32_t neg = code[r][n & 1][2 * pair + (n >> 1)] >> 3;
+                    w[wi] |= neg << (16 * half + 4 * n + 3);
+                }
+            }
+    } else {
+        for (int k = 0; k < 4; ++k)
+            for (int i = 0; i < 8; ++i) w[k] |= (code[i][0][k] & 7u) << (4 * i);
+        for (int h = 0; h < 8; ++h)                   // row h -> word h/2, half h%2, nibble k
+            for (int k = 0; k < 4; ++k) w[h / 2] |= (code[h][0][k] >> 3) << (16 * (h % 2) + 4 * k + 3);
+    }
+}
+
+inline void encode_stream(const PlainWeights &P, const StreamLayout &L, uint8_t *out) {
+    std::memset(out, 0, L.total);
+    const int NG = L.one_scale ? 1 : P.K / L.group_size;
+    for (int rsb = 0; rsb < L.nrsb; ++rsb)
+        for (int c = 0; c < L.nchunk; ++c) {
+            uint8_t *blk = out + (size_t)rsb * L.rsb_stride + (size_t)c * L.blk;
+            uint32_t *wq = reinterpret_cast<uint32_t *>(blk);
+            for (int q = 0; q < L.qch; ++q)
+                for (int lane = 0; lane < 32; ++lane)
+                    pack_quad(P, L.pb, rsb * L.rsb + lane * L.rw, (c * L.qch + q) * 4, wq + ((size_t)q * 32 + lane) * 4);
+            if (L.one_scale) continue;
+            const int wg = (int)(((size_t)c * L.ck) / L.group_size);
+            (void)NG;
+            uint8_t *sp = blk + L.wbytes;
+            for (int part = 0; part < (L.zp ? 2 : 1); ++part)
+                for (int r = 0; r < L.rsb; ++r) {
+                    const int row = rsb * L.rsb + r;
+                    float v = 0.f;
+                    if (row < P.Mout) v = part ? P.zeros[(size_t)row * (P.K / L.group_size) + wg]
+                                               : P.scales[(size_t)row * (P.K / L.group_size) + wg];
+                    uint8_t *dst = sp + ((size_t)part * L.rsb + r) * L.sd;
+                    if (L.sd == 2) { uint16_t h = f32_to_f16_bits(v); std::memcpy(dst, &h, 2); }
+                    else std::memcpy(dst, &v, 4);
+                }
+        }
+}
+
+}  // namespace tmac_b200

@@ -1,0 +1,196 @@
+"""tmac_b200.py -- ctypes binding of libtmac_b200.so (the C ABI in include/tmac_b200.h) plus a
+Python mirror of the reference's host wrapper `TMAC::TMACGeMMWrapper`
+(include/t-mac/tmac_gemm_wrapper.h:79-347) for tests and benchmarks.
+
+This module never computes anything itself and has no CPU fallback: if the shared library is
+missing it raises, and every compute call goes through the C ABI into the sm_100a kernels.
+PyTorch is used by callers only to own device memory / streams; raw pointers cross this boundary.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtmac_b200.so")
+
+F32, F16 = 0, 1
+
+
+class KCfg(C.Structure):
+    """struct tmac_b200_kcfg (include/tmac_b200.h) == TMACGeMMConfig + compile-time options."""
+    _fields_ = [("M", C.c_int), ("K", C.c_int), ("bits", C.c_int), ("bm", C.c_int), ("kfactor", C.c_int),
+                ("simd_n_in", C.c_int), ("simd_n_out", C.c_int), ("group_size", C.c_int),
+                ("act_group_size", C.c_int), ("zero_point", C.c_int), ("one_scale", C.c_int)]
+
+
+class TensorExtra(C.Structure):
+    """struct tmac_tensor_extra_b200 (mirrors ggml-tmac.h:17-23)."""
+    _fields_ = [("lut_scales_size", C.c_int), ("scales_size", C.c_int), ("n_tile_num", C.c_int),
+                ("qweights", C.c_void_p), ("scales", C.c_void_p)]
+
+
+EXPORTS = [
+    "tmac_b200_init", "tmac_b200_shutdown", "tmac_b200_last_error", "tmac_b200_version", "tmac_b200_set_stream",
+    "tmac_b200_set_float_type", "tmac_b200_set_lut_mode", "tmac_b200_register_kcfg", "tmac_b200_load_kcfg_file",
+    "tmac_b200_find_kcfg", "tmac_b200_clear_kcfg", "tmac_b200_upload_weights", "tmac_b200_upload_plain",
+    "tmac_b200_upload_plain_rows", "tmac_b200_debug_encode", "tmac_b200_free_weights", "tmac_b200_weights_nbytes", "tmac_b200_preprocessor",
+    "tmac_b200_qgemm_lut", "tmac_b200_gemv", "tmac_b200_cbits", "qgemm_lut_int8", "preprocessor_int8",
+    "ggml_tmac_init", "ggml_tmac_free", "ggml_tmac_mul_mat_task_init", "ggml_tmac_mul_mat_task_compute",
+    "ggml_tmac_set_n_threads", "ggml_tmac_get_type_bits", "ggml_tmac_b200_can_mul_mat",
+    "ggml_tmac_b200_mul_mat_get_wsize", "ggml_tmac_b200_get_nbytes", "ggml_tmac_b200_transform_tensor",
+]
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the in-tree shared library; fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libtmac_b200.so is not built (run ./build.sh or __graft_entry__.build()); "
+                           "there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    vp, i, i64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+    sig = {
+        "tmac_b200_init": (i, [i]), "tmac_b200_shutdown": (None, []), "tmac_b200_last_error": (C.c_char_p, []),
+        "tmac_b200_version": (i, []), "tmac_b200_set_stream": (i, [vp]), "tmac_b200_set_float_type": (i, [i]),
+        "tmac_b200_set_lut_mode": (i, [i]),
+        "tmac_b200_register_kcfg": (i, [C.POINTER(KCfg)]), "tmac_b200_load_kcfg_file": (i, [C.c_char_p]),
+        "tmac_b200_find_kcfg": (i, [i, i, i, C.POINTER(KCfg)]), "tmac_b200_clear_kcfg": (None, []),
+        "tmac_b200_upload_weights": (i64, [C.POINTER(KCfg), vp, vp, i]),
+        "tmac_b200_upload_plain": (i64, [C.POINTER(KCfg), vp, vp, vp]),
+        "tmac_b200_upload_plain_rows": (i64, [C.POINTER(KCfg), vp, vp, vp, i, i]),
+        "tmac_b200_debug_encode": (i64, [C.POINTER(KCfg), vp, vp, vp, sz, C.POINTER(C.c_int)]),
+        "tmac_b200_free_weights": (i, [i64]), "tmac_b200_weights_nbytes": (sz, [i64]),
+        "tmac_b200_preprocessor": (i, [i, i, i, i, vp, vp, vp, vp]),
+        "tmac_b200_qgemm_lut": (i, [i64, i, i, i, i, vp, vp, vp, vp]),
+        "tmac_b200_gemv": (i, [i64, i, i, vp, vp]), "tmac_b200_cbits": (i, [i64, i, vp, vp]),
+        "qgemm_lut_int8": (i, [i, i, i, i, vp, vp, vp, vp, vp, vp]),
+        "preprocessor_int8": (i, [i, i, i, i, vp, vp, vp, vp]),
+        "ggml_tmac_init": (None, []), "ggml_tmac_free": (None, []),
+        "ggml_tmac_mul_mat_task_init": (None, [vp, vp, vp, vp, i, i, i, i]),
+        "ggml_tmac_mul_mat_task_compute": (None, [vp, vp, vp, vp, vp, vp, i, i, i, i]),
+        "ggml_tmac_set_n_threads": (None, [i]), "ggml_tmac_get_type_bits": (i, [i]),
+        "ggml_tmac_b200_can_mul_mat": (i, [i, i, i, C.c_char_p]),
+        "ggml_tmac_b200_mul_mat_get_wsize": (sz, [i, i, i, i]), "ggml_tmac_b200_get_nbytes": (sz, [i, i, i]),
+        "ggml_tmac_b200_transform_tensor": (i, [vp, i, i, i, C.POINTER(TensorExtra)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class TMACError(RuntimeError):
+    pass
+
+
+def last_error() -> str:
+    return load().tmac_b200_last_error().decode()
+
+
+def check(rc: int, what: str = "") -> int:
+    if rc < 0:
+        raise TMACError("%s failed: %s" % (what or "tmac_b200 call", last_error()))
+    return rc
+
+
+def ptr(x) -> int:
+    """Raw address of a numpy array (host) or torch tensor (host or device)."""
+    if x is None:
+        return 0
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    return x.ctypes.data
+
+
+def make_kcfg(M, K, bits, bm, kfactor=16, group_size=128, act_group_size=64, zero_point=False, one_scale=False) -> KCfg:
+    return KCfg(M, K, bits, bm, kfactor, 16, 8, group_size, act_group_size, int(zero_point), int(one_scale))
+
+
+@dataclass
+class Weights:
+    handle: int
+    cfg: KCfg
+
+    @property
+    def nbytes(self) -> int:
+        return load().tmac_b200_weights_nbytes(self.handle)
+
+    def free(self):
+        if self.handle > 0:
+            load().tmac_b200_free_weights(self.handle)
+            self.handle = -1
+
+
+def upload_reference_layout(cfg: KCfg, A, scales) -> Weights:
+    """A / scales: host numpy arrays in the reference run-time layout (kept alive by the caller:
+    the host range of A is the alias key used by qgemm_lut_int8)."""
+    h = load().tmac_b200_upload_weights(C.byref(cfg), ptr(A), ptr(scales), F32)
+    check(h, "tmac_b200_upload_weights")
+    return Weights(h, cfg)
+
+
+def upload_plain(cfg: KCfg, w, scales, zeros=None, row0: int = 0, rows: Optional[int] = None) -> Weights:
+    rows = cfg.M - row0 if rows is None else rows
+    h = load().tmac_b200_upload_plain_rows(C.byref(cfg), ptr(w), ptr(scales), ptr(zeros), row0, rows)
+    check(h, "tmac_b200_upload_plain_rows")
+    return Weights(h, cfg)
+
+
+def preprocessor(K, N, ags, B, lut_scales, lut_biases, qlut, dtype=F32):
+    check(load().tmac_b200_preprocessor(K, N, ags, dtype, ptr(B), ptr(lut_scales), ptr(lut_biases), ptr(qlut)),
+          "tmac_b200_preprocessor")
+
+
+def qgemm_lut(wt: Weights, N, qlut, lut_scales, lut_biases, Cout, row0=0, rows=None, dtype=F32):
+    rows = wt.cfg.M - row0 if rows is None else rows
+    check(load().tmac_b200_qgemm_lut(wt.handle, row0, rows, N, dtype, ptr(qlut), ptr(lut_scales), ptr(lut_biases), ptr(Cout)),
+          "tmac_b200_qgemm_lut")
+
+
+def gemv(wt: Weights, N, B, Cout, dtype=F32):
+    check(load().tmac_b200_gemv(wt.handle, N, dtype, ptr(B), ptr(Cout)), "tmac_b200_gemv")
+
+
+def cbits(wt: Weights, N, qlut, out):
+    check(load().tmac_b200_cbits(wt.handle, N, ptr(qlut), ptr(out)), "tmac_b200_cbits")
+
+
+class TMACGeMMWrapper:
+    """Python mirror of TMAC::TMACGeMMWrapper<T> (include/t-mac/tmac_gemm_wrapper.h:79-347):
+    same method names and argument meaning; kernels are looked up by (M, K, N, bits) in the kcfg
+    registry instead of a generated `if` chain."""
+
+    def __init__(self, n_threads: int = 1, act_group_size: int = 32, kcfg_file: str = "", library_file: str = ""):
+        self._lib = load()
+        check(self._lib.tmac_b200_init(-1), "tmac_b200_init")
+        self._act_group_size = act_group_size
+        kcfg_file = kcfg_file or os.environ.get("TMAC_KCFG_FILE", "")  # tmac_gemm_wrapper.h:40-56
+        if kcfg_file:
+            check(self._lib.tmac_b200_load_kcfg_file(kcfg_file.encode()), "load kcfg")
+
+    def set_num_threads(self, n_threads: int):  # :102-112 -- no CPU thread pool on the GPU path
+        self._lib.ggml_tmac_set_n_threads(n_threads)
+
+    def get_kcfg(self, M, K, N, bits) -> KCfg:  # :230-255
+        out = KCfg()
+        check(self._lib.tmac_b200_find_kcfg(M * bits, K, bits, C.byref(out)), "get_kcfg")
+        return out
+
+    def llama_cpp_init(self, B, qlut, lut_scales, lut_biases, M, K, N, bits):  # :173-195
+        check(self._lib.preprocessor_int8(M * bits, K, N, bits, ptr(B), ptr(lut_scales), ptr(lut_biases), ptr(qlut)),
+              "preprocessor_int8")
+
+    def llama_cpp_compute(self, A, scales, qlut, lut_scales, lut_biases, Cout, M, K, N, bits):  # :200-228
+        check(self._lib.qgemm_lut_int8(M * bits, K, N, bits, ptr(A), ptr(qlut), ptr(scales), ptr(lut_scales),
+                                       ptr(lut_biases), ptr(Cout)), "qgemm_lut_int8")

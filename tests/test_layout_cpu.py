@@ -1,0 +1,150 @@
+"""CPU suite, part 2: the host side of libtmac_b200.so without a GPU.
+ * the shared library loads and exports every symbol include/tmac_b200.h declares;
+ * kcfg registry / kcfg.ini parsing (host logic);
+ * the reference-layout -> stream-layout transform (tmac_b200_debug_encode) decodes, through a
+   numpy emulation of the kernel's PRMT/DP4A algebra (tests/stream_emul.py), to exactly the
+   integer sums of the oracle, for symmetric and general LUTs;
+ * no compute entry point works without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import stream_emul as E
+import tmac_b200 as tb
+import tmac_oracle as T
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    lib = tb.load()
+    hdr = open(os.path.join(ROOT, "include", "tmac_b200.h")).read()
+    declared = set(re.findall(r"TMAC_B200_API\s+[\w\s\*]+?\b(\w+)\s*\(", hdr))
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), "libtmac_b200.so does not export %s" % name
+    assert declared == set(tb.EXPORTS), declared ^ set(tb.EXPORTS)
+    assert lib.tmac_b200_version() >= 100
+
+
+def test_kcfg_registry_and_ini(tmp_path):
+    lib = tb.load()
+    lib.tmac_b200_clear_kcfg()
+    ini = tmp_path / "kcfg.ini"
+    # the reference's own format (deploy/tuned/aarch64-hf-bitnet-3b/kcfg.ini, deploy/compile.py:156-165)
+    ini.write_text("""[qgemm_lut_t1_int8_m6400_k8640_n1_b2]
+bm = 128
+simd_n_in = 16
+simd_n_out = 8
+kfactor = 16
+group_size = 128
+lut_scales_size = 135
+scales_size = 1
+n_tile_num = 50
+
+[qgemm_lut_t1_int8_m8192_k4096_n1_b2]
+bm = 128
+simd_n_in = 16
+simd_n_out = 8
+kfactor = 16
+group_size = 128
+lut_scales_size = 64
+scales_size = 262144
+n_tile_num = 64
+""")
+    assert lib.tmac_b200_load_kcfg_file(str(ini).encode()) == 2
+    c = tb.KCfg()
+    assert lib.tmac_b200_find_kcfg(6400, 8640, 2, C.byref(c)) == 0
+    assert (c.M, c.K, c.bits, c.bm, c.act_group_size, c.one_scale, c.zero_point) == (3200, 8640, 2, 128, 64, 1, 0)
+    assert lib.tmac_b200_find_kcfg(8192, 4096, 2, C.byref(c)) == 0
+    assert (c.M, c.group_size, c.act_group_size, c.one_scale, c.zero_point) == (4096, 128, 64, 0, 1)
+    # a tile-sized m (bm) resolves to the same section, like the reference's dispatcher (kernels.h:21-37)
+    assert lib.tmac_b200_find_kcfg(128, 4096, 2, C.byref(c)) == 0 and c.M == 4096
+    assert lib.tmac_b200_find_kcfg(128, 4096, 4, C.byref(c)) == -1
+    assert b"no kcfg" in lib.tmac_b200_last_error()
+    # wsize / nbytes formulas of ggml-tmac.cpp:250-288
+    assert lib.ggml_tmac_b200_mul_mat_get_wsize(4096, 4096, 1, 2) == ((4096 * 4 + 64 * 2 * 4 - 1) // 64 + 1) * 64
+    assert lib.ggml_tmac_b200_get_nbytes(4096, 4096, 2) == 4096 * 4096 // 8 * 2 + 262144 * 4
+    assert [lib.ggml_tmac_get_type_bits(t) for t in (36, 37, 38, 39, 2, 34, 35, 0)] == [1, 2, 3, 4, 4, 2, 2, 0]
+    assert lib.ggml_tmac_b200_can_mul_mat(37, 1, 1, b"blk.0.attn_q.weight") == 1
+    assert lib.ggml_tmac_b200_can_mul_mat(37, 1, 1, b"output.weight") == 0
+    bad = tb.make_kcfg(100, 4096, 2, 128)
+    assert lib.tmac_b200_register_kcfg(C.byref(bad)) == -1  # bm does not divide M*bits
+    lib.tmac_b200_clear_kcfg()
+
+
+CASES = [
+    T.Config(128, 512, 2, zero_point=True), T.Config(64, 256, 4), T.Config(128, 256, 4, zero_point=True),
+    T.Config(128, 256, 3), T.Config(256, 256, 1, zero_point=True), T.Config(160, 640, 2, one_scale=True),
+    T.Config(64, 256, 4, kfactor=8, group_size=32, act_group_size=32),
+    T.Config(192, 512, 2, bm=128, kfactor=8, group_size=64, act_group_size=32, zero_point=True),
+]
+
+
+@pytest.mark.parametrize("cfg", CASES, ids=lambda c: "w%d_%dx%d%s" % (c.bits, c.Mout, c.K, "_os" if c.one_scale else ""))
+@pytest.mark.parametrize("sym", [True, False], ids=["symLUT", "generalLUT"])
+def test_stream_layout_decodes_to_oracle_sums(oracle, cfg, sym):
+    lib = tb.load()
+    cfg = cfg.resolved()
+    w, sc, z, x = T.make_problem(cfg, seed=21, N=1)
+    A, S = T.pack_reference_layout(w, sc, z, cfg)
+    k = tb.make_kcfg(cfg.Mout, cfg.K, cfg.bits, cfg.bm, cfg.kfactor, cfg.group_size, cfg.act_group_size, cfg.zero_point, cfg.one_scale)
+    lay = (C.c_int * 12)()
+    n = lib.tmac_b200_debug_encode(C.byref(k), A.ctypes.data, S.ctypes.data, None, 0, lay)
+    assert n > 0, tb.last_error()
+    buf = np.zeros(n, np.uint8)
+    assert lib.tmac_b200_debug_encode(C.byref(k), A.ctypes.data, S.ctypes.data, buf.ctypes.data, n, lay) == n
+    if sym:
+        qlut, _, _ = oracle.preprocessor(x, cfg.act_group_size)
+    else:  # the reference's own verification feeds random, non-symmetric LUTs (python/t_mac/ops/qgemm.py:289)
+        qlut = np.random.default_rng(5).integers(-127, 128, size=(1, cfg.K // 4, 16)).astype(np.int8)
+    got = E.emulate_int_sums(buf, list(lay), qlut[0], cfg.Mout, cfg.bits, sym)
+    cb = oracle.cbits(cfg, A, qlut)[0].astype(np.int64)          # [M*bits] reference plane layout
+    rows = np.arange(cfg.Mout)
+    want = np.zeros(cfg.Mout, np.int64)
+    for b in range(cfg.bits):
+        want += (1 << b) * cb[(rows // 8) * 8 * cfg.bits + b * 8 + rows % 8]
+    assert np.array_equal(got, want)
+    if not cfg.one_scale:
+        s_dec, z_dec = E.decode_scales(buf, list(lay), cfg.Mout)
+        per_chunk = np.repeat(sc, cfg.group_size // int(lay[4]), axis=1) if cfg.group_size > int(lay[4]) else sc
+        assert np.array_equal(s_dec, per_chunk)
+        if cfg.zero_point:
+            assert np.array_equal(z_dec, z)
+
+
+def test_scales_fall_back_to_fp32_when_not_fp16_exact(oracle):
+    lib = tb.load()
+    cfg = T.Config(64, 256, 4).resolved()
+    w, sc, z, x = T.make_problem(cfg, seed=2)
+    sc = (sc * np.float32(1.0001)).astype(np.float32)  # no longer fp16-representable
+    A, S = T.pack_reference_layout(w, sc, z, cfg)
+    k = tb.make_kcfg(cfg.Mout, cfg.K, cfg.bits, cfg.bm, cfg.kfactor, cfg.group_size, cfg.act_group_size)
+    lay = (C.c_int * 12)()
+    n = lib.tmac_b200_debug_encode(C.byref(k), A.ctypes.data, S.ctypes.data, None, 0, lay)
+    assert n > 0 and lay[7] == 4
+    buf = np.zeros(n, np.uint8)
+    lib.tmac_b200_debug_encode(C.byref(k), A.ctypes.data, S.ctypes.data, buf.ctypes.data, n, lay)
+    s_dec, _ = E.decode_scales(buf, list(lay), cfg.Mout)
+    assert np.array_equal(s_dec, sc)
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback_without_gpu():
+    lib = tb.load()
+    assert lib.tmac_b200_init(-1) == -1
+    assert b"no CUDA device" in lib.tmac_b200_last_error() or b"cuda" in lib.tmac_b200_last_error().lower()
+    x = np.zeros((1, 128), np.float32)
+    ls = np.zeros(2, np.float32); lb = np.zeros(2, np.float32); q = np.zeros((32, 16), np.int8)
+    assert lib.tmac_b200_preprocessor(128, 1, 64, 0, x.ctypes.data, ls.ctypes.data, lb.ctypes.data, q.ctypes.data) == -1
