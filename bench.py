@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path's headline benchmark (contract: see the task statement).
+
+Metric (BASELINE.json): W2A16 GEMV achieved HBM GB/s on the Llama-2-7B layer shape
+out=11008, K=4096, batch=1, W2 g128 zero-point, act_group_size 64.
+
+A *step* is one pass of the hot path (preprocessor + qgemm_lut, both through the C ABI) over one
+batch of synthetic input: LAYERS distinct weight tensors of that shape (LAYERS x 12.7 MB = 407 MB,
+more than 3x the 126 MB L2, so every weight byte streams from HBM; that is the L2 policy: inputs
+larger than L2), each with its own activation row.  The step is captured once in a CUDA graph and
+replayed; time is CUDA events on the launching stream, max over ranks.
+
+  value     = algorithmic bytes of all ranks / step time, inputs resident in HBM          [GB/s]
+  roofline  = the dominant kernel (gemv_kernel) alone: algorithmic bytes per launch / its
+              average duration (graph of gemv launches only, same rotating buffers) vs the
+              measured HBM peak in MEASURED_PEAKS.json
+  e2e       = the same metric through the reference-facing call tmac_b200_gemv with HOST
+              activations/outputs (H2D + 2 kernels + D2H + sync per GEMV inside the timed region)
+  cpu_baseline = the reference's own AVX2 kernels (oracle/_ref, built from /root/reference) on the
+              box's host cores, bounded sample of the same workload
+  --impl reference : that CPU arm alone, same metric / config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "t-mac_b200"))
+
+METRIC = "w2a16_gemv_hbm_gbps"
+UNIT = "GB/s"
+MOUT, K, BITS, GS, AGS, ZP = 11008, 4096, 2, 128, 64, True
+LAYERS = 32
+
+
+def algorithmic_bytes(mout=MOUT, k=K, bits=BITS, gs=GS, zp=ZP, act_bytes=4, out_bytes=4, scale_bytes=2):
+    """SURVEY.md 8d / DESIGN.md: packed indices + scales(+zeros) + activations + outputs, each byte once."""
+    return mout * k * bits // 8 + mout * (k // gs) * scale_bytes * (2 if zp else 1) + k * act_bytes + mout * out_bytes
+
+
+def synth(seed, mout=MOUT, k=K, bits=BITS, gs=GS, zp=ZP, one_scale=False):
+    rng = np.random.default_rng(seed)
+    if one_scale:
+        w = (rng.integers(-1, 2, size=(mout, k)) + 2).astype(np.uint8)
+        return w, np.array([0.037], np.float16).astype(np.float32), None
+    w = rng.integers(0, 1 << bits, size=(mout, k), dtype=np.uint8)
+    sc = (np.abs(rng.standard_normal((mout, k // gs))) * 0.01 + 1e-4).astype(np.float16).astype(np.float32)
+    z = (rng.standard_normal((mout, k // gs)) * 0.01).astype(np.float16).astype(np.float32) if zp else None
+    return w, sc, z
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own kernels on the host cores (oracle/_ref), or the oracle port.
+# ------------------------------------------------------------------------------------------------
+def cpu_arm(budget_s, nbuf=4):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import tmac_oracle as T   # the one place bench.py executes oracle/: as the measured CPU baseline
+    ref = T.load_ref()
+    cfg = T.Config(MOUT, K, BITS, group_size=GS, act_group_size=AGS, zero_point=ZP).resolved()
+    cores = os.cpu_count() or 1
+    w, sc, z = synth(0)
+    A, S = T.pack_reference_layout(w, sc, z, cfg)
+    x = np.random.default_rng(1).standard_normal((1, K)).astype(np.float16).astype(np.float32)
+    if ref is not None:
+        kind, lib = "reference", ref
+        ref.set_threads(cores)
+        bufs = [(A.copy(), S.copy()) for _ in range(nbuf)]   # distinct buffers: weights stream from DRAM, not L2/L3
+        work = None
+
+        def one(i):
+            a, s = bufs[i % nbuf]
+            ref.gemv_mt(cfg, a, s, x)
+    else:
+        kind, lib, cores = "port", T.load_oracle(), 1
+
+        def one(i):
+            q, ls, lb = lib.preprocessor(x, AGS)
+            lib.qgemm(cfg, A, S, q, ls, lb)
+    for i in range(3):
+        one(i)
+    t0 = time.perf_counter(); n = 0
+    while True:
+        one(n); n += 1
+        el = time.perf_counter() - t0
+        if el > budget_s:
+            break
+    per = el / n
+    gbps = algorithmic_bytes() / per / 1e9
+    return {"value": gbps, "unit": UNIT, "cores": cores, "kind": kind, "ms_per_gemv": per * 1e3,
+            "sample": "%d GEMVs %dx%d W2 g128 zp over %d distinct weight buffers, preprocessor included, %.1f s" % (n, MOUT, K, nbuf, el)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step_budget = max(0.5, min(10.0, 60.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_arm(per_step_budget * 0.25)
+    vals = [cpu_arm(per_step_budget) for _ in range(max(1, args.steps))]
+    v = float(np.mean([r["value"] for r in vals]))
+    cb = dict(vals[-1]); cb["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": float(np.mean([r["ms_per_gemv"] for r in vals])) * LAYERS, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int8 LUT / fp32 accumulate", "data": "synthetic",
+            "config": workload_config(args.gpus), "cpu_baseline": cb,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(gpus):
+    return {"workload": "Llama-2-7B ffn up/gate shape W2A16 GEMV: out=%d K=%d batch=1, W2 g128 zero-point, act_group 64, "
+                        "%d distinct layers per step per GPU" % (MOUT, K, LAYERS),
+            "layers_per_step": LAYERS, "l2_policy": "inputs larger than L2 (%.0f MB of weights per step per GPU)" % (LAYERS * algorithmic_bytes() / 1e6),
+            "parallelism": "rows sharded: %d x %d rows, one NCCL all_gather of the step's outputs" % (gpus, MOUT) if gpus > 1 else "single GPU"}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-extras", action="store_true", help="skip tokens/s extras and the CPU baseline")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import tmac_b200 as tb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback in the product path)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = tb.load()
+    tb.check(lib.tmac_b200_init(local), "init")
+    stream = torch.cuda.Stream()
+    tb.check(lib.tmac_b200_set_stream(stream.cuda_stream), "set_stream")
+    launches = {"n": 0}
+
+    # ---- workload: LAYERS distinct resident tensors (one host encode, LAYERS-1 device clones) ----
+    w, sc, z = synth(100 + rank)
+    cfg = tb.make_kcfg(MOUT, K, BITS, 128, 16, GS, AGS, ZP, False)
+    base = tb.upload_plain(cfg, w, sc, z)
+    layers = [base] + [tb.clone(base) for _ in range(LAYERS - 1)]
+    nag = K // AGS
+    with torch.cuda.stream(stream):
+        x = torch.randn((LAYERS, K), device="cuda").half().float()
+        qlut = torch.zeros((LAYERS, K // 4, 16), dtype=torch.int8, device="cuda")
+        ls = torch.zeros((LAYERS, nag), device="cuda"); lb = torch.zeros_like(ls)
+        out = torch.zeros((LAYERS, MOUT), device="cuda")
+        gathered = torch.zeros((world, LAYERS, MOUT), device="cuda") if world > 1 else None
+
+    def step_calls(with_pre=True):
+        for i, wt in enumerate(layers):
+            if with_pre:
+                tb.preprocessor(K, 1, AGS, x[i], ls[i], lb[i], qlut[i])
+            tb.qgemm_lut(wt, 1, qlut[i], ls[i], lb[i], out[i])
+
+    def capture(with_pre):
+        step_calls(with_pre)                     # eager warm-up allocates every workspace
+        tb.check(lib.tmac_b200_sync(), "sync")
+        tb.check(lib.tmac_b200_graph_begin(), "graph_begin")
+        step_calls(with_pre)
+        g = lib.tmac_b200_graph_end()
+        tb.check(g, "graph_end")
+        return g
+
+    g_step = capture(True)
+    g_gemv = capture(False)
+    kernels_per_step = 2 * LAYERS
+
+    def run_steps(graph, n):
+        tb.check(lib.tmac_b200_graph_launch(graph, 1) if n == 1 else lib.tmac_b200_graph_launch(graph, n), "graph_launch")
+
+    def timed(graph, steps, collective):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                run_steps(graph, 1)
+                if collective and world > 1:
+                    dist.all_gather_into_tensor(gathered.view(-1), out.view(-1))
+            e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            dist.barrier()
+        return ms
+
+    with torch.cuda.stream(stream):
+        timed(g_step, max(3, args.warmup), True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ms = timed(g_step, args.steps, True)
+    launches["n"] = args.steps * kernels_per_step
+    # keep the GPU busy a little longer so that the 100 ms clock sampler sees load
+    t_end = time.time() + 1.0
+    while time.time() < t_end:
+        timed(g_step, args.steps, True)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms / args.steps
+    bytes_step = LAYERS * algorithmic_bytes()
+    value = world * bytes_step / (ms_per_step * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel: gemv launches only --------------------------------------
+    timed(g_gemv, 3, False)
+    ms_g = timed(g_gemv, args.steps, False)
+    t_gemv = ms_g / args.steps / LAYERS * 1e-3
+    peak, peak_src = measured_peak()
+    achieved = algorithmic_bytes() / t_gemv / 1e9
+    roofline = {"bound": "hbm", "kernel": "gemv_kernel<2,sym,8>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": peak_src, "us_per_launch": t_gemv * 1e6, "algorithmic_bytes_per_launch": algorithmic_bytes(), "traffic": None}
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            roofline["traffic"] = json.load(open(tp)).get("gemv_kernel_dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- e2e: host buffers through the reference-facing call -----------------------------------
+    hx = torch.randn((LAYERS, K)).half().float().pin_memory().numpy()
+    hout = torch.zeros((LAYERS, MOUT)).pin_memory().numpy()
+
+    def e2e_step():
+        for i, wt in enumerate(layers):
+            tb.gemv(wt, 1, hx[i], hout[i])
+
+    for _ in range(3):
+        e2e_step()
+    e2e_steps = max(3, min(args.steps, 20))
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t.item())
+    e2e = {"value": world * bytes_step / e2e_s / 1e9, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
+           "h2d_bytes_per_step": LAYERS * K * 4, "d2h_bytes_per_step": LAYERS * MOUT * 4,
+           "call": "tmac_b200_gemv(handle, 1, F32, host_x, host_out) per layer: H2D + preprocessor + qgemm_lut + D2H + sync"}
+    launches["n"] += 0
+
+    extras = {}
+    cpu = None
+    if rank == 0 and not args.no_extras:
+        try:
+            extras = tokens_per_second(tb, lib, torch, stream)
+        except Exception as ex:  # extras must never kill the headline line
+            extras = {"error": str(ex)[:200]}
+        if world == 1:
+            cpu = cpu_arm(12.0)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int8 LUT / int32 dp4a / fp32 scale", "data": "synthetic", "config": workload_config(world),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches["n"], "roofline": roofline,
+                "cpu_baseline": cpu, "tokens_per_s": extras}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def tokens_per_second(tb, lib, torch, stream):
+    """Matmul-only decode tokens/s (all quantised linears of every layer, preprocessors shared as in
+    the model graph: q/k/v share one, gate/up share one), synthetic weights at the real shapes."""
+    models = {
+        "llama2_7b_w2_g128_zp": dict(L=32, bits=2, zp=True, os=False, shapes=[("qkv", 4096, 4096, 3), ("o", 4096, 4096, 1), ("gateup", 11008, 4096, 2), ("down", 4096, 11008, 1)]),
+        "llama2_7b_w4_g128": dict(L=32, bits=4, zp=False, os=False, shapes=[("qkv", 4096, 4096, 3), ("o", 4096, 4096, 1), ("gateup", 11008, 4096, 2), ("down", 4096, 11008, 1)]),
+        "bitnet_3b_w2": dict(L=26, bits=2, zp=False, os=True, shapes=[("qkv", 3200, 3200, 3), ("o", 3200, 3200, 1), ("gateup", 8640, 3200, 2), ("down", 3200, 8640, 1)]),
+    }
+    res = {}
+    for name, m in models.items():
+        handles, plan, total_bytes = [], [], 0
+        for (tag, mout, k, cnt) in m["shapes"]:
+            w, sc, z = synth(7, mout, k, m["bits"], 128, m["zp"], m["os"])
+            bm = 256 if (mout * m["bits"]) % 256 == 0 else (128 if (mout * m["bits"]) % 128 == 0 else 320)
+            cfg = tb.make_kcfg(mout, k, m["bits"], bm, 16, 128, k if m["os"] else 64, m["zp"], m["os"])
+            base = tb.upload_plain(cfg, w, sc, z)
+            hs = [base] + [tb.clone(base) for _ in range(m["L"] * cnt - 1)]
+            handles += hs
+            ags = k if m["os"] else 64
+            with torch.cuda.stream(stream):
+                xb = torch.randn((1, k), device="cuda")
+                q = torch.zeros((1, k // 4, 16), dtype=torch.int8, device="cuda")
+                l1 = torch.zeros((1, k // ags), device="cuda"); l2 = torch.zeros_like(l1)
+                o = torch.zeros((cnt, mout), device="cuda")
+            plan.append((hs, cnt, k, ags, xb, q, l1, l2, o))
+            total_bytes += m["L"] * cnt * tb.load().tmac_b200_weights_nbytes(base.handle)
+
+        def token():
+            for layer in range(m["L"]):
+                for (hs, cnt, k, ags, xb, q, l1, l2, o) in plan:
+                    tb.preprocessor(k, 1, ags, xb, l1, l2, q)
+                    for c in range(cnt):
+                        tb.qgemm_lut(hs[layer * cnt + c], 1, q, l1, l2, o[c])
+        token()
+        tb.check(lib.tmac_b200_sync(), "sync")
+        tb.check(lib.tmac_b200_graph_begin(), "graph_begin")
+        token()
+        g = lib.tmac_b200_graph_end(); tb.check(g, "graph_end")
+        tb.check(lib.tmac_b200_graph_launch(g, 3), "warm"); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 20
+        e0.record(stream); tb.check(lib.tmac_b200_graph_launch(g, n), "run"); e1.record(stream)
+        torch.cuda.synchronize()
+        s = e0.elapsed_time(e1) / n * 1e-3
+        res[name] = {"tokens_per_s_matmul_only": 1.0 / s, "ms_per_token": s * 1e3, "resident_weight_GB": total_bytes / 1e9,
+                     "weight_stream_GBps": total_bytes / s / 1e9}
+        lib.tmac_b200_graph_free(g)
+        for h in handles:
+            h.free()
+    return res
+
+
+if __name__ == "__main__":
+    main()

@@ -64,6 +64,14 @@ TMAC_B200_API int tmac_b200_set_float_type(int dtype); /* TMAC_B200_F32 (default
  * other QLUT the general 16-entry path), 1 = always general, 2 = always symmetric. */
 TMAC_B200_API int tmac_b200_set_lut_mode(int mode);
 
+/* CUDA-graph helpers: capture the library calls issued between begin/end (device pointers only,
+ * after one eager warm-up of the same sequence) on the current stream and replay them. */
+TMAC_B200_API int tmac_b200_graph_begin(void);
+TMAC_B200_API int64_t tmac_b200_graph_end(void);
+TMAC_B200_API int tmac_b200_graph_launch(int64_t graph, int times);
+TMAC_B200_API int tmac_b200_graph_free(int64_t graph);
+TMAC_B200_API int tmac_b200_sync(void);
+
 /* ---- configuration (replaces kcfg.ini lookup, tmac_gemm_wrapper.h:230-255) -------------- */
 TMAC_B200_API int tmac_b200_register_kcfg(const tmac_b200_kcfg *cfg);
 /* Parses a reference kcfg.ini (sections qgemm_lut_t{T}_int8_m{M*bits}_k{K}_n{N}_b{bits}).
@@ -94,6 +102,9 @@ TMAC_B200_API int64_t tmac_b200_upload_plain(const tmac_b200_kcfg *cfg, const ui
 TMAC_B200_API int64_t tmac_b200_debug_encode(const tmac_b200_kcfg *cfg, const void *A, const void *scales,
                                              void *dst, size_t cap, int *layout_out);
 TMAC_B200_API int tmac_b200_free_weights(int64_t handle);
+/* A second resident copy in its own HBM allocation (distinct layers with tied shapes; benchmarks
+ * that must stream weights from HBM rather than L2). */
+TMAC_B200_API int64_t tmac_b200_clone_weights(int64_t handle);
 TMAC_B200_API size_t tmac_b200_weights_nbytes(int64_t handle); /* resident bytes in HBM */
 /* Row-shard view for multi-GPU: keep only rows [row0,row0+rows) resident. */
 TMAC_B200_API int64_t tmac_b200_upload_plain_rows(const tmac_b200_kcfg *cfg, const uint8_t *w,

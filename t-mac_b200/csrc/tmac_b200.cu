@@ -516,6 +516,66 @@ size_t tmac_b200_weights_nbytes(int64_t handle) {
     return it == g.res.end() ? 0 : it->second.L.total;
 }
 
+// Second resident copy of the same tensor in its own HBM allocation (benchmarks rotate through
+// distinct buffers so that weights stream from HBM, not L2; multi-layer models with tied shapes).
+int64_t tmac_b200_clone_weights(int64_t handle) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g.res.find(handle);
+    if (it == g.res.end()) return fail("clone: bad handle");
+    Resident R = it->second;
+    R.host_a = nullptr; R.host_a_bytes = 0;
+    if (cudaMalloc((void **)&R.d, R.L.total) != cudaSuccess) { cudaGetLastError(); return fail("out of device memory for clone"); }
+    if (cudaMemcpy(R.d, it->second.d, R.L.total, cudaMemcpyDeviceToDevice) != cudaSuccess) { cudaFree(R.d); return fail("clone copy failed"); }
+    const int64_t h = g.next_handle++;
+    g.res[h] = R;
+    return h;
+}
+
+// ---- CUDA-graph helpers: capture a sequence of library calls (device pointers only; run the
+// sequence once eagerly first so that every workspace is allocated) and replay it. -------------
+static std::map<int64_t, cudaGraphExec_t> g_graphs;
+static int64_t g_next_graph = 1;
+
+int tmac_b200_graph_begin(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    CUDA_OK(cudaStreamBeginCapture(g.stream(), cudaStreamCaptureModeThreadLocal));
+    return 0;
+}
+int64_t tmac_b200_graph_end(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    cudaGraph_t graph = nullptr;
+    CUDA_OK(cudaStreamEndCapture(g.stream(), &graph));
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    const int64_t h = g_next_graph++;
+    g_graphs[h] = exec;
+    return h;
+}
+int tmac_b200_graph_launch(int64_t graph, int times) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_graphs.find(graph);
+    if (it == g_graphs.end()) return fail("graph_launch: bad handle");
+    for (int i = 0; i < times; ++i) CUDA_OK(cudaGraphLaunch(it->second, g.stream()));
+    return 0;
+}
+int tmac_b200_graph_free(int64_t graph) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_graphs.find(graph);
+    if (it == g_graphs.end()) return fail("graph_free: bad handle");
+    cudaGraphExecDestroy(it->second);
+    g_graphs.erase(it);
+    return 0;
+}
+int tmac_b200_sync(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g.inited) return 0;
+    CUDA_OK(cudaStreamSynchronize(g.stream()));
+    return 0;
+}
+
 int tmac_b200_set_lut_mode(int mode) {
     std::lock_guard<std::mutex> lk(g_mu);
     g.lut_mode = mode;

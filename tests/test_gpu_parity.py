@@ -1,0 +1,259 @@
+"""GPU suite (-m gpu): parity of the sm_100a path against the oracle, through the C ABI.
+
+Gates:
+  G1 exact   : QLUT bytes, LUT_Scales, LUT_Biases (fp32 bit patterns)
+  G2 exact   : integer bit-plane sums (CBits) and the whole int32 (BitNet) path output
+  G3 fp path : max|dC| <= 1e-3 * max|C_ref| (north_star tolerance) -- we hold 2e-5 -- and NMSE <= 1e-8
+  G4 sanity  : NMSE <= 5e-4 vs dense dequant matmul (python/t_mac/ops/qgemm.py:277-282)
+No test here reads /root/reference."""
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import tmac_b200 as tb
+import tmac_oracle as T
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-3      # north_star: within 1e-3 relative for fp16 activations
+TIGHT_TOL = 2e-5    # what the kernel actually achieves (fp32 re-association only)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device; libtmac_b200 has no CPU fallback")
+    lib = tb.load()
+    tb.check(lib.tmac_b200_init(0), "init")
+    tb.check(lib.tmac_b200_set_stream(None), "set_stream")
+    return lib
+
+
+def kc(cfg):
+    return tb.make_kcfg(cfg.Mout, cfg.K, cfg.bits, cfg.bm, cfg.kfactor, cfg.group_size, cfg.act_group_size, cfg.zero_point, cfg.one_scale)
+
+
+def run_gpu(lib, cfg, A, S, x, N, device_ptrs=True, use_dispatch=False):
+    """preprocessor + qgemm through the C ABI; returns (qlut, ls, lb, C, cbits) as numpy."""
+    k = kc(cfg)
+    wt = tb.upload_reference_layout(k, A, S)
+    nag = cfg.K // cfg.act_group_size
+    try:
+        if device_ptrs:
+            dx = torch.from_numpy(x).cuda()
+            dq = torch.zeros((N, cfg.K // 4, 16), dtype=torch.int8, device="cuda")
+            dls = torch.zeros((N, nag), dtype=torch.float32, device="cuda")
+            dlb = torch.zeros_like(dls)
+            dC = torch.zeros((N, cfg.Mout), dtype=torch.float32, device="cuda")
+            dcb = torch.zeros((N, cfg.Mout * cfg.bits), dtype=torch.int32, device="cuda")
+            if use_dispatch:
+                tb.check(lib.tmac_b200_register_kcfg(C.byref(k)), "register")
+                tb.check(lib.preprocessor_int8(cfg.Mout * cfg.bits, cfg.K, N, cfg.bits, dx.data_ptr(), dls.data_ptr(), dlb.data_ptr(), dq.data_ptr()), "preprocessor_int8")
+                tb.check(lib.qgemm_lut_int8(cfg.Mout * cfg.bits, cfg.K, N, cfg.bits, A.ctypes.data, dq.data_ptr(), S.ctypes.data, dls.data_ptr(), dlb.data_ptr(), dC.data_ptr()), "qgemm_lut_int8")
+            else:
+                tb.preprocessor(cfg.K, N, cfg.act_group_size, dx, dls, dlb, dq)
+                tb.qgemm_lut(wt, N, dq, dls, dlb, dC)
+            tb.cbits(wt, N, dq, dcb)
+            torch.cuda.synchronize()
+            return dq.cpu().numpy(), dls.cpu().numpy(), dlb.cpu().numpy(), dC.cpu().numpy(), dcb.cpu().numpy()
+        q = np.zeros((N, cfg.K // 4, 16), np.int8); ls = np.zeros((N, nag), np.float32); lb = np.zeros_like(ls)
+        Cout = np.zeros((N, cfg.Mout), np.float32); cb = np.zeros((N, cfg.Mout * cfg.bits), np.int32)
+        tb.preprocessor(cfg.K, N, cfg.act_group_size, x, ls, lb, q)
+        tb.qgemm_lut(wt, N, q, ls, lb, Cout)
+        tb.cbits(wt, N, q, cb)
+        return q, ls, lb, Cout, cb
+    finally:
+        wt.free()
+
+
+def check_against_oracle(cfg, w, sc, z, x, A, S, got, oracle):
+    q, ls, lb, Cout, cb = got
+    qo, lso, lbo = oracle.preprocessor(x, cfg.act_group_size)
+    assert np.array_equal(q, qo), "G1: QLUT bytes differ"
+    assert np.array_equal(ls.view(np.uint32), lso.view(np.uint32)), "G1: LUT_Scales differ"
+    assert np.array_equal(lb.view(np.uint32), lbo.view(np.uint32)), "G1: LUT_Biases differ"
+    assert np.array_equal(cb, oracle.cbits(cfg, A, qo)), "G2: integer plane sums differ"
+    Co = oracle.qgemm(cfg, A, S, qo, lso, lbo)
+    if cfg.one_scale and cfg.act_group_size == cfg.K:
+        assert np.array_equal(Cout.view(np.uint32), Co.view(np.uint32)), "G2/G3: int32 path must be bit exact"
+    else:
+        err = np.abs(Cout - Co).max() / max(np.abs(Co).max(), 1e-30)
+        assert err <= REL_TOL, "G3: rel err %g" % err
+        assert err <= TIGHT_TOL, "G3 (tight): rel err %g" % err
+        assert T.nmse(Co, Cout) <= 1e-8
+    assert T.nmse(T.dense_reference(w, sc, z, x, cfg), Cout) <= 5e-4, "G4"
+
+
+GOLDEN = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "w*.npz")))
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_golden_fixtures(lib, oracle, golden_dir, name):
+    """CUDA path vs outputs of the reference's own kernels (committed fixtures)."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    Mout, K, bits, bm, kf, gs, ags, zp, os_ = [int(v) for v in g["cfg"]]
+    cfg = T.Config(Mout, K, bits, bm, kf, gs, ags, bool(zp), bool(os_))
+    x = g["x"]; N = x.shape[0]
+    q, ls, lb, Cout, cb = run_gpu(lib, cfg, np.ascontiguousarray(g["A"]), np.ascontiguousarray(g["S"]), x, N)
+    assert np.array_equal(q, g["qlut"])
+    assert np.array_equal(ls.view(np.uint32), g["lut_scales"].view(np.uint32))
+    assert np.array_equal(lb.view(np.uint32), g["lut_biases"].view(np.uint32))
+    assert np.array_equal(cb, g["cbits"])
+    if os_:
+        assert np.array_equal(Cout.view(np.uint32), g["C"].view(np.uint32))
+    else:
+        assert np.abs(Cout - g["C"]).max() <= TIGHT_TOL * np.abs(g["C"]).max()
+
+
+SHAPES = [
+    # (Config, N)   Llama-2-7B / BitNet-3B / Qwen2-7B layer shapes at reduced row counts + odd cases
+    (T.Config(1024, 4096, 2, zero_point=True), 1),
+    (T.Config(512, 4096, 4), 1),
+    (T.Config(512, 4096, 4, zero_point=True), 2),
+    (T.Config(768, 11008, 2, zero_point=True), 1),
+    (T.Config(384, 1024, 3, zero_point=True), 1),
+    (T.Config(512, 2048, 1), 1),
+    (T.Config(640, 3200, 2, one_scale=True), 1),
+    (T.Config(1280, 8640, 2, one_scale=True), 2),
+    (T.Config(512, 3584, 4), 1),
+    (T.Config(256, 1024, 4, kfactor=8, group_size=32, act_group_size=32), 1),
+    (T.Config(320, 1024, 2, bm=320, group_size=64, act_group_size=64, zero_point=True), 1),
+    (T.Config(192, 512, 2, bm=128, zero_point=True), 1),  # 192 rows = 1.5 super-blocks: ragged last super-block
+]
+
+
+@pytest.mark.parametrize("cfg,N", SHAPES, ids=lambda v: ("w%d_%dx%d" % (v.bits, v.Mout, v.K)) if isinstance(v, T.Config) else "n%d" % v)
+def test_parity_device_pointers(lib, oracle, cfg, N):
+    cfg = cfg.resolved()
+    w, sc, z, x = T.make_problem(cfg, seed=0, N=N)
+    A, S = T.pack_reference_layout(w, sc, z, cfg)
+    check_against_oracle(cfg, w, sc, z, x, A, S, run_gpu(lib, cfg, A, S, x, N), oracle)
+
+
+@pytest.mark.parametrize("cfg", [T.Config(512, 2048, 2, zero_point=True), T.Config(256, 1024, 4), T.Config(640, 3200, 2, one_scale=True)],
+                         ids=["w2zp", "w4", "bitnet"])
+def test_parity_host_pointers_and_dispatchers(lib, oracle, cfg):
+    """The reference's call shape: host buffers, qgemm_lut_int8 / preprocessor_int8 names."""
+    cfg = cfg.resolved()
+    w, sc, z, x = T.make_problem(cfg, seed=3, N=1)
+    A, S = T.pack_reference_layout(w, sc, z, cfg)
+    check_against_oracle(cfg, w, sc, z, x, A, S, run_gpu(lib, cfg, A, S, x, 1, device_ptrs=False), oracle)
+    check_against_oracle(cfg, w, sc, z, x, A, S, run_gpu(lib, cfg, A, S, x, 1, device_ptrs=True, use_dispatch=True), oracle)
+
+
+@pytest.mark.parametrize("bits", [1, 2, 3, 4])
+def test_general_lut_matches_oracle(lib, oracle, bits):
+    """Random, NON-symmetric LUT as in the reference's own verification (python/t_mac/ops/qgemm.py:289):
+    exercises the 16-entry lookup path."""
+    cfg = T.Config(384 if bits == 3 else 512, 1024, bits, zero_point=(bits % 2 == 0)).resolved()
+    w, sc, z, x = T.make_problem(cfg, seed=5)
+    A, S = T.pack_reference_layout(w, sc, z, cfg)
+    rng = np.random.default_rng(9)
+    nag = cfg.K // cfg.act_group_size
+    q = rng.integers(-127, 128, size=(1, cfg.K // 4, 16)).astype(np.int8)
+    ls = np.abs(rng.standard_normal((1, nag))).astype(np.float32); lb = rng.standard_normal((1, nag)).astype(np.float32)
+    wt = tb.upload_reference_layout(kc(cfg), A, S)
+    try:
+        for dev in (False, True):
+            Cout = np.zeros((1, cfg.Mout), np.float32)
+            if dev:
+                dq, dls, dlb = torch.from_numpy(q).cuda(), torch.from_numpy(ls).cuda(), torch.from_numpy(lb).cuda()
+                dC = torch.zeros((1, cfg.Mout), dtype=torch.float32, device="cuda")
+                tb.qgemm_lut(wt, 1, dq, dls, dlb, dC)
+                Cout = dC.cpu().numpy()
+            else:
+                tb.qgemm_lut(wt, 1, q, ls, lb, Cout)
+            Co = oracle.qgemm(cfg, A, S, q, ls, lb)
+            assert np.abs(Cout - Co).max() <= TIGHT_TOL * np.abs(Co).max()
+    finally:
+        wt.free()
+
+
+def test_tile_calls_like_ggml(lib, oracle):
+    """ggml's per-tile calls (ggml.c:12662-12691): src0 + w_offset, dst + dst_offset, n = chunk_size0."""
+    cfg = T.Config(1024, 2048, 2, bm=128, zero_point=True).resolved()
+    w, sc, z, x = T.make_problem(cfg, seed=7)
+    A, S = T.pack_reference_layout(w, sc, z, cfg)
+    k = kc(cfg)
+    tb.check(lib.tmac_b200_register_kcfg(C.byref(k)), "register")
+    wt = tb.upload_reference_layout(k, A, S)
+    try:
+        nag = cfg.K // cfg.act_group_size
+        q = np.zeros((1, cfg.K // 4, 16), np.int8); ls = np.zeros((1, nag), np.float32); lb = np.zeros_like(ls)
+        lib.ggml_tmac_mul_mat_task_init(x.ctypes.data, q.ctypes.data, ls.ctypes.data, lb.ctypes.data, cfg.Mout, cfg.K, 1, cfg.bits)
+        out = np.zeros((1, cfg.Mout), np.float32)
+        n_tile = cfg.n_tile_num; chunk0 = cfg.Mout // n_tile
+        w_chunk = A.size // n_tile; s_chunk = S.size // n_tile
+        for t in range(n_tile):
+            lib.ggml_tmac_mul_mat_task_compute(A.ctypes.data + t * w_chunk, S.ctypes.data + 4 * t * s_chunk, q.ctypes.data, ls.ctypes.data,
+                                               lb.ctypes.data, out.ctypes.data + 4 * t * chunk0, chunk0, cfg.K, 1, cfg.bits)
+        qo, lso, lbo = oracle.preprocessor(x, cfg.act_group_size)
+        Co = oracle.qgemm(cfg, A, S, qo, lso, lbo)
+        assert np.array_equal(q, qo)
+        assert np.abs(out - Co).max() <= TIGHT_TOL * np.abs(Co).max()
+    finally:
+        wt.free()
+
+
+def test_fused_gemv_fp16_and_plain_upload(lib, oracle):
+    """tmac_b200_gemv (init+compute in one call) with fp16 activations/outputs (the ARM `T`), weights
+    uploaded from un-permuted quantised values."""
+    cfg = T.Config(512, 2048, 4, zero_point=True).resolved()
+    w, sc, z, x = T.make_problem(cfg, seed=4)
+    A, S = T.pack_reference_layout(w, sc, z, cfg)
+    wt = tb.upload_plain(kc(cfg), w, sc, z)
+    try:
+        dx = torch.from_numpy(x).cuda().half()
+        dC = torch.zeros((1, cfg.Mout), dtype=torch.float16, device="cuda")
+        tb.gemv(wt, 1, dx, dC, dtype=tb.F16)
+        qo, lso, lbo = oracle.preprocessor(x, cfg.act_group_size)   # x is fp16-representable
+        Co = oracle.qgemm(cfg, A, S, qo, lso, lbo)
+        got = dC.float().cpu().numpy()
+        assert np.abs(got - Co).max() <= REL_TOL * np.abs(Co).max()   # fp16 output rounding ~ 5e-4
+        hC = np.zeros((1, cfg.Mout), np.float32)
+        tb.gemv(wt, 1, x, hC)                                        # host buffers end to end
+        assert np.abs(hC - Co).max() <= TIGHT_TOL * np.abs(Co).max()
+    finally:
+        wt.free()
+
+
+def test_full_size_properties(lib, oracle):
+    """BASELINE.json full size (W2 g128 zp, 11008 x 4096): size-independent properties + a row sample
+    against the oracle.  (a) determinism, (b) linearity in the weight scales: doubling every
+    scale and zero doubles C exactly (power-of-two scaling commutes with every rounding),
+    (c) 256 sampled rows vs the oracle."""
+    cfg = T.Config(11008, 4096, 2, zero_point=True).resolved()
+    w, sc, z, x = T.make_problem(cfg, seed=1)
+    k = kc(cfg)
+    wt = tb.upload_plain(k, w, sc, z)
+    wt2 = tb.upload_plain(k, w, (2 * sc).astype(np.float32), (2 * z).astype(np.float32))
+    try:
+        dx = torch.from_numpy(x).cuda()
+        c1 = torch.zeros((1, cfg.Mout), dtype=torch.float32, device="cuda"); c2 = torch.zeros_like(c1); c3 = torch.zeros_like(c1)
+        tb.gemv(wt, 1, dx, c1); tb.gemv(wt, 1, dx, c2); tb.gemv(wt2, 1, dx, c3)
+        torch.cuda.synchronize()
+        assert torch.equal(c1, c2)
+        assert torch.equal(2 * c1, c3)
+        rows = np.sort(np.random.default_rng(0).choice(cfg.Mout // 128, 2, replace=False))  # two 128-row tiles
+        sub = np.concatenate([np.arange(r * 128, (r + 1) * 128) for r in rows])
+        cfg_s = T.Config(len(sub), cfg.K, 2, zero_point=True).resolved()
+        As, Ss = T.pack_reference_layout(w[sub], sc[sub], z[sub], cfg_s)
+        qo, lso, lbo = oracle.preprocessor(x, 64)
+        Co = oracle.qgemm(cfg_s, As, Ss, qo, lso, lbo)
+        got = c1.cpu().numpy()[:, sub]
+        assert np.abs(got - Co).max() <= TIGHT_TOL * np.abs(Co).max()
+    finally:
+        wt.free(); wt2.free()
+
+
+def test_errors_follow_reference_convention(lib):
+    """0 / -1 return codes (kernels.h:27,37), no exceptions across the C ABI."""
+    x = torch.zeros((1, 96), device="cuda")
+    assert lib.tmac_b200_preprocessor(96, 1, 64, 0, x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr()) == -1
+    assert lib.qgemm_lut_int8(256, 4096, 1, 2, x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr()) == -1
+    assert b"not a registered" in lib.tmac_b200_last_error()
+    assert lib.tmac_b200_qgemm_lut(123456, 0, 1, 1, 0, x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr()) == -1
