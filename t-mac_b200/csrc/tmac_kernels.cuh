@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_kernel(const GemvParams p, 
     constexpr int RW = 8 / PB;
     constexpr int RSB = 32 * RW;
     constexpr int TW = SYM ? 2 : 4;               // 32-bit words per group table
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
 
     const int rsb = blockIdx.x, ks = blockIdx.y, n = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -359,6 +359,308 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_kernel(const GemvParams p, 
     else reinterpret_cast<float *>(p.C)[o] = out;
 }
 
+// ==========================================================================================
+// gemv2_kernel -- the production GEMV: persistent CTAs over contiguous block ranges, weights
+// streamed HBM -> shared memory by TMA bulk copies (cp.async.bulk + mbarrier complete_tx), LUT
+// slice copied the same way, programmatic dependent launch (PDL) so that the weight stream of
+// launch i+1 overlaps the tail of launch i.
+//
+//   blocks   : the (row super-block, K chunk) blocks of the stream layout in memory order,
+//              NB = nrsb * nchunk of them; CTA i owns the contiguous range [NB*i/G, NB*(i+1)/G)
+//              (equal bytes per SM, +-1 block).
+//   producer : warp NW.  Before griddepcontrol.wait it arms the stage barriers and issues the
+//              bulk copies of this CTA's weight range (weights are static data, so this may
+//              overlap the previous kernel in the stream); after the wait it copies the LUT.
+//   consumers: warps 0..NW-1, block b of the range goes to warp (b - b0) % NW.  Lane l owns RW rows
+//              of the super-block (no cross-lane reduction).  Accumulators are flushed to a
+//              per-CTA buffer when the warp moves to another super-block.
+//   epilogue : fixed-order sum over warps; a super-block whose K range is split between CTAs goes
+//              through a global scratch slot + arrival counter, the last CTA summing the slots in
+//              CTA order (deterministic, bit-reproducible run to run).
+// ==========================================================================================
+struct Gemv2Params {
+    const unsigned char *W;        // first block of the launch's first row super-block
+    const int8_t *qlut;            // [N][K/4][16]
+    const float *lut_scales, *lut_biases;  // [N][K/ags]
+    void *C;                       // [N][ldc]
+    float *partial;                // [N][nrsb][maxc][RSB]
+    int *counters;                 // [N][nrsb]
+    int K, ldc, row_begin, row_end, c_row0, bits;
+    int nrsb, rsb0, nchunk, nblocks;
+    int ags, agq_shift, ck;        // act group size, log2(quads per act group), K per chunk
+    int zp, one_scale, int_path, sd, out_f16;
+    int blk_bytes;                 // bytes per block (weights + scales)
+    int nslots;                    // stage ring slots (>= 1)
+    int maxc;                      // scratch slots per super-block
+    int max_rsb_cta;               // super-blocks a CTA range can touch
+    int lut_bytes;                 // K*4 (multiple of 16)
+    float scale0;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Quad lookups with the raw QLUT rows in shared memory (16 B per group, no re-ordering):
+// symmetric mode reads entries 0..7; general mode also reads 8..15 and reverses the selector
+// (code (neg=1, j) <-> LUT index 15 - j  =>  byte (7 - j) of the upper half).
+template <int PB, bool SYM> struct QuadRaw {
+    static __device__ __forceinline__ void run(const uint4 w, const uint4 *lut4 /* 4 groups */, int *acc, uint32_t wtx, uint32_t wty) {
+        if (SYM) {
+            uint32_t t[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint2 v = *reinterpret_cast<const uint2 *>(lut4 + k);
+                t[2 * k] = v.x; t[2 * k + 1] = v.y;
+            }
+            Quad<PB, true>::run(w, t, acc, wtx, wty);
+        } else {
+            uint32_t t[16];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint4 v = lut4[k];
+                t[4 * k] = v.x; t[4 * k + 1] = v.y;
+                t[4 * k + 2] = __byte_perm(v.w, 0, 0x0123); t[4 * k + 3] = __byte_perm(v.z, 0, 0x0123);
+            }
+            Quad<PB, false>::run(w, t, acc, wtx, wty);
+        }
+    }
+};
+
+constexpr int kG2Warps = 8;                       // consumer warps
+constexpr int kG2Threads = (kG2Warps + 1) * 32;   // + 1 producer warp
+
+template <int PB, bool SYM, int QCH>
+__global__ void __launch_bounds__(kG2Threads) gemv2_kernel(const Gemv2Params p, const uint32_t wtx, const uint32_t wty) {
+    constexpr int RW = 8 / PB;
+    constexpr int RSB = 32 * RW;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, cta = blockIdx.x, n = blockIdx.y;
+    const int b0 = (int)((long long)p.nblocks * cta / G), b1 = (int)((long long)p.nblocks * (cta + 1) / G);
+    const int nb = b1 - b0;
+    const int S = p.nslots;
+    const int rsb_first = b0 / p.nchunk;
+
+    // ---- shared memory carve-up (host computes the same sizes) ----
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem);          // [S]
+    uint64_t *empty = full + S;                                   // [S]
+    uint64_t *lut_bar = empty + S;                                // [1]
+    unsigned char *stage = smem + (((size_t)(2 * S + 1) * 8 + 127) & ~(size_t)127);   // [S][blk_bytes]
+    uint4 *lut_s = reinterpret_cast<uint4 *>(stage + (size_t)S * p.blk_bytes);        // [K/4] raw QLUT rows
+    float *ls_s = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(lut_s) + p.lut_bytes);   // [nag]
+    float *lb_s = ls_s + p.K / p.ags;                                                  // [nag]
+    float *red = lb_s + p.K / p.ags;                                                   // [max_rsb_cta][NW][RSB]
+    __shared__ int s_flag;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(lut_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < p.max_rsb_cta * kG2Warps * RSB; i += kG2Threads) red[i] = 0.f;
+    __syncthreads();
+    pdl_launch_dependents();    // let the next kernel in the stream start its own weight prefetch
+
+    const int nag = p.K / p.ags;
+    if (warp == kG2Warps) {
+        // ================= producer warp =================
+        if (lane == 0 && nb > 0) {
+            const uint64_t pol_w = policy_evict_first(), pol_l = policy_evict_last();
+            const unsigned char *src = p.W + (size_t)b0 * p.blk_bytes;
+            const int first = nb < S ? nb : S;
+            for (int i = 0; i < first; ++i) {                 // static weights: may run ahead of the dependency
+                mbar_expect_tx(full + i, (uint32_t)p.blk_bytes);
+                bulk_g2s(stage + (size_t)i * p.blk_bytes, src + (size_t)i * p.blk_bytes, (uint32_t)p.blk_bytes, full + i, pol_w);
+            }
+            pdl_wait();                                       // LUT / scales come from the previous kernel
+            mbar_expect_tx(lut_bar, (uint32_t)p.lut_bytes);
+            bulk_g2s(lut_s, p.qlut + (size_t)n * p.K * 4, (uint32_t)p.lut_bytes, lut_bar, pol_l);
+            for (int i = S; i < nb; ++i) {                    // ring reuse (ranges larger than the ring)
+                const int s = i % S;
+                mbar_wait(empty + s, (uint32_t)(((i / S) - 1) & 1));
+                mbar_expect_tx(full + s, (uint32_t)p.blk_bytes);
+                bulk_g2s(stage + (size_t)s * p.blk_bytes, src + (size_t)i * p.blk_bytes, (uint32_t)p.blk_bytes, full + s, pol_w);
+            }
+        }
+    } else {
+        // ================= consumer warps =================
+        pdl_wait();
+        {   // LUT scales / biases of this activation row -> shared (consumer threads only)
+            const float *lsg = p.lut_scales + (size_t)n * nag, *lbg = p.lut_biases + (size_t)n * nag;
+            for (int a = tid; a < nag; a += kG2Warps * 32) { ls_s[a] = __ldg(lsg + a); lb_s[a] = __ldg(lbg + a); }
+            asm volatile("bar.sync 1, %0;" ::"n"(kG2Warps * 32) : "memory");
+        }
+        float cacc[RW];
+        int iacc[RW];
+#pragma unroll
+        for (int i = 0; i < RW; ++i) { cacc[i] = 0.f; iacc[i] = 0; }
+        int cur_rsb = -1;
+        bool lut_ready = false;
+        // first block of this warp: b0 + warp
+        int bi = warp;
+        int rsb = 0, c = 0;
+        if (bi < nb) { const int b = b0 + bi; rsb = b / p.nchunk; c = b - rsb * p.nchunk; }
+        const int agq = 1 << p.agq_shift;
+        for (; bi < nb; bi += kG2Warps) {
+            if (rsb != cur_rsb) {
+                if (cur_rsb >= 0) {
+                    float *r = red + ((size_t)(cur_rsb - rsb_first) * kG2Warps + warp) * RSB + lane * RW;
+#pragma unroll
+                    for (int i = 0; i < RW; ++i) { r[i] = p.int_path ? __int_as_float(iacc[i]) : cacc[i]; cacc[i] = 0.f; iacc[i] = 0; }
+                }
+                cur_rsb = rsb;
+            }
+            const int slot = bi % S;
+            mbar_wait(full + slot, (uint32_t)((bi / S) & 1));
+            const unsigned char *blk = stage + (size_t)slot * p.blk_bytes;
+            const uint4 *wp = reinterpret_cast<const uint4 *>(blk) + lane;
+            uint4 wv[QCH];
+#pragma unroll
+            for (int q = 0; q < QCH; ++q) wv[q] = wp[q * 32];
+            float sc[RW], zr[RW];
+            if (!p.one_scale) {
+                const unsigned char *sp = blk + (size_t)QCH * 512;
+#pragma unroll
+                for (int i = 0; i < RW; ++i) {
+                    sc[i] = load_scale(sp, p.sd, lane * RW + i);
+                    zr[i] = p.zp ? load_scale(sp + (size_t)RSB * p.sd, p.sd, lane * RW + i) : 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < RW; ++i) { sc[i] = p.scale0; zr[i] = 0.f; }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + slot);          // stage bytes are in registers now
+            if (!lut_ready) { mbar_wait(lut_bar, 0); lut_ready = true; }
+            const uint4 *lq = lut_s + (size_t)c * QCH * 4;
+            float facc[RW];
+#pragma unroll
+            for (int i = 0; i < RW; ++i) facc[i] = 0.f;
+            float lbsum = 0.f;
+#pragma unroll
+            for (int q = 0; q < QCH; ++q) {
+                QuadRaw<PB, SYM>::run(wv[q], lq + q * 4, iacc, wtx, wty);
+                if (!p.int_path && (((q + 1) & (agq - 1)) == 0 || q == QCH - 1)) {
+                    const int ag = (c * QCH + q) >> p.agq_shift;
+                    const float lsv = ls_s[ag];
+                    lbsum += lb_s[ag];
+#pragma unroll
+                    for (int i = 0; i < RW; ++i) { facc[i] = fmaf(lsv, (float)iacc[i], facc[i]); iacc[i] = 0; }
+                }
+            }
+            if (!p.int_path) {
+#pragma unroll
+                for (int i = 0; i < RW; ++i) {
+                    float v = fmaf(0.5f * sc[i], facc[i] + lbsum, cacc[i]);
+                    if (p.zp) v = fmaf(zr[i], lbsum, v);
+                    cacc[i] = v;
+                }
+            }
+            c += kG2Warps;
+            while (c >= p.nchunk) { c -= p.nchunk; ++rsb; }
+        }
+        if (cur_rsb >= 0) {
+            float *r = red + ((size_t)(cur_rsb - rsb_first) * kG2Warps + warp) * RSB + lane * RW;
+#pragma unroll
+            for (int i = 0; i < RW; ++i) r[i] = p.int_path ? __int_as_float(iacc[i]) : cacc[i];
+        }
+    }
+    __syncthreads();
+    if (nb <= 0) return;
+
+    // ---- epilogue: one super-block at a time ------------------------------------------------
+    const int rsb_last = (b1 - 1) / p.nchunk;
+    const int padded_rows = p.nrsb * RSB;
+    for (int r = rsb_first; r <= rsb_last; ++r) {
+        float fsum = 0.f; int isum = 0;
+        if (tid < RSB) {
+#pragma unroll
+            for (int w = 0; w < kG2Warps; ++w) {
+                const float v = red[((size_t)(r - rsb_first) * kG2Warps + w) * RSB + tid];
+                if (p.int_path) isum += __float_as_int(v); else fsum += v;
+            }
+        }
+        const int rb0 = r * p.nchunk, rb1 = rb0 + p.nchunk;     // block range of super-block r
+        const bool whole = (rb0 >= b0 && rb1 <= b1);
+        if (!whole) {
+            const int cfirst = (int)(((long long)(rb0 + 1) * G + p.nblocks - 1) / p.nblocks) - 1;
+            const int clast = (int)(((long long)rb1 * G + p.nblocks - 1) / p.nblocks) - 1;
+            const int nctr = clast - cfirst + 1;
+            float *slots = p.partial + (((size_t)n * p.nrsb + r) * p.maxc) * RSB;
+            if (tid < RSB) slots[(size_t)(cta - cfirst) * RSB + tid] = p.int_path ? __int_as_float(isum) : fsum;
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                const int t = atomicAdd(p.counters + (size_t)n * p.nrsb + r, 1);
+                s_flag = (t == nctr - 1);
+                if (s_flag) p.counters[(size_t)n * p.nrsb + r] = 0;
+            }
+            __syncthreads();
+            const bool last = s_flag != 0;
+            __syncthreads();
+            if (!last) continue;
+            __threadfence();
+            fsum = 0.f; isum = 0;
+            if (tid < RSB)
+                for (int k2 = 0; k2 < nctr; ++k2) {
+                    const float v = __ldcg(slots + (size_t)k2 * RSB + tid);
+                    if (p.int_path) isum += __float_as_int(v); else fsum += v;
+                }
+        }
+        const int row = (p.rsb0 + r) * RSB + tid;
+        if (tid < RSB && row >= p.row_begin && row < p.row_end) {
+            float out;
+            if (p.int_path) {
+                const float cb = __fmul_rn((float)isum, 0.5f);
+                const float t1 = __fmul_rn(cb, ls_s[0]);
+                const float t2 = __fmul_rn(lb_s[0], 0.5f);
+                out = __fmul_rn(__fadd_rn(t1, t2), p.scale0);
+            } else
+                out = fsum;
+            const size_t o = (size_t)n * p.ldc + (size_t)(row - p.c_row0);
+            if (p.out_f16) reinterpret_cast<__half *>(p.C)[o] = __float2half_rn(out);
+            else reinterpret_cast<float *>(p.C)[o] = out;
+        }
+        (void)padded_rows;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // cbits_kernel (debug / parity gate G2): per-plane int32 sums in the reference plane layout.
 // One thread per (row, plane); straightforward lookups in the full 16-entry table, decoding the
@@ -417,7 +719,7 @@ template <> __device__ __forceinline__ float ld_act<__half>(const __half *p, siz
 template <typename TIn>
 __global__ void __launch_bounds__(kPreThreads) preprocessor_kernel(const TIn *B, float *lut_scales, float *lut_biases,
                                                                     int8_t *qlut, int K, int ags, int agb) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     const int n = blockIdx.y;
     const int nag = K / ags;
     const int a_begin = blockIdx.x * agb;
