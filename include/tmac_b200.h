@@ -71,6 +71,8 @@ TMAC_B200_API int64_t tmac_b200_graph_end(void);
 TMAC_B200_API int tmac_b200_graph_launch(int64_t graph, int times);
 TMAC_B200_API int tmac_b200_graph_free(int64_t graph);
 TMAC_B200_API int tmac_b200_sync(void);
+/* Debug (TMAC_B200_TRACE=1): per-CTA clock64 stamps [ctas][8] of the last qgemm_lut launch. */
+TMAC_B200_API int tmac_b200_debug_trace(long long *dst, int cap_ctas);
 
 /* ---- configuration (replaces kcfg.ini lookup, tmac_gemm_wrapper.h:230-255) -------------- */
 TMAC_B200_API int tmac_b200_register_kcfg(const tmac_b200_kcfg *cfg);

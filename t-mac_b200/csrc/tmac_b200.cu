@@ -88,7 +88,8 @@ struct Context {
     std::vector<tmac_b200_kcfg> kcfgs;
     std::set<const void *> sym_qluts;    // device QLUT buffers last written by our preprocessor
     // workspaces
-    DevBuf d_b, d_qlut, d_ls, d_lb, d_c, d_part, d_cnt, d_cbits;
+    DevBuf d_b, d_qlut, d_ls, d_lb, d_c, d_part, d_cnt, d_cbits, d_trace;
+    int trace = 0, trace_ctas = 0;
     PinBuf h_in, h_out;
     cudaEvent_t stage_ev = nullptr;      // last H2D that read h_in
     bool stage_pending = false;
@@ -126,6 +127,7 @@ int ensure_init() {
     if (const char *e = getenv("TMAC_B200_CTAS_PER_SM")) g.ctas_per_sm = atoi(e);
     if (const char *e = getenv("TMAC_B200_SMEM_BUDGET")) g.smem_budget = atoi(e);
     if (const char *e = getenv("TMAC_B200_PDL")) g.use_pdl = atoi(e);
+    if (const char *e = getenv("TMAC_B200_TRACE")) g.trace = atoi(e);
     g.inited = true;
     return 0;
 }
@@ -213,6 +215,11 @@ int launch_gemv2(const Resident &R, int row_begin, int row_end, int N, const int
     }
     p.partial = (float *)g.d_part.p;
     p.counters = (int *)g.d_cnt.p;
+    if (g.trace) {
+        if (g.d_trace.ensure((size_t)G * 8 * sizeof(long long))) return fail("out of device memory (trace)");
+        p.trace = (long long *)g.d_trace.p;
+        g.trace_ctas = G;
+    }
     gemv2_fn fn = pick_gemv2(L.pb, sym, L.qch);
     if (!fn) return fail("qgemm_lut: unsupported chunking (qch=" + std::to_string(L.qch) + ")");
     if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -658,6 +665,16 @@ int tmac_b200_sync(void) {
     if (!g.inited) return 0;
     CUDA_OK(cudaStreamSynchronize(g.stream()));
     return 0;
+}
+
+// Debug: per-CTA clock64 stamps of the last gemv2 launch ([ctas][8]); returns #ctas or -1.
+int tmac_b200_debug_trace(long long *dst, int cap_ctas) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g.trace || !g.d_trace.p) return fail("trace disabled (TMAC_B200_TRACE=1)");
+    CUDA_OK(cudaStreamSynchronize(g.stream()));
+    const int n = std::min(cap_ctas, g.trace_ctas);
+    CUDA_OK(cudaMemcpy(dst, g.d_trace.p, (size_t)n * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return n;
 }
 
 int tmac_b200_set_lut_mode(int mode) {

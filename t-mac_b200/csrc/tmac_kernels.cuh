@@ -395,7 +395,9 @@ struct Gemv2Params {
     int max_rsb_cta;               // super-blocks a CTA range can touch
     int lut_bytes;                 // K*4 (multiple of 16)
     float scale0;
+    long long *trace;              // optional [gridDim.x][8] clock64 stamps (debug), else null
 };
+#define TMAC_TRACE(slot) do { if (p.trace) p.trace[(size_t)blockIdx.x * 8 + (slot)] = clock64(); } while (0)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -488,6 +490,7 @@ __global__ void __launch_bounds__(kG2Threads) gemv2_kernel(const Gemv2Params p, 
     float *red = lb_s + p.K / p.ags;                                                   // [max_rsb_cta][NW][RSB]
     __shared__ int s_flag;
 
+    if (tid == 0) TMAC_TRACE(0);
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         mbar_init(lut_bar, 1);
@@ -496,6 +499,7 @@ __global__ void __launch_bounds__(kG2Threads) gemv2_kernel(const Gemv2Params p, 
     for (int i = tid; i < p.max_rsb_cta * kG2Warps * RSB; i += kG2Threads) red[i] = 0.f;
     __syncthreads();
     pdl_launch_dependents();    // let the next kernel in the stream start its own weight prefetch
+    if (tid == 0) TMAC_TRACE(1);
 
     const int nag = p.K / p.ags;
     if (warp == kG2Warps) {
@@ -508,6 +512,7 @@ __global__ void __launch_bounds__(kG2Threads) gemv2_kernel(const Gemv2Params p, 
                 mbar_expect_tx(full + i, (uint32_t)p.blk_bytes);
                 bulk_g2s(stage + (size_t)i * p.blk_bytes, src + (size_t)i * p.blk_bytes, (uint32_t)p.blk_bytes, full + i, pol_w);
             }
+            TMAC_TRACE(2);
             pdl_wait();                                       // LUT / scales come from the previous kernel
             mbar_expect_tx(lut_bar, (uint32_t)p.lut_bytes);
             bulk_g2s(lut_s, p.qlut + (size_t)n * p.K * 4, (uint32_t)p.lut_bytes, lut_bar, pol_l);
@@ -526,6 +531,7 @@ __global__ void __launch_bounds__(kG2Threads) gemv2_kernel(const Gemv2Params p, 
             for (int a = tid; a < nag; a += kG2Warps * 32) { ls_s[a] = __ldg(lsg + a); lb_s[a] = __ldg(lbg + a); }
             asm volatile("bar.sync 1, %0;" ::"n"(kG2Warps * 32) : "memory");
         }
+        if (tid == 0) TMAC_TRACE(3);
         float cacc[RW];
         int iacc[RW];
 #pragma unroll
@@ -548,6 +554,7 @@ __global__ void __launch_bounds__(kG2Threads) gemv2_kernel(const Gemv2Params p, 
             }
             const int slot = bi % S;
             mbar_wait(full + slot, (uint32_t)((bi / S) & 1));
+            if (tid == 0 && bi == 0) TMAC_TRACE(4);
             const unsigned char *blk = stage + (size_t)slot * p.blk_bytes;
             const uint4 *wp = reinterpret_cast<const uint4 *>(blk) + lane;
             uint4 wv[QCH];
@@ -595,6 +602,7 @@ __global__ void __launch_bounds__(kG2Threads) gemv2_kernel(const Gemv2Params p, 
             c += kG2Warps;
             while (c >= p.nchunk) { c -= p.nchunk; ++rsb; }
         }
+        if (tid == 0) TMAC_TRACE(5);
         if (cur_rsb >= 0) {
             float *r = red + ((size_t)(cur_rsb - rsb_first) * kG2Warps + warp) * RSB + lane * RW;
 #pragma unroll
@@ -602,6 +610,7 @@ __global__ void __launch_bounds__(kG2Threads) gemv2_kernel(const Gemv2Params p, 
         }
     }
     __syncthreads();
+    if (tid == 0) TMAC_TRACE(6);
     if (nb <= 0) return;
 
     // ---- epilogue: one super-block at a time ------------------------------------------------
@@ -659,6 +668,7 @@ __global__ void __launch_bounds__(kG2Threads) gemv2_kernel(const Gemv2Params p, 
         }
         (void)padded_rows;
     }
+    if (tid == 0) TMAC_TRACE(7);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -1,0 +1,28 @@
+"""Debug helper: per-phase clock64 timeline of gemv2_kernel (TMAC_B200_TRACE=1)."""
+import os, sys
+import numpy as np
+os.environ["TMAC_B200_TRACE"] = "1"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "t-mac_b200")); sys.path.insert(0, ROOT)
+import torch
+import tmac_b200 as tb
+import bench
+lib = tb.load(); tb.check(lib.tmac_b200_init(0), "init")
+w, sc, z = bench.synth(1)
+cfg = tb.make_kcfg(bench.MOUT, bench.K, 2, 128, 16, 128, 64, True, False)
+wt = tb.upload_plain(cfg, w, sc, z)
+x = torch.randn((1, bench.K), device="cuda")
+q = torch.zeros((1, bench.K // 4, 16), dtype=torch.int8, device="cuda")
+ls = torch.zeros((1, 64), device="cuda"); lb = torch.zeros_like(ls); out = torch.zeros((1, bench.MOUT), device="cuda")
+tb.preprocessor(bench.K, 1, 64, x, ls, lb, q)
+for it in range(3):
+    tb.qgemm_lut(wt, 1, q, ls, lb, out)
+    tb.check(lib.tmac_b200_sync(), "sync")
+buf = np.zeros((512, 8), np.int64)
+n = lib.tmac_b200_debug_trace(buf.ctypes.data, 512)
+t = buf[:n].astype(np.float64)
+d = t - t[:, :1]
+names = ["entry", "init+sync", "tma issued", "wait+lslb", "first full", "loop done", "all done", "epilogue"]
+print("ctas", n, "SM cycles since entry (mean / min / max):")
+for i, nm in enumerate(names):
+    print("  %-12s %8.0f %8.0f %8.0f" % (nm, d[:, i].mean(), d[:, i].min(), d[:, i].max()))
