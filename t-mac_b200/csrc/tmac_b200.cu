@@ -83,6 +83,7 @@ struct Context {
     int ctas_per_sm = 1;
     int smem_budget = 100 * 1024;        // per CTA, so that two launches can overlap on one SM (PDL)
     int use_pdl = 1;
+    int consumer_warps = 16;
     std::map<int64_t, Resident> res;
     int64_t next_handle = 1;
     std::vector<tmac_b200_kcfg> kcfgs;
@@ -128,6 +129,7 @@ int ensure_init() {
     if (const char *e = getenv("TMAC_B200_SMEM_BUDGET")) g.smem_budget = atoi(e);
     if (const char *e = getenv("TMAC_B200_PDL")) g.use_pdl = atoi(e);
     if (const char *e = getenv("TMAC_B200_TRACE")) g.trace = atoi(e);
+    if (const char *e = getenv("TMAC_B200_WARPS")) g.consumer_warps = atoi(e);
     g.inited = true;
     return 0;
 }
@@ -194,11 +196,13 @@ int launch_gemv2(const Resident &R, int row_begin, int row_end, int N, const int
     p.zp = L.zp; p.one_scale = L.one_scale; p.int_path = int_path ? 1 : 0; p.sd = L.sd; p.out_f16 = out_f16;
     p.blk_bytes = (int)L.blk; p.scale0 = L.scale0; p.lut_bytes = L.K * 4;
     const int G = std::max(1, std::min(p.nblocks, g.sms * std::max(1, g.ctas_per_sm)));
+    const int NW = std::max(1, std::min(g.consumer_warps, kG2MaxWarps));
     const int max_range = (p.nblocks + G - 1) / G;
     p.max_rsb_cta = (max_range + L.nchunk - 1) / L.nchunk + 1;
+    if (p.max_rsb_cta > 8) return fail("qgemm_lut: K too small for this many rows per CTA (max_rsb_cta > 8)");
     p.maxc = std::min(G, (int)(((long long)L.nchunk * G + p.nblocks - 1) / p.nblocks) + 1);
     const size_t nag = (size_t)L.K / L.act_group_size;
-    const size_t fixed_no_bar = (size_t)p.lut_bytes + 2 * nag * 4 + (size_t)p.max_rsb_cta * kG2Warps * L.rsb * 4 + 256;
+    const size_t fixed_no_bar = (size_t)p.lut_bytes + 2 * nag * 4 + (size_t)p.max_rsb_cta * NW * L.rsb * 4 + 256;
     size_t budget = (size_t)g.smem_budget;
     int S = max_range;
     while (S > 1 && fixed_no_bar + (((size_t)(2 * S + 1) * 8 + 127) & ~(size_t)127) + (size_t)S * L.blk > budget) --S;
@@ -227,7 +231,7 @@ int launch_gemv2(const Resident &R, int row_begin, int row_end, int N, const int
     plane_weight_regs(L.bits, sym, &wtx, &wty);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(G, N, 1);
-    cfg.blockDim = dim3(kG2Threads, 1, 1);
+    cfg.blockDim = dim3((NW + 1) * 32, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = g.stream();
     cudaLaunchAttribute attr[1];

@@ -464,20 +464,31 @@ template <int PB, bool SYM> struct QuadRaw {
     }
 };
 
-constexpr int kG2Warps = 8;                       // consumer warps
-constexpr int kG2Threads = (kG2Warps + 1) * 32;   // + 1 producer warp
+constexpr int kG2MaxWarps = 24;                   // consumer warps per CTA (runtime: blockDim.x/32 - 1)
 
+__device__ __forceinline__ int atom_add_acq_rel_gpu(int *addr, int v) {
+    int old;
+    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(addr), "r"(v) : "memory");
+    return old;
+}
+
+// Work unit = a pair of quads (8 K-groups = 32 K positions) of one block; unit u of the CTA goes
+// to consumer warp u % NW.  With 16 warps and ~75 units per CTA the static schedule is within 7 %
+// of perfect balance while every warp still follows the order in which the stream arrives.
 template <int PB, bool SYM, int QCH>
-__global__ void __launch_bounds__(kG2Threads) gemv2_kernel(const Gemv2Params p, const uint32_t wtx, const uint32_t wty) {
+__global__ void __launch_bounds__((kG2MaxWarps + 1) * 32) gemv2_kernel(const Gemv2Params p, const uint32_t wtx, const uint32_t wty) {
     constexpr int RW = 8 / PB;
     constexpr int RSB = 32 * RW;
+    constexpr int UPB = QCH / 2;                  // units per block
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NW = (blockDim.x >> 5) - 1;         // consumer warps; warp NW is the producer
     const int G = gridDim.x, cta = blockIdx.x, n = blockIdx.y;
     const int b0 = (int)((long long)p.nblocks * cta / G), b1 = (int)((long long)p.nblocks * (cta + 1) / G);
     const int nb = b1 - b0;
     const int S = p.nslots;
     const int rsb_first = b0 / p.nchunk;
+    const int nag = p.K / p.ags;
 
     // ---- shared memory carve-up (host computes the same sizes) ----
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);          // [S]
@@ -486,36 +497,40 @@ __global__ void __launch_bounds__(kG2Threads) gemv2_kernel(const Gemv2Params p, 
     unsigned char *stage = smem + (((size_t)(2 * S + 1) * 8 + 127) & ~(size_t)127);   // [S][blk_bytes]
     uint4 *lut_s = reinterpret_cast<uint4 *>(stage + (size_t)S * p.blk_bytes);        // [K/4] raw QLUT rows
     float *ls_s = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(lut_s) + p.lut_bytes);   // [nag]
-    float *lb_s = ls_s + p.K / p.ags;                                                  // [nag]
-    float *red = lb_s + p.K / p.ags;                                                   // [max_rsb_cta][NW][RSB]
-    __shared__ int s_flag;
+    float *lb_s = ls_s + nag;                                                          // [nag]
+    float *red = lb_s + nag;                                                           // [max_rsb_cta][NW][RSB]
+    __shared__ int s_last[8];
 
     if (tid == 0) TMAC_TRACE(0);
-    if (tid == 0) {
-        for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        mbar_init(lut_bar, 1);
+    if (warp == NW) {
+        // ---- producer warp: barriers + the whole weight stream of this CTA, issued lane-parallel,
+        //      before any dependency wait (weights are static).
+        for (int s = lane; s < S; s += 32) { mbar_init(full + s, 1); mbar_init(empty + s, UPB); }
+        if (lane == 0) mbar_init(lut_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncwarp();
+        const uint64_t pol_w = policy_evict_first();
+        const unsigned char *src = p.W + (size_t)b0 * p.blk_bytes;
+        const int first = nb < S ? nb : S;
+        for (int i = lane; i < first; i += 32) {
+            mbar_expect_tx(full + i, (uint32_t)p.blk_bytes);
+            bulk_g2s(stage + (size_t)i * p.blk_bytes, src + (size_t)i * p.blk_bytes, (uint32_t)p.blk_bytes, full + i, pol_w);
+        }
+        if (lane == 0) TMAC_TRACE(2);
+    } else {
+        for (int i = tid; i < p.max_rsb_cta * NW * RSB; i += NW * 32) red[i] = 0.f;
     }
-    for (int i = tid; i < p.max_rsb_cta * kG2Warps * RSB; i += kG2Threads) red[i] = 0.f;
     __syncthreads();
-    pdl_launch_dependents();    // let the next kernel in the stream start its own weight prefetch
+    pdl_launch_dependents();    // the next kernel in the stream may start its own weight prefetch
     if (tid == 0) TMAC_TRACE(1);
 
-    const int nag = p.K / p.ags;
-    if (warp == kG2Warps) {
-        // ================= producer warp =================
+    if (warp == NW) {
         if (lane == 0 && nb > 0) {
-            const uint64_t pol_w = policy_evict_first(), pol_l = policy_evict_last();
-            const unsigned char *src = p.W + (size_t)b0 * p.blk_bytes;
-            const int first = nb < S ? nb : S;
-            for (int i = 0; i < first; ++i) {                 // static weights: may run ahead of the dependency
-                mbar_expect_tx(full + i, (uint32_t)p.blk_bytes);
-                bulk_g2s(stage + (size_t)i * p.blk_bytes, src + (size_t)i * p.blk_bytes, (uint32_t)p.blk_bytes, full + i, pol_w);
-            }
-            TMAC_TRACE(2);
-            pdl_wait();                                       // LUT / scales come from the previous kernel
+            pdl_wait();                                       // the LUT comes from the previous kernel
+            const uint64_t pol_l = policy_evict_last(), pol_w = policy_evict_first();
             mbar_expect_tx(lut_bar, (uint32_t)p.lut_bytes);
             bulk_g2s(lut_s, p.qlut + (size_t)n * p.K * 4, (uint32_t)p.lut_bytes, lut_bar, pol_l);
+            const unsigned char *src = p.W + (size_t)b0 * p.blk_bytes;
             for (int i = S; i < nb; ++i) {                    // ring reuse (ranges larger than the ring)
                 const int s = i % S;
                 mbar_wait(empty + s, (uint32_t)(((i / S) - 1) & 1));
@@ -526,10 +541,10 @@ __global__ void __launch_bounds__(kG2Threads) gemv2_kernel(const Gemv2Params p, 
     } else {
         // ================= consumer warps =================
         pdl_wait();
-        {   // LUT scales / biases of this activation row -> shared (consumer threads only)
+        {
             const float *lsg = p.lut_scales + (size_t)n * nag, *lbg = p.lut_biases + (size_t)n * nag;
-            for (int a = tid; a < nag; a += kG2Warps * 32) { ls_s[a] = __ldg(lsg + a); lb_s[a] = __ldg(lbg + a); }
-            asm volatile("bar.sync 1, %0;" ::"n"(kG2Warps * 32) : "memory");
+            for (int a = tid; a < nag; a += NW * 32) { ls_s[a] = __ldg(lsg + a); lb_s[a] = __ldg(lbg + a); }
+            asm volatile("bar.sync 1, %0;" ::"r"(NW * 32) : "memory");
         }
         if (tid == 0) TMAC_TRACE(3);
         float cacc[RW];
@@ -538,15 +553,14 @@ __global__ void __launch_bounds__(kG2Threads) gemv2_kernel(const Gemv2Params p, 
         for (int i = 0; i < RW; ++i) { cacc[i] = 0.f; iacc[i] = 0; }
         int cur_rsb = -1;
         bool lut_ready = false;
-        // first block of this warp: b0 + warp
-        int bi = warp;
-        int rsb = 0, c = 0;
-        if (bi < nb) { const int b = b0 + bi; rsb = b / p.nchunk; c = b - rsb * p.nchunk; }
-        const int agq = 1 << p.agq_shift;
-        for (; bi < nb; bi += kG2Warps) {
+        const int nu = nb * UPB;
+        for (int u = warp; u < nu; u += NW) {
+            const int bi = u / UPB, q0 = (u - bi * UPB) * 2;
+            const int b = b0 + bi;
+            const int rsb = b / p.nchunk, c = b - rsb * p.nchunk;
             if (rsb != cur_rsb) {
                 if (cur_rsb >= 0) {
-                    float *r = red + ((size_t)(cur_rsb - rsb_first) * kG2Warps + warp) * RSB + lane * RW;
+                    float *r = red + ((size_t)(cur_rsb - rsb_first) * NW + warp) * RSB + lane * RW;
 #pragma unroll
                     for (int i = 0; i < RW; ++i) { r[i] = p.int_path ? __int_as_float(iacc[i]) : cacc[i]; cacc[i] = 0.f; iacc[i] = 0; }
                 }
@@ -554,12 +568,10 @@ __global__ void __launch_bounds__(kG2Threads) gemv2_kernel(const Gemv2Params p, 
             }
             const int slot = bi % S;
             mbar_wait(full + slot, (uint32_t)((bi / S) & 1));
-            if (tid == 0 && bi == 0) TMAC_TRACE(4);
+            if (tid == 0 && u == 0) TMAC_TRACE(4);
             const unsigned char *blk = stage + (size_t)slot * p.blk_bytes;
-            const uint4 *wp = reinterpret_cast<const uint4 *>(blk) + lane;
-            uint4 wv[QCH];
-#pragma unroll
-            for (int q = 0; q < QCH; ++q) wv[q] = wp[q * 32];
+            const uint4 *wp = reinterpret_cast<const uint4 *>(blk) + lane + q0 * 32;
+            const uint4 w0 = wp[0], w1 = wp[32];
             float sc[RW], zr[RW];
             if (!p.one_scale) {
                 const unsigned char *sp = blk + (size_t)QCH * 512;
@@ -573,38 +585,38 @@ __global__ void __launch_bounds__(kG2Threads) gemv2_kernel(const Gemv2Params p, 
                 for (int i = 0; i < RW; ++i) { sc[i] = p.scale0; zr[i] = 0.f; }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(empty + slot);          // stage bytes are in registers now
+            if (lane == 0) mbar_arrive(empty + slot);          // this unit's stage bytes are in registers
             if (!lut_ready) { mbar_wait(lut_bar, 0); lut_ready = true; }
-            const uint4 *lq = lut_s + (size_t)c * QCH * 4;
-            float facc[RW];
+            const uint4 *lq = lut_s + ((size_t)c * QCH + q0) * 4;
+            if (p.int_path) {
+                QuadRaw<PB, SYM>::run(w0, lq, iacc, wtx, wty);
+                QuadRaw<PB, SYM>::run(w1, lq + 4, iacc, wtx, wty);
+            } else {
+                // a pair never straddles an activation group unless ags == 32 (one quad pair == one group)
+                int ia[RW];
 #pragma unroll
-            for (int i = 0; i < RW; ++i) facc[i] = 0.f;
-            float lbsum = 0.f;
-#pragma unroll
-            for (int q = 0; q < QCH; ++q) {
-                QuadRaw<PB, SYM>::run(wv[q], lq + q * 4, iacc, wtx, wty);
-                if (!p.int_path && (((q + 1) & (agq - 1)) == 0 || q == QCH - 1)) {
-                    const int ag = (c * QCH + q) >> p.agq_shift;
-                    const float lsv = ls_s[ag];
-                    lbsum += lb_s[ag];
-#pragma unroll
-                    for (int i = 0; i < RW; ++i) { facc[i] = fmaf(lsv, (float)iacc[i], facc[i]); iacc[i] = 0; }
+                for (int i = 0; i < RW; ++i) ia[i] = 0;
+                QuadRaw<PB, SYM>::run(w0, lq, ia, wtx, wty);
+                QuadRaw<PB, SYM>::run(w1, lq + 4, ia, wtx, wty);
+                const int ag = (c * QCH + q0) >> p.agq_shift;
+                const float lsv = ls_s[ag];
+                // the chunk's bias sum is charged once per (row, chunk): by the unit with q0 == 0
+                float lbsum = 0.f;
+                if (q0 == 0) {
+                    const int a1 = ((c + 1) * QCH) >> p.agq_shift;
+                    for (int a = ag; a < a1; ++a) lbsum += lb_s[a];
                 }
-            }
-            if (!p.int_path) {
 #pragma unroll
                 for (int i = 0; i < RW; ++i) {
-                    float v = fmaf(0.5f * sc[i], facc[i] + lbsum, cacc[i]);
+                    float v = fmaf(0.5f * sc[i], fmaf(lsv, (float)ia[i], lbsum), cacc[i]);
                     if (p.zp) v = fmaf(zr[i], lbsum, v);
                     cacc[i] = v;
                 }
             }
-            c += kG2Warps;
-            while (c >= p.nchunk) { c -= p.nchunk; ++rsb; }
         }
         if (tid == 0) TMAC_TRACE(5);
         if (cur_rsb >= 0) {
-            float *r = red + ((size_t)(cur_rsb - rsb_first) * kG2Warps + warp) * RSB + lane * RW;
+            float *r = red + ((size_t)(cur_rsb - rsb_first) * NW + warp) * RSB + lane * RW;
 #pragma unroll
             for (int i = 0; i < RW; ++i) r[i] = p.int_path ? __int_as_float(iacc[i]) : cacc[i];
         }
@@ -613,49 +625,19 @@ __global__ void __launch_bounds__(kG2Threads) gemv2_kernel(const Gemv2Params p, 
     if (tid == 0) TMAC_TRACE(6);
     if (nb <= 0) return;
 
-    // ---- epilogue: one super-block at a time ------------------------------------------------
+    // ---- epilogue.  Pass 1: fixed-order sum over warps for every super-block of the range;
+    //      whole super-blocks are finished, split ones publish a partial.  One release/acquire
+    //      round on the arrival counters.  Pass 2: the last arriver of a split super-block sums the
+    //      partials in CTA order.
     const int rsb_last = (b1 - 1) / p.nchunk;
-    const int padded_rows = p.nrsb * RSB;
-    for (int r = rsb_first; r <= rsb_last; ++r) {
-        float fsum = 0.f; int isum = 0;
-        if (tid < RSB) {
-#pragma unroll
-            for (int w = 0; w < kG2Warps; ++w) {
-                const float v = red[((size_t)(r - rsb_first) * kG2Warps + w) * RSB + tid];
-                if (p.int_path) isum += __float_as_int(v); else fsum += v;
-            }
-        }
-        const int rb0 = r * p.nchunk, rb1 = rb0 + p.nchunk;     // block range of super-block r
-        const bool whole = (rb0 >= b0 && rb1 <= b1);
-        if (!whole) {
-            const int cfirst = (int)(((long long)(rb0 + 1) * G + p.nblocks - 1) / p.nblocks) - 1;
-            const int clast = (int)(((long long)rb1 * G + p.nblocks - 1) / p.nblocks) - 1;
-            const int nctr = clast - cfirst + 1;
-            float *slots = p.partial + (((size_t)n * p.nrsb + r) * p.maxc) * RSB;
-            if (tid < RSB) slots[(size_t)(cta - cfirst) * RSB + tid] = p.int_path ? __int_as_float(isum) : fsum;
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) {
-                const int t = atomicAdd(p.counters + (size_t)n * p.nrsb + r, 1);
-                s_flag = (t == nctr - 1);
-                if (s_flag) p.counters[(size_t)n * p.nrsb + r] = 0;
-            }
-            __syncthreads();
-            const bool last = s_flag != 0;
-            __syncthreads();
-            if (!last) continue;
-            __threadfence();
-            fsum = 0.f; isum = 0;
-            if (tid < RSB)
-                for (int k2 = 0; k2 < nctr; ++k2) {
-                    const float v = __ldcg(slots + (size_t)k2 * RSB + tid);
-                    if (p.int_path) isum += __float_as_int(v); else fsum += v;
-                }
-        }
+    const int nloc = rsb_last - rsb_first + 1;
+    auto finish = [&](int r, float fsum, int isum) {
         const int row = (p.rsb0 + r) * RSB + tid;
-        if (tid < RSB && row >= p.row_begin && row < p.row_end) {
+        if (row >= p.row_begin && row < p.row_end) {
             float out;
             if (p.int_path) {
+                // C = ((sum_b alpha_b*CBits_b) * LUT_Scales[0] + LUT_Biases[0]*alpha_0) * Scales[0]
+                // (python/t_mac/ops/qgemm.py:160,171-174); isum = sum_b 2*alpha_b*CBits_b exactly.
                 const float cb = __fmul_rn((float)isum, 0.5f);
                 const float t1 = __fmul_rn(cb, ls_s[0]);
                 const float t2 = __fmul_rn(lb_s[0], 0.5f);
@@ -666,7 +648,49 @@ __global__ void __launch_bounds__(kG2Threads) gemv2_kernel(const Gemv2Params p, 
             if (p.out_f16) reinterpret_cast<__half *>(p.C)[o] = __float2half_rn(out);
             else reinterpret_cast<float *>(p.C)[o] = out;
         }
-        (void)padded_rows;
+    };
+    bool any_split = false;
+    for (int r = rsb_first; r <= rsb_last; ++r) {
+        float fsum = 0.f; int isum = 0;
+        if (tid < RSB)
+            for (int w = 0; w < NW; ++w) {
+                const float v = red[((size_t)(r - rsb_first) * NW + w) * RSB + tid];
+                if (p.int_path) isum += __float_as_int(v); else fsum += v;
+            }
+        const int rb0 = r * p.nchunk, rb1 = rb0 + p.nchunk;
+        if (rb0 >= b0 && rb1 <= b1) { if (tid < RSB) finish(r, fsum, isum); continue; }
+        any_split = true;
+        const int cfirst = (int)(((long long)(rb0 + 1) * G + p.nblocks - 1) / p.nblocks) - 1;
+        float *slots = p.partial + (((size_t)n * p.nrsb + r) * p.maxc) * RSB;
+        if (tid < RSB) slots[(size_t)(cta - cfirst) * RSB + tid] = p.int_path ? __int_as_float(isum) : fsum;
+    }
+    if (!any_split) { if (tid == 0) TMAC_TRACE(7); return; }
+    __syncthreads();                    // all partial stores of this CTA happen-before the release below
+    if (tid < nloc) {
+        const int r = rsb_first + tid;
+        const int rb0 = r * p.nchunk, rb1 = rb0 + p.nchunk;
+        int last = 0;
+        if (!(rb0 >= b0 && rb1 <= b1)) {
+            const int cfirst = (int)(((long long)(rb0 + 1) * G + p.nblocks - 1) / p.nblocks) - 1;
+            const int clast = (int)(((long long)rb1 * G + p.nblocks - 1) / p.nblocks) - 1;
+            const int nctr = clast - cfirst + 1;
+            int *ctr = p.counters + (size_t)n * p.nrsb + r;
+            const int t = atom_add_acq_rel_gpu(ctr, 1);
+            if (t == nctr - 1) { last = nctr; *ctr = 0; }     // self-reset for the next launch
+        }
+        s_last[tid & 7] = last;
+    }
+    __syncthreads();
+    for (int r = rsb_first; r <= rsb_last; ++r) {
+        const int nctr = s_last[(r - rsb_first) & 7];
+        if (nctr == 0 || tid >= RSB) continue;
+        const float *slots = p.partial + (((size_t)n * p.nrsb + r) * p.maxc) * RSB;
+        float fsum = 0.f; int isum = 0;
+        for (int k2 = 0; k2 < nctr; ++k2) {
+            const float v = __ldcg(slots + (size_t)k2 * RSB + tid);
+            if (p.int_path) isum += __float_as_int(v); else fsum += v;
+        }
+        finish(r, fsum, isum);
     }
     if (tid == 0) TMAC_TRACE(7);
 }
