@@ -37,6 +37,7 @@ METRIC = "w2a16_gemv_hbm_gbps"
 UNIT = "GB/s"
 MOUT, K, BITS, GS, AGS, ZP = 11008, 4096, 2, 128, 64, True
 LAYERS = 32
+PREFETCH_NEXT = os.environ.get("TMAC_BENCH_PREFETCH", "1") != "0"
 
 
 def algorithmic_bytes(mout=MOUT, k=K, bits=BITS, gs=GS, zp=ZP, act_bytes=4, out_bytes=4, scale_bytes=2):
@@ -232,6 +233,8 @@ def main():
         for i, wt in enumerate(layers):
             if with_pre:
                 tb.preprocessor(K, 1, AGS, x[i], ls[i], lb[i], qlut[i])
+            if PREFETCH_NEXT:
+                lib.tmac_b200_hint_next_weights(layers[(i + 1) % LAYERS].handle)
             tb.qgemm_lut(wt, 1, qlut[i], ls[i], lb[i], out[i])
 
     def capture(with_pre):

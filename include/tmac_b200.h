@@ -107,6 +107,9 @@ TMAC_B200_API int tmac_b200_free_weights(int64_t handle);
 /* A second resident copy in its own HBM allocation (distinct layers with tied shapes; benchmarks
  * that must stream weights from HBM rather than L2). */
 TMAC_B200_API int64_t tmac_b200_clone_weights(int64_t handle);
+/* One-shot hint for the next qgemm_lut / gemv call: `handle` is the tensor that will be multiplied
+ * after it (next layer).  The launch prefetches that tensor's blocks into L2 while it computes. */
+TMAC_B200_API int tmac_b200_hint_next_weights(int64_t handle);
 TMAC_B200_API size_t tmac_b200_weights_nbytes(int64_t handle); /* resident bytes in HBM */
 /* Row-shard view for multi-GPU: keep only rows [row0,row0+rows) resident. */
 TMAC_B200_API int64_t tmac_b200_upload_plain_rows(const tmac_b200_kcfg *cfg, const uint8_t *w,

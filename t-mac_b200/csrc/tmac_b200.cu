@@ -79,11 +79,10 @@ struct Context {
     int float_type = TMAC_B200_F32;
     int lut_mode = 0;                    // 0 auto, 1 general, 2 symmetric
     int ks_override = 0;
-    int kernel_version = 2;              // 2 = gemv2_kernel (TMA + PDL), 1 = gemv_kernel
-    int ctas_per_sm = 1;
-    int smem_budget = 100 * 1024;        // per CTA, so that two launches can overlap on one SM (PDL)
+    int kernel_version = 3;              // 3 = gemv3_kernel (clusters + DSMEM + PDL), 1 = gemv_kernel (split-K scratch)
     int use_pdl = 1;
-    int consumer_warps = 16;
+    int cs_override = 0, wpc_override = 0;
+    int64_t next_hint = 0;               // one-shot: tensor whose blocks the next launch prefetches into L2
     std::map<int64_t, Resident> res;
     int64_t next_handle = 1;
     std::vector<tmac_b200_kcfg> kcfgs;
@@ -125,11 +124,10 @@ int ensure_init() {
     if (const char *e = getenv("TMAC_B200_KS")) g.ks_override = atoi(e);
     if (const char *e = getenv("TMAC_B200_LUT_MODE")) g.lut_mode = atoi(e);
     if (const char *e = getenv("TMAC_B200_KERNEL")) g.kernel_version = atoi(e);
-    if (const char *e = getenv("TMAC_B200_CTAS_PER_SM")) g.ctas_per_sm = atoi(e);
-    if (const char *e = getenv("TMAC_B200_SMEM_BUDGET")) g.smem_budget = atoi(e);
     if (const char *e = getenv("TMAC_B200_PDL")) g.use_pdl = atoi(e);
     if (const char *e = getenv("TMAC_B200_TRACE")) g.trace = atoi(e);
-    if (const char *e = getenv("TMAC_B200_WARPS")) g.consumer_warps = atoi(e);
+    if (const char *e = getenv("TMAC_B200_CS")) g.cs_override = atoi(e);
+    if (const char *e = getenv("TMAC_B200_WPC")) g.wpc_override = atoi(e);
     g.inited = true;
     return 0;
 }
@@ -152,23 +150,103 @@ gemv_fn pick_gemv(int pb, bool sym, int qch) {
     return nullptr;
 }
 
-typedef void (*gemv2_fn)(const Gemv2Params, const uint32_t, const uint32_t);
-template <int PB, bool SYM> gemv2_fn pick2_qch(int qch) {
+typedef void (*gemv3_fn)(const Gemv3Params, const uint32_t, const uint32_t);
+template <int PB, bool SYM> gemv3_fn pick3_qch(int qch) {
     switch (qch) {
-        case 2: return gemv2_kernel<PB, SYM, 2>;
-        case 4: return gemv2_kernel<PB, SYM, 4>;
-        case 8: return gemv2_kernel<PB, SYM, 8>;
+        case 2: return gemv3_kernel<PB, SYM, 2>;
+        case 4: return gemv3_kernel<PB, SYM, 4>;
+        case 8: return gemv3_kernel<PB, SYM, 8>;
     }
     return nullptr;
 }
-gemv2_fn pick_gemv2(int pb, bool sym, int qch) {
-    if (pb == 4) return sym ? pick2_qch<4, true>(qch) : pick2_qch<4, false>(qch);
-    if (pb == 2) return sym ? pick2_qch<2, true>(qch) : pick2_qch<2, false>(qch);
-    if (pb == 1) return sym ? pick2_qch<1, true>(qch) : pick2_qch<1, false>(qch);
+gemv3_fn pick_gemv3(int pb, bool sym, int qch) {
+    if (pb == 4) return sym ? pick3_qch<4, true>(qch) : pick3_qch<4, false>(qch);
+    if (pb == 2) return sym ? pick3_qch<2, true>(qch) : pick3_qch<2, false>(qch);
+    if (pb == 1) return sym ? pick3_qch<1, true>(qch) : pick3_qch<1, false>(qch);
     return nullptr;
 }
 
 int ilog2(int v) { int s = 0; while ((1 << (s + 1)) <= v) ++s; return s; }
+
+// Decomposition of one launch: cluster size CS (K slices of a super-block), warps per CTA, chunks
+// per warp.  Minimises the work of the busiest SM (CTAs are spread round-robin over SMs), then
+// prefers more warps in flight.
+void choose_decomposition(int nrsb, int nchunk, int N, int *cs_out, int *wpc_out, int *bpw_out) {
+    double best_cost = 1e30; int bcs = 1, bwpc = 1, bbpw = nchunk;
+    for (int cs : {1, 2, 4, 8})
+        for (int wpc = 1; wpc <= kG3MaxWarps; ++wpc) {
+            if (cs * wpc > nchunk && !(cs == 1 && wpc == 1)) { if (cs * (wpc - 1) >= nchunk) continue; }
+            const int bpw = (nchunk + cs * wpc - 1) / (cs * wpc);
+            if ((cs - 1) * wpc * bpw >= nchunk) continue;              // an entirely idle CTA
+            const long ctas = (long)nrsb * cs * N;
+            const int res = std::max(1, std::min(32, 2048 / (wpc * 32)));   // resident CTAs per SM (threads)
+            const long per_sm = (ctas + g.sms - 1) / g.sms;
+            const long waves = (per_sm + res - 1) / res;
+            double cost = (double)per_sm * wpc * bpw;                  // chunk-slots on the busiest SM
+            cost *= 1.0 + 0.15 * (waves - 1);                          // later waves lose the overlap
+            cost += 0.02 * bpw * wpc;                                  // prefer short per-warp chains ...
+            cost += 0.5 * std::max(0L, 8 - per_sm * wpc);              // ... and at least 8 warps per SM
+            if (cost < best_cost) { best_cost = cost; bcs = cs; bwpc = wpc; bbpw = bpw; }
+        }
+    *cs_out = bcs; *wpc_out = bwpc; *bpw_out = bbpw;
+}
+
+// Production launch: clusters + DSMEM reduction + PDL (gemv3_kernel).
+int launch_gemv3(const Resident &R, int row_begin, int row_end, int N, const int8_t *qlut, const float *ls, const float *lb, void *C,
+                 int ldc, int c_row0, int out_f16, bool sym) {
+    const StreamLayout &L = R.L;
+    if (row_begin < 0 || row_end > L.Mout || row_begin >= row_end) return fail("qgemm_lut: bad row range");
+    const int rsb0 = row_begin / L.rsb, rsb1 = (row_end + L.rsb - 1) / L.rsb, nrsb = rsb1 - rsb0;
+    const bool int_path = L.one_scale && L.act_group_size == L.K;
+    Gemv3Params p{};
+    p.W = R.d + (size_t)rsb0 * L.rsb_stride;
+    p.Wnext = nullptr;
+    if (g.next_hint) {
+        auto it = g.res.find(g.next_hint);
+        if (it != g.res.end() && it->second.L.total == L.total && it->second.L.blk == L.blk) p.Wnext = it->second.d + (size_t)rsb0 * L.rsb_stride;
+        g.next_hint = 0;
+    }
+    p.qlut = qlut; p.lut_scales = ls; p.lut_biases = lb; p.C = C;
+    p.K = L.K; p.ldc = ldc; p.row_begin = row_begin; p.row_end = row_end; p.c_row0 = c_row0; p.bits = L.bits;
+    p.nrsb = nrsb; p.rsb0 = rsb0; p.nchunk = L.nchunk;
+    p.ags = L.act_group_size; p.ck = L.ck;
+    p.agq_shift = ilog2(std::max(1, std::min(L.act_group_size, L.ck) / 16));
+    p.zp = L.zp; p.one_scale = L.one_scale; p.int_path = int_path ? 1 : 0; p.sd = L.sd; p.out_f16 = out_f16;
+    p.blk_bytes = (int)L.blk; p.scale0 = L.scale0; p.rsb_stride = L.rsb_stride;
+    choose_decomposition(nrsb, L.nchunk, N, &p.cs, &p.wpc, &p.bpw);
+    if (g.cs_override > 0) { p.cs = g.cs_override; }
+    if (g.wpc_override > 0) { p.wpc = std::min(g.wpc_override, kG3MaxWarps); }
+    if (g.cs_override > 0 || g.wpc_override > 0) p.bpw = (L.nchunk + p.cs * p.wpc - 1) / (p.cs * p.wpc);
+    if (g.trace) {
+        if (g.d_trace.ensure((size_t)nrsb * p.cs * 8 * sizeof(long long))) return fail("out of device memory (trace)");
+        p.trace = (long long *)g.d_trace.p;
+        g.trace_ctas = nrsb * p.cs;
+    }
+    gemv3_fn fn = pick_gemv3(L.pb, sym, L.qch);
+    if (!fn) return fail("qgemm_lut: unsupported chunking (qch=" + std::to_string(L.qch) + ")");
+    const size_t smem = (size_t)p.wpc * L.qch * 4 * (sym ? 8 : 16) + (size_t)p.wpc * L.rsb * 4 + (size_t)p.cs * L.rsb * 4;
+    if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint32_t wtx, wty;
+    plane_weight_regs(L.bits, sym, &wtx, &wty);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(nrsb * p.cs, N, 1);
+    cfg.blockDim = dim3(p.wpc * 32, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = g.stream();
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = g.use_pdl ? 1 : 0;
+    ++na;
+    if (p.cs > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = p.cs; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    CUDA_OK(cudaLaunchKernelEx(&cfg, fn, p, wtx, wty));
+    return 0;
+}
 
 int choose_ks(const StreamLayout &L, int nrsb, int N) {
     if (g.ks_override > 0) return std::max(1, std::min(g.ks_override, L.nchunk));
@@ -179,76 +257,13 @@ int choose_ks(const StreamLayout &L, int nrsb, int N) {
     return ks;
 }
 
-// Production launch: persistent block ranges + TMA staging + PDL (gemv2_kernel).
-int launch_gemv2(const Resident &R, int row_begin, int row_end, int N, const int8_t *qlut, const float *ls, const float *lb, void *C,
-                 int ldc, int c_row0, int out_f16, bool sym) {
-    const StreamLayout &L = R.L;
-    if (row_begin < 0 || row_end > L.Mout || row_begin >= row_end) return fail("qgemm_lut: bad row range");
-    const int rsb0 = row_begin / L.rsb, rsb1 = (row_end + L.rsb - 1) / L.rsb, nrsb = rsb1 - rsb0;
-    const bool int_path = L.one_scale && L.act_group_size == L.K;
-    Gemv2Params p{};
-    p.W = R.d + (size_t)rsb0 * L.rsb_stride;
-    p.qlut = qlut; p.lut_scales = ls; p.lut_biases = lb; p.C = C;
-    p.K = L.K; p.ldc = ldc; p.row_begin = row_begin; p.row_end = row_end; p.c_row0 = c_row0; p.bits = L.bits;
-    p.nrsb = nrsb; p.rsb0 = rsb0; p.nchunk = L.nchunk; p.nblocks = nrsb * L.nchunk;
-    p.ags = L.act_group_size; p.ck = L.ck;
-    p.agq_shift = ilog2(std::max(1, std::min(L.act_group_size, L.ck) / 16));
-    p.zp = L.zp; p.one_scale = L.one_scale; p.int_path = int_path ? 1 : 0; p.sd = L.sd; p.out_f16 = out_f16;
-    p.blk_bytes = (int)L.blk; p.scale0 = L.scale0; p.lut_bytes = L.K * 4;
-    const int G = std::max(1, std::min(p.nblocks, g.sms * std::max(1, g.ctas_per_sm)));
-    const int NW = std::max(1, std::min(g.consumer_warps, kG2MaxWarps));
-    const int max_range = (p.nblocks + G - 1) / G;
-    p.max_rsb_cta = (max_range + L.nchunk - 1) / L.nchunk + 1;
-    if (p.max_rsb_cta > 8) return fail("qgemm_lut: K too small for this many rows per CTA (max_rsb_cta > 8)");
-    p.maxc = std::min(G, (int)(((long long)L.nchunk * G + p.nblocks - 1) / p.nblocks) + 1);
-    const size_t nag = (size_t)L.K / L.act_group_size;
-    const size_t fixed_no_bar = (size_t)p.lut_bytes + 2 * nag * 4 + (size_t)p.max_rsb_cta * NW * L.rsb * 4 + 256;
-    size_t budget = (size_t)g.smem_budget;
-    int S = max_range;
-    while (S > 1 && fixed_no_bar + (((size_t)(2 * S + 1) * 8 + 127) & ~(size_t)127) + (size_t)S * L.blk > budget) --S;
-    p.nslots = S;
-    const size_t smem = fixed_no_bar + (((size_t)(2 * S + 1) * 8 + 127) & ~(size_t)127) + (size_t)S * L.blk;
-    if (smem > 227 * 1024) return fail("qgemm_lut: K too large for the shared-memory LUT (" + std::to_string(smem) + " B)");
-    const size_t part_bytes = (size_t)N * nrsb * p.maxc * L.rsb * sizeof(float);
-    const size_t cnt_bytes = (size_t)N * nrsb * sizeof(int);
-    if (g.d_part.ensure(part_bytes)) return fail("out of device memory (split scratch)");
-    if (cnt_bytes > g.d_cnt.cap || g.cnt_zeroed < cnt_bytes) {
-        if (g.d_cnt.ensure(cnt_bytes)) return fail("out of device memory (counters)");
-        CUDA_OK(cudaMemsetAsync(g.d_cnt.p, 0, g.d_cnt.cap, g.stream()));
-        g.cnt_zeroed = g.d_cnt.cap;
-    }
-    p.partial = (float *)g.d_part.p;
-    p.counters = (int *)g.d_cnt.p;
-    if (g.trace) {
-        if (g.d_trace.ensure((size_t)G * 8 * sizeof(long long))) return fail("out of device memory (trace)");
-        p.trace = (long long *)g.d_trace.p;
-        g.trace_ctas = G;
-    }
-    gemv2_fn fn = pick_gemv2(L.pb, sym, L.qch);
-    if (!fn) return fail("qgemm_lut: unsupported chunking (qch=" + std::to_string(L.qch) + ")");
-    if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    uint32_t wtx, wty;
-    plane_weight_regs(L.bits, sym, &wtx, &wty);
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(G, N, 1);
-    cfg.blockDim = dim3((NW + 1) * 32, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = g.stream();
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = g.use_pdl ? 1 : 0;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    CUDA_OK(cudaLaunchKernelEx(&cfg, fn, p, wtx, wty));
-    return 0;
-}
-
 // v1 launch (one CTA per (super-block, K split); kept for A/B comparison: TMAC_B200_KERNEL=1).
 // Launch qgemm_lut over rows [row_begin,row_end) (relative to the resident tensor).
 // All pointers are device pointers; C is [N][ldc] with C[n][row - c_row0].
 int launch_gemv(const Resident &R, int row_begin, int row_end, int N, const int8_t *qlut, const float *ls,
                 const float *lb, void *C, int ldc, int c_row0, int out_f16, bool sym, int32_t *cbits_unused) {
     (void)cbits_unused;
-    if (g.kernel_version != 1) return launch_gemv2(R, row_begin, row_end, N, qlut, ls, lb, C, ldc, c_row0, out_f16, sym);
+    if (g.kernel_version != 1) return launch_gemv3(R, row_begin, row_end, N, qlut, ls, lb, C, ldc, c_row0, out_f16, sym);
     const StreamLayout &L = R.L;
     if (row_begin < 0 || row_end > L.Mout || row_begin >= row_end) return fail("qgemm_lut: bad row range");
     const int rsb0 = row_begin / L.rsb, rsb1 = (row_end + L.rsb - 1) / L.rsb, nrsb = rsb1 - rsb0;
@@ -671,7 +686,16 @@ int tmac_b200_sync(void) {
     return 0;
 }
 
-// Debug: per-CTA clock64 stamps of the last gemv2 launch ([ctas][8]); returns #ctas or -1.
+// One-shot hint: the tensor that will be multiplied next.  The next qgemm_lut launch prefetches its
+// blocks into L2 (cp.async.bulk.prefetch.L2) while it computes, so that the HBM stream of launch
+// i+1 overlaps launch i.  Ignored unless the tensor has the same stream geometry.
+int tmac_b200_hint_next_weights(int64_t handle) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g.next_hint = handle;
+    return 0;
+}
+
+// Debug: per-CTA clock64 stamps of the last gemv3 launch ([ctas][8]); returns #ctas or -1.
 int tmac_b200_debug_trace(long long *dst, int cap_ctas) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g.trace || !g.d_trace.p) return fail("trace disabled (TMAC_B200_TRACE=1)");

@@ -360,287 +360,223 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_kernel(const GemvParams p, 
 }
 
 // ==========================================================================================
-// gemv2_kernel -- the production GEMV: persistent CTAs over contiguous block ranges, weights
-// streamed HBM -> shared memory by TMA bulk copies (cp.async.bulk + mbarrier complete_tx), LUT
-// slice copied the same way, programmatic dependent launch (PDL) so that the weight stream of
-// launch i+1 overlaps the tail of launch i.
+// gemv3_kernel -- the production GEMV.
 //
-//   blocks   : the (row super-block, K chunk) blocks of the stream layout in memory order,
-//              NB = nrsb * nchunk of them; CTA i owns the contiguous range [NB*i/G, NB*(i+1)/G)
-//              (equal bytes per SM, +-1 block).
-//   producer : warp NW.  Before griddepcontrol.wait it arms the stage barriers and issues the
-//              bulk copies of this CTA's weight range (weights are static data, so this may
-//              overlap the previous kernel in the stream); after the wait it copies the LUT.
-//   consumers: warps 0..NW-1, block b of the range goes to warp (b - b0) % NW.  Lane l owns RW rows
-//              of the super-block (no cross-lane reduction).  Accumulators are flushed to a
-//              per-CTA buffer when the warp moves to another super-block.
-//   epilogue : fixed-order sum over warps; a super-block whose K range is split between CTAs goes
-//              through a global scratch slot + arrival counter, the last CTA summing the slots in
-//              CTA order (deterministic, bit-reproducible run to run).
+//   decomposition : CTA = (row super-block, K slice); the K slices of one super-block form a
+//                   thread-block CLUSTER (size CS <= 8) and are summed through distributed shared
+//                   memory in rank order -- deterministic, no global scratch, no atomics.
+//   warps         : warp-autonomous.  Warp w of CTA rank r owns the `bpw` consecutive K chunks
+//                   starting at (r*WPC + w)*bpw.  Every lane owns RW rows (no cross-lane reduce).
+//   memory        : each lane issues its 128-bit weight loads for the first chunk BEFORE
+//                   griddepcontrol.wait (weights are static, so under programmatic dependent
+//                   launch they overlap the previous kernel's tail); the activation LUT slice of
+//                   the chunk (32 groups x 16 B) is fetched after the wait, compacted into a
+//                   warp-private shared-memory table and read back as broadcast LDS.
+//                   One lane per warp also issues cp.async.bulk.prefetch.L2 for the same block of
+//                   the NEXT tensor (software pipelining of the HBM stream across launches).
+//   arithmetic    : Quad<PB,SYM> (PRMT lookups + DP4A), per-act-group fp32 scale, per-chunk weight
+//                   scale / zero point, exactly the algebra of tbl.cc:435-529 re-associated.
 // ==========================================================================================
-struct Gemv2Params {
+struct Gemv3Params {
     const unsigned char *W;        // first block of the launch's first row super-block
+    const unsigned char *Wnext;    // same, for the tensor that will be used next (L2 prefetch) or null
     const int8_t *qlut;            // [N][K/4][16]
     const float *lut_scales, *lut_biases;  // [N][K/ags]
     void *C;                       // [N][ldc]
-    float *partial;                // [N][nrsb][maxc][RSB]
-    int *counters;                 // [N][nrsb]
     int K, ldc, row_begin, row_end, c_row0, bits;
-    int nrsb, rsb0, nchunk, nblocks;
+    int nrsb, rsb0, nchunk;
     int ags, agq_shift, ck;        // act group size, log2(quads per act group), K per chunk
     int zp, one_scale, int_path, sd, out_f16;
     int blk_bytes;                 // bytes per block (weights + scales)
-    int nslots;                    // stage ring slots (>= 1)
-    int maxc;                      // scratch slots per super-block
-    int max_rsb_cta;               // super-blocks a CTA range can touch
-    int lut_bytes;                 // K*4 (multiple of 16)
+    int cs, wpc, bpw;              // cluster size, warps per CTA, chunks per warp
+    size_t rsb_stride;
     float scale0;
-    long long *trace;              // optional [gridDim.x][8] clock64 stamps (debug), else null
+    long long *trace;
 };
 #define TMAC_TRACE(slot) do { if (p.trace) p.trace[(size_t)blockIdx.x * 8 + (slot)] = clock64(); } while (0)
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
-}
-__device__ __forceinline__ uint64_t policy_evict_first() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ uint64_t policy_evict_last() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
-// Quad lookups with the raw QLUT rows in shared memory (16 B per group, no re-ordering):
-// symmetric mode reads entries 0..7; general mode also reads 8..15 and reverses the selector
-// (code (neg=1, j) <-> LUT index 15 - j  =>  byte (7 - j) of the upper half).
-template <int PB, bool SYM> struct QuadRaw {
-    static __device__ __forceinline__ void run(const uint4 w, const uint4 *lut4 /* 4 groups */, int *acc, uint32_t wtx, uint32_t wty) {
-        if (SYM) {
-            uint32_t t[8];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint2 v = *reinterpret_cast<const uint2 *>(lut4 + k);
-                t[2 * k] = v.x; t[2 * k + 1] = v.y;
-            }
-            Quad<PB, true>::run(w, t, acc, wtx, wty);
-        } else {
-            uint32_t t[16];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint4 v = lut4[k];
-                t[4 * k] = v.x; t[4 * k + 1] = v.y;
-                t[4 * k + 2] = __byte_perm(v.w, 0, 0x0123); t[4 * k + 3] = __byte_perm(v.z, 0, 0x0123);
-            }
-            Quad<PB, false>::run(w, t, acc, wtx, wty);
-        }
-    }
-};
-
-constexpr int kG2MaxWarps = 24;                   // consumer warps per CTA (runtime: blockDim.x/32 - 1)
-
-__device__ __forceinline__ int atom_add_acq_rel_gpu(int *addr, int v) {
-    int old;
-    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(addr), "r"(v) : "memory");
-    return old;
+__device__ __forceinline__ void l2_prefetch_bulk(const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster_f32(float *local_ptr, uint32_t rank, float v) {
+    uint32_t laddr = (uint32_t)__cvta_generic_to_shared(local_ptr), raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(rank));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(raddr), "f"(v) : "memory");
 }
 
-// Work unit = a pair of quads (8 K-groups = 32 K positions) of one block; unit u of the CTA goes
-// to consumer warp u % NW.  With 16 warps and ~75 units per CTA the static schedule is within 7 %
-// of perfect balance while every warp still follows the order in which the stream arrives.
+constexpr int kG3MaxWarps = 8;
+
 template <int PB, bool SYM, int QCH>
-__global__ void __launch_bounds__((kG2MaxWarps + 1) * 32) gemv2_kernel(const Gemv2Params p, const uint32_t wtx, const uint32_t wty) {
+__global__ void __launch_bounds__(kG3MaxWarps * 32, 3) gemv3_kernel(const Gemv3Params p, const uint32_t wtx, const uint32_t wty) {
     constexpr int RW = 8 / PB;
     constexpr int RSB = 32 * RW;
-    constexpr int UPB = QCH / 2;                  // units per block
+    constexpr int TB = SYM ? 8 : 16;              // table bytes per group in shared memory
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int NW = (blockDim.x >> 5) - 1;         // consumer warps; warp NW is the producer
-    const int G = gridDim.x, cta = blockIdx.x, n = blockIdx.y;
-    const int b0 = (int)((long long)p.nblocks * cta / G), b1 = (int)((long long)p.nblocks * (cta + 1) / G);
-    const int nb = b1 - b0;
-    const int S = p.nslots;
-    const int rsb_first = b0 / p.nchunk;
-    const int nag = p.K / p.ags;
-
-    // ---- shared memory carve-up (host computes the same sizes) ----
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem);          // [S]
-    uint64_t *empty = full + S;                                   // [S]
-    uint64_t *lut_bar = empty + S;                                // [1]
-    unsigned char *stage = smem + (((size_t)(2 * S + 1) * 8 + 127) & ~(size_t)127);   // [S][blk_bytes]
-    uint4 *lut_s = reinterpret_cast<uint4 *>(stage + (size_t)S * p.blk_bytes);        // [K/4] raw QLUT rows
-    float *ls_s = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(lut_s) + p.lut_bytes);   // [nag]
-    float *lb_s = ls_s + nag;                                                          // [nag]
-    float *red = lb_s + nag;                                                           // [max_rsb_cta][NW][RSB]
-    __shared__ int s_last[8];
+    const int WPC = p.wpc;
+    const int rank = (p.cs > 1) ? (int)cluster_ctarank() : 0;
+    const int rsb = blockIdx.x / p.cs, n = blockIdx.y;
+    // shared memory: [WPC] warp-private tables (QCH*4 groups * TB) | red [WPC][RSB] | cl [CS][RSB] (leader)
+    unsigned char *tab_all = smem;
+    const int tab_bytes = QCH * 4 * TB;
+    float *red = reinterpret_cast<float *>(smem + (size_t)WPC * tab_bytes);
+    float *cl = red + (size_t)WPC * RSB;
 
     if (tid == 0) TMAC_TRACE(0);
-    if (warp == NW) {
-        // ---- producer warp: barriers + the whole weight stream of this CTA, issued lane-parallel,
-        //      before any dependency wait (weights are static).
-        for (int s = lane; s < S; s += 32) { mbar_init(full + s, 1); mbar_init(empty + s, UPB); }
-        if (lane == 0) mbar_init(lut_bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        __syncwarp();
-        const uint64_t pol_w = policy_evict_first();
-        const unsigned char *src = p.W + (size_t)b0 * p.blk_bytes;
-        const int first = nb < S ? nb : S;
-        for (int i = lane; i < first; i += 32) {
-            mbar_expect_tx(full + i, (uint32_t)p.blk_bytes);
-            bulk_g2s(stage + (size_t)i * p.blk_bytes, src + (size_t)i * p.blk_bytes, (uint32_t)p.blk_bytes, full + i, pol_w);
-        }
-        if (lane == 0) TMAC_TRACE(2);
-    } else {
-        for (int i = tid; i < p.max_rsb_cta * NW * RSB; i += NW * 32) red[i] = 0.f;
-    }
-    __syncthreads();
-    pdl_launch_dependents();    // the next kernel in the stream may start its own weight prefetch
-    if (tid == 0) TMAC_TRACE(1);
+    pdl_launch_dependents();                      // the next launch may start its weight loads now
 
-    if (warp == NW) {
-        if (lane == 0 && nb > 0) {
-            pdl_wait();                                       // the LUT comes from the previous kernel
-            const uint64_t pol_l = policy_evict_last(), pol_w = policy_evict_first();
-            mbar_expect_tx(lut_bar, (uint32_t)p.lut_bytes);
-            bulk_g2s(lut_s, p.qlut + (size_t)n * p.K * 4, (uint32_t)p.lut_bytes, lut_bar, pol_l);
-            const unsigned char *src = p.W + (size_t)b0 * p.blk_bytes;
-            for (int i = S; i < nb; ++i) {                    // ring reuse (ranges larger than the ring)
-                const int s = i % S;
-                mbar_wait(empty + s, (uint32_t)(((i / S) - 1) & 1));
-                mbar_expect_tx(full + s, (uint32_t)p.blk_bytes);
-                bulk_g2s(stage + (size_t)s * p.blk_bytes, src + (size_t)i * p.blk_bytes, (uint32_t)p.blk_bytes, full + s, pol_w);
-            }
-        }
-    } else {
-        // ================= consumer warps =================
-        pdl_wait();
-        {
-            const float *lsg = p.lut_scales + (size_t)n * nag, *lbg = p.lut_biases + (size_t)n * nag;
-            for (int a = tid; a < nag; a += NW * 32) { ls_s[a] = __ldg(lsg + a); lb_s[a] = __ldg(lbg + a); }
-            asm volatile("bar.sync 1, %0;" ::"r"(NW * 32) : "memory");
-        }
-        if (tid == 0) TMAC_TRACE(3);
-        float cacc[RW];
-        int iacc[RW];
+    const int c_first = (rank * WPC + warp) * p.bpw;
+    const int c_end = min(p.nchunk, c_first + p.bpw);
+    const unsigned char *rsb_base = p.W + (size_t)rsb * p.rsb_stride;
+    const int nag = p.K / p.ags;
+
+    // ---- first chunk's weights: issued before the dependency wait -----------------------------
+    uint4 wv[QCH];
+    uint2 sraw = make_uint2(0, 0), zraw = make_uint2(0, 0);   // fp16 x RW (sd == 2) fast path
+    float sc[RW], zr[RW];
+    auto load_block = [&](int c) {
+        const unsigned char *blk = rsb_base + (size_t)c * p.blk_bytes;
+        const uint4 *wp = reinterpret_cast<const uint4 *>(blk) + lane;
 #pragma unroll
-        for (int i = 0; i < RW; ++i) { cacc[i] = 0.f; iacc[i] = 0; }
-        int cur_rsb = -1;
-        bool lut_ready = false;
-        const int nu = nb * UPB;
-        for (int u = warp; u < nu; u += NW) {
-            const int bi = u / UPB, q0 = (u - bi * UPB) * 2;
-            const int b = b0 + bi;
-            const int rsb = b / p.nchunk, c = b - rsb * p.nchunk;
-            if (rsb != cur_rsb) {
-                if (cur_rsb >= 0) {
-                    float *r = red + ((size_t)(cur_rsb - rsb_first) * NW + warp) * RSB + lane * RW;
-#pragma unroll
-                    for (int i = 0; i < RW; ++i) { r[i] = p.int_path ? __int_as_float(iacc[i]) : cacc[i]; cacc[i] = 0.f; iacc[i] = 0; }
-                }
-                cur_rsb = rsb;
-            }
-            const int slot = bi % S;
-            mbar_wait(full + slot, (uint32_t)((bi / S) & 1));
-            if (tid == 0 && u == 0) TMAC_TRACE(4);
-            const unsigned char *blk = stage + (size_t)slot * p.blk_bytes;
-            const uint4 *wp = reinterpret_cast<const uint4 *>(blk) + lane + q0 * 32;
-            const uint4 w0 = wp[0], w1 = wp[32];
-            float sc[RW], zr[RW];
-            if (!p.one_scale) {
-                const unsigned char *sp = blk + (size_t)QCH * 512;
+        for (int q = 0; q < QCH; ++q) wv[q] = ldg_stream(wp + q * 32);
+        if (!p.one_scale) {
+            const unsigned char *sp = blk + (size_t)QCH * 512;
+            if (p.sd == 2 && RW == 4) {
+                sraw = __ldg(reinterpret_cast<const uint2 *>(sp) + lane);
+                if (p.zp) zraw = __ldg(reinterpret_cast<const uint2 *>(sp + (size_t)RSB * 2) + lane);
+            } else {
 #pragma unroll
                 for (int i = 0; i < RW; ++i) {
                     sc[i] = load_scale(sp, p.sd, lane * RW + i);
                     zr[i] = p.zp ? load_scale(sp + (size_t)RSB * p.sd, p.sd, lane * RW + i) : 0.f;
                 }
-            } else {
-#pragma unroll
-                for (int i = 0; i < RW; ++i) { sc[i] = p.scale0; zr[i] = 0.f; }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + slot);          // this unit's stage bytes are in registers
-            if (!lut_ready) { mbar_wait(lut_bar, 0); lut_ready = true; }
-            const uint4 *lq = lut_s + ((size_t)c * QCH + q0) * 4;
-            if (p.int_path) {
-                QuadRaw<PB, SYM>::run(w0, lq, iacc, wtx, wty);
-                QuadRaw<PB, SYM>::run(w1, lq + 4, iacc, wtx, wty);
-            } else {
-                // a pair never straddles an activation group unless ags == 32 (one quad pair == one group)
-                int ia[RW];
-#pragma unroll
-                for (int i = 0; i < RW; ++i) ia[i] = 0;
-                QuadRaw<PB, SYM>::run(w0, lq, ia, wtx, wty);
-                QuadRaw<PB, SYM>::run(w1, lq + 4, ia, wtx, wty);
-                const int ag = (c * QCH + q0) >> p.agq_shift;
-                const float lsv = ls_s[ag];
-                // the chunk's bias sum is charged once per (row, chunk): by the unit with q0 == 0
-                float lbsum = 0.f;
-                if (q0 == 0) {
-                    const int a1 = ((c + 1) * QCH) >> p.agq_shift;
-                    for (int a = ag; a < a1; ++a) lbsum += lb_s[a];
-                }
-#pragma unroll
-                for (int i = 0; i < RW; ++i) {
-                    float v = fmaf(0.5f * sc[i], fmaf(lsv, (float)ia[i], lbsum), cacc[i]);
-                    if (p.zp) v = fmaf(zr[i], lbsum, v);
-                    cacc[i] = v;
-                }
             }
         }
-        if (tid == 0) TMAC_TRACE(5);
-        if (cur_rsb >= 0) {
-            float *r = red + ((size_t)(cur_rsb - rsb_first) * NW + warp) * RSB + lane * RW;
+    };
+    if (c_first < c_end) {
+        load_block(c_first);
+        if (p.Wnext && lane == 0)                  // pull the next tensor's blocks of this warp into L2
+            l2_prefetch_bulk(p.Wnext + (size_t)rsb * p.rsb_stride + (size_t)c_first * p.blk_bytes,
+                             (uint32_t)((c_end - c_first) * p.blk_bytes));
+    }
+    if (tid == 0) TMAC_TRACE(1);
+    pdl_wait();                                   // LUT / LUT scales come from the previous kernel
+    if (tid == 0) TMAC_TRACE(2);
+
+    float cacc[RW];
+    int iacc[RW];
 #pragma unroll
-            for (int i = 0; i < RW; ++i) r[i] = p.int_path ? __int_as_float(iacc[i]) : cacc[i];
+    for (int i = 0; i < RW; ++i) { cacc[i] = 0.f; iacc[i] = 0; }
+    unsigned char *tab = tab_all + (size_t)warp * tab_bytes;
+    const uint4 *qrow = reinterpret_cast<const uint4 *>(p.qlut + (size_t)n * p.K * 4);
+    const float *lsg = p.lut_scales + (size_t)n * nag, *lbg = p.lut_biases + (size_t)n * nag;
+    const int agq = 1 << p.agq_shift;
+
+    for (int c = c_first; c < c_end; ++c) {
+        // ---- LUT slice of this chunk -> warp-private table -----------------------------------
+        if (lane < QCH * 4) {
+            const uint4 L = __ldg(qrow + (size_t)c * QCH * 4 + lane);
+            if (SYM) reinterpret_cast<uint2 *>(tab)[lane] = make_uint2(L.x, L.y);
+            else reinterpret_cast<uint4 *>(tab)[lane] = make_uint4(L.x, L.y, __byte_perm(L.w, 0, 0x0123), __byte_perm(L.z, 0, 0x0123));
         }
+        float ls_l = 0.f, lb_l = 0.f;             // lane a holds the a-th act group of the chunk
+        const int ag0 = (c * QCH) >> p.agq_shift;
+        if (!p.int_path && lane < (QCH >> p.agq_shift)) { ls_l = __ldg(lsg + ag0 + lane); lb_l = __ldg(lbg + ag0 + lane); }
+        if (p.sd == 2 && RW == 4 && !p.one_scale) {
+            const __half2 s01 = *reinterpret_cast<const __half2 *>(&sraw.x), s23 = *reinterpret_cast<const __half2 *>(&sraw.y);
+            const float2 f01 = __half22float2(s01), f23 = __half22float2(s23);
+            sc[0] = f01.x; sc[1] = f01.y; sc[2] = f23.x; sc[3] = f23.y;
+            const __half2 z01 = *reinterpret_cast<const __half2 *>(&zraw.x), z23 = *reinterpret_cast<const __half2 *>(&zraw.y);
+            const float2 g01 = __half22float2(z01), g23 = __half22float2(z23);
+            zr[0] = g01.x; zr[1] = g01.y; zr[2] = g23.x; zr[3] = g23.y;
+        } else if (p.one_scale) {
+#pragma unroll
+            for (int i = 0; i < RW; ++i) { sc[i] = p.scale0; zr[i] = 0.f; }
+        }
+        __syncwarp();
+        if (tid == 0 && c == c_first) TMAC_TRACE(3);
+        float facc[RW];
+#pragma unroll
+        for (int i = 0; i < RW; ++i) facc[i] = 0.f;
+        float lbsum = 0.f;
+#pragma unroll
+        for (int q = 0; q < QCH; ++q) {
+            uint32_t t[SYM ? 8 : 16];
+            if (SYM) {
+                const uint4 a = reinterpret_cast<const uint4 *>(tab)[2 * q], b2 = reinterpret_cast<const uint4 *>(tab)[2 * q + 1];
+                t[0] = a.x; t[1] = a.y; t[2] = a.z; t[3] = a.w; t[4] = b2.x; t[5] = b2.y; t[6] = b2.z; t[7] = b2.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint4 a = reinterpret_cast<const uint4 *>(tab)[4 * q + k];
+                    t[4 * k] = a.x; t[4 * k + 1] = a.y; t[4 * k + 2] = a.z; t[4 * k + 3] = a.w;
+                }
+            }
+            Quad<PB, SYM>::run(wv[q], t, iacc, wtx, wty);
+            if (!p.int_path && (((q + 1) & (agq - 1)) == 0 || q == QCH - 1)) {
+                const int a = q >> p.agq_shift;
+                const float lsv = __shfl_sync(0xffffffffu, ls_l, a);
+                lbsum += __shfl_sync(0xffffffffu, lb_l, a);
+#pragma unroll
+                for (int i = 0; i < RW; ++i) { facc[i] = fmaf(lsv, (float)iacc[i], facc[i]); iacc[i] = 0; }
+            }
+        }
+        if (!p.int_path) {
+#pragma unroll
+            for (int i = 0; i < RW; ++i) {
+                float v = fmaf(0.5f * sc[i], facc[i] + lbsum, cacc[i]);
+                if (p.zp) v = fmaf(zr[i], lbsum, v);
+                cacc[i] = v;
+            }
+        }
+        __syncwarp();                              // table is rewritten by the next chunk
+        if (c + 1 < c_end) load_block(c + 1);
+    }
+    if (tid == 0) TMAC_TRACE(4);
+
+    // ---- CTA reduction (fixed warp order) -------------------------------------------------------
+    {
+        float *r = red + (size_t)warp * RSB + lane * RW;
+#pragma unroll
+        for (int i = 0; i < RW; ++i) r[i] = p.int_path ? __int_as_float(iacc[i]) : cacc[i];
     }
     __syncthreads();
+    if (tid == 0) TMAC_TRACE(5);
+    const int nthreads = WPC * 32;
+    for (int t = tid; t < RSB; t += nthreads) {
+        float fsum = 0.f; int isum = 0;
+        for (int w = 0; w < WPC; ++w) {
+            const float v = red[(size_t)w * RSB + t];
+            if (p.int_path) isum += __float_as_int(v); else fsum += v;
+        }
+        const float mine = p.int_path ? __int_as_float(isum) : fsum;
+        if (p.cs > 1) st_cluster_f32(cl + (size_t)rank * RSB + t, 0, mine);   // into the leader's shared memory
+        else cl[t] = mine;
+    }
+    if (p.cs > 1) cluster_sync_all(); else __syncthreads();
     if (tid == 0) TMAC_TRACE(6);
-    if (nb <= 0) return;
-
-    // ---- epilogue.  Pass 1: fixed-order sum over warps for every super-block of the range;
-    //      whole super-blocks are finished, split ones publish a partial.  One release/acquire
-    //      round on the arrival counters.  Pass 2: the last arriver of a split super-block sums the
-    //      partials in CTA order.
-    const int rsb_last = (b1 - 1) / p.nchunk;
-    const int nloc = rsb_last - rsb_first + 1;
-    auto finish = [&](int r, float fsum, int isum) {
-        const int row = (p.rsb0 + r) * RSB + tid;
+    if (rank != 0) return;
+    for (int t = tid; t < RSB; t += nthreads) {
+        float fsum = 0.f; int isum = 0;
+        for (int k2 = 0; k2 < p.cs; ++k2) {
+            const float v = cl[(size_t)k2 * RSB + t];
+            if (p.int_path) isum += __float_as_int(v); else fsum += v;
+        }
+        const int row = (p.rsb0 + rsb) * RSB + t;
         if (row >= p.row_begin && row < p.row_end) {
             float out;
             if (p.int_path) {
                 // C = ((sum_b alpha_b*CBits_b) * LUT_Scales[0] + LUT_Biases[0]*alpha_0) * Scales[0]
                 // (python/t_mac/ops/qgemm.py:160,171-174); isum = sum_b 2*alpha_b*CBits_b exactly.
                 const float cb = __fmul_rn((float)isum, 0.5f);
-                const float t1 = __fmul_rn(cb, ls_s[0]);
-                const float t2 = __fmul_rn(lb_s[0], 0.5f);
+                const float t1 = __fmul_rn(cb, __ldg(lsg));
+                const float t2 = __fmul_rn(__ldg(lbg), 0.5f);
                 out = __fmul_rn(__fadd_rn(t1, t2), p.scale0);
             } else
                 out = fsum;
@@ -648,49 +584,6 @@ __global__ void __launch_bounds__((kG2MaxWarps + 1) * 32) gemv2_kernel(const Gem
             if (p.out_f16) reinterpret_cast<__half *>(p.C)[o] = __float2half_rn(out);
             else reinterpret_cast<float *>(p.C)[o] = out;
         }
-    };
-    bool any_split = false;
-    for (int r = rsb_first; r <= rsb_last; ++r) {
-        float fsum = 0.f; int isum = 0;
-        if (tid < RSB)
-            for (int w = 0; w < NW; ++w) {
-                const float v = red[((size_t)(r - rsb_first) * NW + w) * RSB + tid];
-                if (p.int_path) isum += __float_as_int(v); else fsum += v;
-            }
-        const int rb0 = r * p.nchunk, rb1 = rb0 + p.nchunk;
-        if (rb0 >= b0 && rb1 <= b1) { if (tid < RSB) finish(r, fsum, isum); continue; }
-        any_split = true;
-        const int cfirst = (int)(((long long)(rb0 + 1) * G + p.nblocks - 1) / p.nblocks) - 1;
-        float *slots = p.partial + (((size_t)n * p.nrsb + r) * p.maxc) * RSB;
-        if (tid < RSB) slots[(size_t)(cta - cfirst) * RSB + tid] = p.int_path ? __int_as_float(isum) : fsum;
-    }
-    if (!any_split) { if (tid == 0) TMAC_TRACE(7); return; }
-    __syncthreads();                    // all partial stores of this CTA happen-before the release below
-    if (tid < nloc) {
-        const int r = rsb_first + tid;
-        const int rb0 = r * p.nchunk, rb1 = rb0 + p.nchunk;
-        int last = 0;
-        if (!(rb0 >= b0 && rb1 <= b1)) {
-            const int cfirst = (int)(((long long)(rb0 + 1) * G + p.nblocks - 1) / p.nblocks) - 1;
-            const int clast = (int)(((long long)rb1 * G + p.nblocks - 1) / p.nblocks) - 1;
-            const int nctr = clast - cfirst + 1;
-            int *ctr = p.counters + (size_t)n * p.nrsb + r;
-            const int t = atom_add_acq_rel_gpu(ctr, 1);
-            if (t == nctr - 1) { last = nctr; *ctr = 0; }     // self-reset for the next launch
-        }
-        s_last[tid & 7] = last;
-    }
-    __syncthreads();
-    for (int r = rsb_first; r <= rsb_last; ++r) {
-        const int nctr = s_last[(r - rsb_first) & 7];
-        if (nctr == 0 || tid >= RSB) continue;
-        const float *slots = p.partial + (((size_t)n * p.nrsb + r) * p.maxc) * RSB;
-        float fsum = 0.f; int isum = 0;
-        for (int k2 = 0; k2 < nctr; ++k2) {
-            const float v = __ldcg(slots + (size_t)k2 * RSB + tid);
-            if (p.int_path) isum += __float_as_int(v); else fsum += v;
-        }
-        finish(r, fsum, isum);
     }
     if (tid == 0) TMAC_TRACE(7);
 }

@@ -18,11 +18,13 @@ tb.preprocessor(bench.K, 1, 64, x, ls, lb, q)
 for it in range(3):
     tb.qgemm_lut(wt, 1, q, ls, lb, out)
     tb.check(lib.tmac_b200_sync(), "sync")
-buf = np.zeros((512, 8), np.int64)
-n = lib.tmac_b200_debug_trace(buf.ctypes.data, 512)
+buf = np.zeros((4096, 8), np.int64)
+n = lib.tmac_b200_debug_trace(buf.ctypes.data, 4096)
 t = buf[:n].astype(np.float64)
 d = t - t[:, :1]
-names = ["entry", "init+sync", "tma issued", "wait+lslb", "first full", "loop done", "all done", "epilogue"]
+d[d < 0] = np.nan
+import warnings; warnings.simplefilter("ignore")
+names = ["entry", "loads issued", "pdl wait done", "lut staged", "loop done", "cta reduced", "cluster synced", "stored(leader)"]
 print("ctas", n, "SM cycles since entry (mean / min / max):")
 for i, nm in enumerate(names):
-    print("  %-12s %8.0f %8.0f %8.0f" % (nm, d[:, i].mean(), d[:, i].min(), d[:, i].max()))
+    print("  %-12s %8.0f %8.0f %8.0f" % (nm, np.nanmean(d[:, i]), np.nanmin(d[:, i]), np.nanmax(d[:, i])))
