@@ -151,18 +151,24 @@ gemv_fn pick_gemv(int pb, bool sym, int qch) {
 }
 
 typedef void (*gemv3_fn)(const Gemv3Params, const uint32_t, const uint32_t);
-template <int PB, bool SYM> gemv3_fn pick3_qch(int qch) {
-    switch (qch) {
-        case 2: return gemv3_kernel<PB, SYM, 2>;
-        case 4: return gemv3_kernel<PB, SYM, 4>;
-        case 8: return gemv3_kernel<PB, SYM, 8>;
+template <int PB, bool SYM> gemv3_fn pick3_qa(int qch, int agq) {
+    switch (qch * 16 + agq) {
+        case 8 * 16 + 8: return gemv3_kernel<PB, SYM, 8, 8>;
+        case 8 * 16 + 4: return gemv3_kernel<PB, SYM, 8, 4>;
+        case 8 * 16 + 2: return gemv3_kernel<PB, SYM, 8, 2>;
+        case 8 * 16 + 0: return gemv3_kernel<PB, SYM, 8, 0>;
+        case 4 * 16 + 4: return gemv3_kernel<PB, SYM, 4, 4>;
+        case 4 * 16 + 2: return gemv3_kernel<PB, SYM, 4, 2>;
+        case 4 * 16 + 0: return gemv3_kernel<PB, SYM, 4, 0>;
+        case 2 * 16 + 2: return gemv3_kernel<PB, SYM, 2, 2>;
+        case 2 * 16 + 0: return gemv3_kernel<PB, SYM, 2, 0>;
     }
     return nullptr;
 }
-gemv3_fn pick_gemv3(int pb, bool sym, int qch) {
-    if (pb == 4) return sym ? pick3_qch<4, true>(qch) : pick3_qch<4, false>(qch);
-    if (pb == 2) return sym ? pick3_qch<2, true>(qch) : pick3_qch<2, false>(qch);
-    if (pb == 1) return sym ? pick3_qch<1, true>(qch) : pick3_qch<1, false>(qch);
+gemv3_fn pick_gemv3(int pb, bool sym, int qch, int agq) {
+    if (pb == 4) return sym ? pick3_qa<4, true>(qch, agq) : pick3_qa<4, false>(qch, agq);
+    if (pb == 2) return sym ? pick3_qa<2, true>(qch, agq) : pick3_qa<2, false>(qch, agq);
+    if (pb == 1) return sym ? pick3_qa<1, true>(qch, agq) : pick3_qa<1, false>(qch, agq);
     return nullptr;
 }
 
@@ -209,9 +215,9 @@ int launch_gemv3(const Resident &R, int row_begin, int row_end, int N, const int
     p.qlut = qlut; p.lut_scales = ls; p.lut_biases = lb; p.C = C;
     p.K = L.K; p.ldc = ldc; p.row_begin = row_begin; p.row_end = row_end; p.c_row0 = c_row0; p.bits = L.bits;
     p.nrsb = nrsb; p.rsb0 = rsb0; p.nchunk = L.nchunk;
-    p.ags = L.act_group_size; p.ck = L.ck;
-    p.agq_shift = ilog2(std::max(1, std::min(L.act_group_size, L.ck) / 16));
-    p.zp = L.zp; p.one_scale = L.one_scale; p.int_path = int_path ? 1 : 0; p.sd = L.sd; p.out_f16 = out_f16;
+    p.ags = L.act_group_size;
+    const int agq = int_path ? 0 : std::min(L.act_group_size, L.ck) / 16;
+    p.zp = L.zp; p.one_scale = L.one_scale; p.sd = L.sd; p.out_f16 = out_f16;
     p.blk_bytes = (int)L.blk; p.scale0 = L.scale0; p.rsb_stride = L.rsb_stride;
     choose_decomposition(nrsb, L.nchunk, N, &p.cs, &p.wpc, &p.bpw);
     if (g.cs_override > 0) { p.cs = g.cs_override; }
@@ -222,9 +228,10 @@ int launch_gemv3(const Resident &R, int row_begin, int row_end, int N, const int
         p.trace = (long long *)g.d_trace.p;
         g.trace_ctas = nrsb * p.cs;
     }
-    gemv3_fn fn = pick_gemv3(L.pb, sym, L.qch);
-    if (!fn) return fail("qgemm_lut: unsupported chunking (qch=" + std::to_string(L.qch) + ")");
-    const size_t smem = (size_t)p.wpc * L.qch * 4 * (sym ? 8 : 16) + (size_t)p.wpc * L.rsb * 4 + (size_t)p.cs * L.rsb * 4;
+    gemv3_fn fn = pick_gemv3(L.pb, sym, L.qch, agq);
+    if (!fn) return fail("qgemm_lut: unsupported chunking (qch=" + std::to_string(L.qch) + ", agq=" + std::to_string(agq) + ")");
+    const size_t smem = (size_t)p.cs * L.rsb * 4 +
+                        std::max((size_t)p.wpc * (L.blk + (size_t)L.qch * 4 * (sym ? 8 : 16)), (size_t)p.wpc * L.rsb * 4);
     if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     uint32_t wtx, wty;
     plane_weight_regs(L.bits, sym, &wtx, &wty);
@@ -317,13 +324,21 @@ int launch_preprocessor(int K, int N, int ags, int dtype, const void *B, float *
     const int ng = agb * (ags / 4);
     const size_t smem = (size_t)agb * 4 + (size_t)ng * 4 + (size_t)(ng / 8 + 1) * 4;
     if (smem > 200 * 1024) return fail("preprocessor: activation group too large");
-    dim3 grid(gx, N);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(gx, N, 1);
+    cfg.blockDim = dim3(kPreThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = g.stream();
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g.use_pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
     if (dtype == TMAC_B200_F16) {
         if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute((const void *)preprocessor_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        preprocessor_kernel<__half><<<grid, kPreThreads, smem, g.stream()>>>((const __half *)B, ls, lb, qlut, K, ags, agb);
+        CUDA_OK(cudaLaunchKernelEx(&cfg, preprocessor_kernel<__half>, (const __half *)B, ls, lb, qlut, K, ags, agb));
     } else {
         if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute((const void *)preprocessor_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        preprocessor_kernel<float><<<grid, kPreThreads, smem, g.stream()>>>((const float *)B, ls, lb, qlut, K, ags, agb);
+        CUDA_OK(cudaLaunchKernelEx(&cfg, preprocessor_kernel<float>, (const float *)B, ls, lb, qlut, K, ags, agb));
     }
     CUDA_OK(cudaGetLastError());
     if (g.sym_qluts.size() > 4096) g.sym_qluts.clear();

@@ -367,15 +367,19 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_kernel(const GemvParams p, 
 //                   memory in rank order -- deterministic, no global scratch, no atomics.
 //   warps         : warp-autonomous.  Warp w of CTA rank r owns the `bpw` consecutive K chunks
 //                   starting at (r*WPC + w)*bpw.  Every lane owns RW rows (no cross-lane reduce).
-//   memory        : each lane issues its 128-bit weight loads for the first chunk BEFORE
-//                   griddepcontrol.wait (weights are static, so under programmatic dependent
-//                   launch they overlap the previous kernel's tail); the activation LUT slice of
-//                   the chunk (32 groups x 16 B) is fetched after the wait, compacted into a
-//                   warp-private shared-memory table and read back as broadcast LDS.
-//                   One lane per warp also issues cp.async.bulk.prefetch.L2 for the same block of
-//                   the NEXT tensor (software pipelining of the HBM stream across launches).
+//   memory        : each warp copies its (contiguous, 16-byte aligned) block HBM -> its private
+//                   shared-memory stage with cp.async (LDGSTS, L2 evict-first) BEFORE
+//                   griddepcontrol.wait: weights are static, so under programmatic dependent launch
+//                   the stream of launch i+1 overlaps the math of launch i, and because the bytes
+//                   wait in shared memory (not registers) both launches fit on an SM together.
+//                   The activation LUT slice of the chunk (QCH*4 groups x 16 B) is fetched after the
+//                   wait into a warp-private table and read back as broadcast LDS.128.
+//                   One lane per warp can also issue cp.async.bulk.prefetch.L2 for the same block of
+//                   the NEXT tensor (optional hint).
 //   arithmetic    : Quad<PB,SYM> (PRMT lookups + DP4A), per-act-group fp32 scale, per-chunk weight
 //                   scale / zero point, exactly the algebra of tbl.cc:435-529 re-associated.
+//   template AGQ  : quads per activation group inside a chunk (2, 4, 8); 0 = integer path
+//                   (one LUT scale for the whole row, python/t_mac/ops/qgemm.py:93-96).
 // ==========================================================================================
 struct Gemv3Params {
     const unsigned char *W;        // first block of the launch's first row super-block
@@ -385,21 +389,38 @@ struct Gemv3Params {
     void *C;                       // [N][ldc]
     int K, ldc, row_begin, row_end, c_row0, bits;
     int nrsb, rsb0, nchunk;
-    int ags, agq_shift, ck;        // act group size, log2(quads per act group), K per chunk
-    int zp, one_scale, int_path, sd, out_f16;
+    int ags;
+    int zp, one_scale, sd, out_f16;
     int blk_bytes;                 // bytes per block (weights + scales)
     int cs, wpc, bpw;              // cluster size, warps per CTA, chunks per warp
     size_t rsb_stride;
     float scale0;
     long long *trace;
 };
-#define TMAC_TRACE(slot) do { if (p.trace) p.trace[(size_t)blockIdx.x * 8 + (slot)] = clock64(); } while (0)
+#ifdef TMAC_ENABLE_TRACE
+__device__ __forceinline__ long long globaltimer_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// slots 0..6: clock64 (SM cycles) since entry; slot 7: globaltimer (ns) at entry.
+#define TMAC_TRACE(slot) do { if (p.trace) p.trace[(size_t)blockIdx.x * 8 + (slot)] = ((slot) == 7) ? globaltimer_ns() : clock64(); } while (0)
+#else
+#define TMAC_TRACE(slot) do { } while (0)
+#endif
 
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void l2_prefetch_bulk(const void *src, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, uint64_t pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -412,55 +433,43 @@ __device__ __forceinline__ void st_cluster_f32(float *local_ptr, uint32_t rank, 
 
 constexpr int kG3MaxWarps = 8;
 
-template <int PB, bool SYM, int QCH>
-__global__ void __launch_bounds__(kG3MaxWarps * 32, 3) gemv3_kernel(const Gemv3Params p, const uint32_t wtx, const uint32_t wty) {
+template <int PB, bool SYM, int QCH, int AGQ>
+__global__ void __launch_bounds__(kG3MaxWarps * 32, 5) gemv3_kernel(const Gemv3Params p, const uint32_t wtx, const uint32_t wty) {
     constexpr int RW = 8 / PB;
     constexpr int RSB = 32 * RW;
     constexpr int TB = SYM ? 8 : 16;              // table bytes per group in shared memory
+    constexpr bool INT_PATH = (AGQ == 0);
+    constexpr int NAG = INT_PATH ? 1 : QCH / AGQ; // activation groups per chunk
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int WPC = p.wpc;
     const int rank = (p.cs > 1) ? (int)cluster_ctarank() : 0;
     const int rsb = blockIdx.x / p.cs, n = blockIdx.y;
-    // shared memory: [WPC] warp-private tables (QCH*4 groups * TB) | red [WPC][RSB] | cl [CS][RSB] (leader)
-    unsigned char *tab_all = smem;
+    // shared memory: cl [CS][RSB] (cluster partials, leader only) | per warp: stage (blk_bytes) + table
+    // (QCH*4*TB).  The CTA reduction buffer red [WPC][RSB] aliases the stages once they are consumed.
+    float *cl = reinterpret_cast<float *>(smem);
     const int tab_bytes = QCH * 4 * TB;
-    float *red = reinterpret_cast<float *>(smem + (size_t)WPC * tab_bytes);
-    float *cl = red + (size_t)WPC * RSB;
+    const int per_warp = p.blk_bytes + tab_bytes;
+    unsigned char *wbase = smem + (size_t)p.cs * RSB * 4;
+    unsigned char *stage = wbase + (size_t)warp * per_warp;
+    unsigned char *tab = stage + p.blk_bytes;
+    float *red = reinterpret_cast<float *>(wbase);
 
-    if (tid == 0) TMAC_TRACE(0);
-    pdl_launch_dependents();                      // the next launch may start its weight loads now
+    if (tid == 0) { TMAC_TRACE(0); TMAC_TRACE(7); }
+    pdl_launch_dependents();                      // the next launch may start its weight stream now
 
     const int c_first = (rank * WPC + warp) * p.bpw;
     const int c_end = min(p.nchunk, c_first + p.bpw);
     const unsigned char *rsb_base = p.W + (size_t)rsb * p.rsb_stride;
     const int nag = p.K / p.ags;
+    const uint64_t pol = policy_evict_first();
+    const int n16 = p.blk_bytes >> 4;
 
-    // ---- first chunk's weights: issued before the dependency wait -----------------------------
-    uint4 wv[QCH];
-    uint2 sraw = make_uint2(0, 0), zraw = make_uint2(0, 0);   // fp16 x RW (sd == 2) fast path
-    float sc[RW], zr[RW];
-    auto load_block = [&](int c) {
-        const unsigned char *blk = rsb_base + (size_t)c * p.blk_bytes;
-        const uint4 *wp = reinterpret_cast<const uint4 *>(blk) + lane;
-#pragma unroll
-        for (int q = 0; q < QCH; ++q) wv[q] = ldg_stream(wp + q * 32);
-        if (!p.one_scale) {
-            const unsigned char *sp = blk + (size_t)QCH * 512;
-            if (p.sd == 2 && RW == 4) {
-                sraw = __ldg(reinterpret_cast<const uint2 *>(sp) + lane);
-                if (p.zp) zraw = __ldg(reinterpret_cast<const uint2 *>(sp + (size_t)RSB * 2) + lane);
-            } else {
-#pragma unroll
-                for (int i = 0; i < RW; ++i) {
-                    sc[i] = load_scale(sp, p.sd, lane * RW + i);
-                    zr[i] = p.zp ? load_scale(sp + (size_t)RSB * p.sd, p.sd, lane * RW + i) : 0.f;
-                }
-            }
-        }
-    };
+    // ---- first chunk: HBM -> shared, issued before the dependency wait -------------------------
     if (c_first < c_end) {
-        load_block(c_first);
+        const unsigned char *src = rsb_base + (size_t)c_first * p.blk_bytes;
+        for (int i = lane; i < n16; i += 32) cp_async16(stage + i * 16, src + i * 16, pol);
+        cp_async_commit();
         if (p.Wnext && lane == 0)                  // pull the next tensor's blocks of this warp into L2
             l2_prefetch_bulk(p.Wnext + (size_t)rsb * p.rsb_stride + (size_t)c_first * p.blk_bytes,
                              (uint32_t)((c_end - c_first) * p.blk_bytes));
@@ -473,40 +482,31 @@ __global__ void __launch_bounds__(kG3MaxWarps * 32, 3) gemv3_kernel(const Gemv3P
     int iacc[RW];
 #pragma unroll
     for (int i = 0; i < RW; ++i) { cacc[i] = 0.f; iacc[i] = 0; }
-    unsigned char *tab = tab_all + (size_t)warp * tab_bytes;
     const uint4 *qrow = reinterpret_cast<const uint4 *>(p.qlut + (size_t)n * p.K * 4);
     const float *lsg = p.lut_scales + (size_t)n * nag, *lbg = p.lut_biases + (size_t)n * nag;
-    const int agq = 1 << p.agq_shift;
 
     for (int c = c_first; c < c_end; ++c) {
-        // ---- LUT slice of this chunk -> warp-private table -----------------------------------
+        // ---- LUT slice of this chunk -> warp-private table (lane = group) ---------------------
         if (lane < QCH * 4) {
             const uint4 L = __ldg(qrow + (size_t)c * QCH * 4 + lane);
             if (SYM) reinterpret_cast<uint2 *>(tab)[lane] = make_uint2(L.x, L.y);
             else reinterpret_cast<uint4 *>(tab)[lane] = make_uint4(L.x, L.y, __byte_perm(L.w, 0, 0x0123), __byte_perm(L.z, 0, 0x0123));
         }
-        float ls_l = 0.f, lb_l = 0.f;             // lane a holds the a-th act group of the chunk
-        const int ag0 = (c * QCH) >> p.agq_shift;
-        if (!p.int_path && lane < (QCH >> p.agq_shift)) { ls_l = __ldg(lsg + ag0 + lane); lb_l = __ldg(lbg + ag0 + lane); }
-        if (p.sd == 2 && RW == 4 && !p.one_scale) {
-            const __half2 s01 = *reinterpret_cast<const __half2 *>(&sraw.x), s23 = *reinterpret_cast<const __half2 *>(&sraw.y);
-            const float2 f01 = __half22float2(s01), f23 = __half22float2(s23);
-            sc[0] = f01.x; sc[1] = f01.y; sc[2] = f23.x; sc[3] = f23.y;
-            const __half2 z01 = *reinterpret_cast<const __half2 *>(&zraw.x), z23 = *reinterpret_cast<const __half2 *>(&zraw.y);
-            const float2 g01 = __half22float2(z01), g23 = __half22float2(z23);
-            zr[0] = g01.x; zr[1] = g01.y; zr[2] = g23.x; zr[3] = g23.y;
-        } else if (p.one_scale) {
+        float lsv[NAG], lbsum = 0.f;
+        if (!INT_PATH) {
 #pragma unroll
-            for (int i = 0; i < RW; ++i) { sc[i] = p.scale0; zr[i] = 0.f; }
+            for (int a = 0; a < NAG; ++a) { lsv[a] = __ldg(lsg + c * NAG + a); lbsum += __ldg(lbg + c * NAG + a); }
         }
+        cp_async_wait_all();
         __syncwarp();
         if (tid == 0 && c == c_first) TMAC_TRACE(3);
+        const uint4 *wp = reinterpret_cast<const uint4 *>(stage) + lane;
         float facc[RW];
 #pragma unroll
         for (int i = 0; i < RW; ++i) facc[i] = 0.f;
-        float lbsum = 0.f;
 #pragma unroll
         for (int q = 0; q < QCH; ++q) {
+            const uint4 wq = wp[q * 32];
             uint32_t t[SYM ? 8 : 16];
             if (SYM) {
                 const uint4 a = reinterpret_cast<const uint4 *>(tab)[2 * q], b2 = reinterpret_cast<const uint4 *>(tab)[2 * q + 1];
@@ -518,33 +518,37 @@ __global__ void __launch_bounds__(kG3MaxWarps * 32, 3) gemv3_kernel(const Gemv3P
                     t[4 * k] = a.x; t[4 * k + 1] = a.y; t[4 * k + 2] = a.z; t[4 * k + 3] = a.w;
                 }
             }
-            Quad<PB, SYM>::run(wv[q], t, iacc, wtx, wty);
-            if (!p.int_path && (((q + 1) & (agq - 1)) == 0 || q == QCH - 1)) {
-                const int a = q >> p.agq_shift;
-                const float lsv = __shfl_sync(0xffffffffu, ls_l, a);
-                lbsum += __shfl_sync(0xffffffffu, lb_l, a);
+            Quad<PB, SYM>::run(wq, t, iacc, wtx, wty);
+            if (!INT_PATH && ((q + 1) % (AGQ ? AGQ : 1)) == 0) {
 #pragma unroll
-                for (int i = 0; i < RW; ++i) { facc[i] = fmaf(lsv, (float)iacc[i], facc[i]); iacc[i] = 0; }
+                for (int i = 0; i < RW; ++i) { facc[i] = fmaf(lsv[q / (AGQ ? AGQ : 1)], (float)iacc[i], facc[i]); iacc[i] = 0; }
             }
         }
-        if (!p.int_path) {
+        if (!INT_PATH) {
+            const unsigned char *sp = stage + (size_t)QCH * 512;
 #pragma unroll
             for (int i = 0; i < RW; ++i) {
-                float v = fmaf(0.5f * sc[i], facc[i] + lbsum, cacc[i]);
-                if (p.zp) v = fmaf(zr[i], lbsum, v);
+                const float s = p.one_scale ? p.scale0 : load_scale(sp, p.sd, lane * RW + i);
+                float v = fmaf(0.5f * s, facc[i] + lbsum, cacc[i]);
+                if (p.zp) v = fmaf(load_scale(sp + (size_t)RSB * p.sd, p.sd, lane * RW + i), lbsum, v);
                 cacc[i] = v;
             }
         }
-        __syncwarp();                              // table is rewritten by the next chunk
-        if (c + 1 < c_end) load_block(c + 1);
+        __syncwarp();                              // stage / table are rewritten by the next chunk
+        if (c + 1 < c_end) {
+            const unsigned char *src = rsb_base + (size_t)(c + 1) * p.blk_bytes;
+            for (int i = lane; i < n16; i += 32) cp_async16(stage + i * 16, src + i * 16, pol);
+            cp_async_commit();
+        }
     }
     if (tid == 0) TMAC_TRACE(4);
 
-    // ---- CTA reduction (fixed warp order) -------------------------------------------------------
+    // ---- CTA reduction (fixed warp order); red aliases the consumed stages ----------------------
+    __syncthreads();
     {
         float *r = red + (size_t)warp * RSB + lane * RW;
 #pragma unroll
-        for (int i = 0; i < RW; ++i) r[i] = p.int_path ? __int_as_float(iacc[i]) : cacc[i];
+        for (int i = 0; i < RW; ++i) r[i] = INT_PATH ? __int_as_float(iacc[i]) : cacc[i];
     }
     __syncthreads();
     if (tid == 0) TMAC_TRACE(5);
@@ -553,9 +557,9 @@ __global__ void __launch_bounds__(kG3MaxWarps * 32, 3) gemv3_kernel(const Gemv3P
         float fsum = 0.f; int isum = 0;
         for (int w = 0; w < WPC; ++w) {
             const float v = red[(size_t)w * RSB + t];
-            if (p.int_path) isum += __float_as_int(v); else fsum += v;
+            if (INT_PATH) isum += __float_as_int(v); else fsum += v;
         }
-        const float mine = p.int_path ? __int_as_float(isum) : fsum;
+        const float mine = INT_PATH ? __int_as_float(isum) : fsum;
         if (p.cs > 1) st_cluster_f32(cl + (size_t)rank * RSB + t, 0, mine);   // into the leader's shared memory
         else cl[t] = mine;
     }
@@ -566,12 +570,12 @@ __global__ void __launch_bounds__(kG3MaxWarps * 32, 3) gemv3_kernel(const Gemv3P
         float fsum = 0.f; int isum = 0;
         for (int k2 = 0; k2 < p.cs; ++k2) {
             const float v = cl[(size_t)k2 * RSB + t];
-            if (p.int_path) isum += __float_as_int(v); else fsum += v;
+            if (INT_PATH) isum += __float_as_int(v); else fsum += v;
         }
         const int row = (p.rsb0 + rsb) * RSB + t;
         if (row >= p.row_begin && row < p.row_end) {
             float out;
-            if (p.int_path) {
+            if (INT_PATH) {
                 // C = ((sum_b alpha_b*CBits_b) * LUT_Scales[0] + LUT_Biases[0]*alpha_0) * Scales[0]
                 // (python/t_mac/ops/qgemm.py:160,171-174); isum = sum_b 2*alpha_b*CBits_b exactly.
                 const float cb = __fmul_rn((float)isum, 0.5f);
@@ -585,7 +589,6 @@ __global__ void __launch_bounds__(kG3MaxWarps * 32, 3) gemv3_kernel(const Gemv3P
             else reinterpret_cast<float *>(p.C)[o] = out;
         }
     }
-    if (tid == 0) TMAC_TRACE(7);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -660,7 +663,11 @@ __global__ void __launch_bounds__(kPreThreads) preprocessor_kernel(const TIn *B,
     const TIn *b = B + (size_t)n * K;
     const int tid = threadIdx.x;
 
+    // Programmatic dependent launch: let the consumer GEMV start streaming its (static) weights now;
+    // the activations and the output buffers belong to the stream order, so wait before touching them.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     for (int a = tid; a < a_end - a_begin; a += kPreThreads) smax[a] = 0;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     __syncthreads();
     // pass 1: abs-sum max per act group (lut_ctor.cc:242-256; association (a0+a1)+(a2+a3) :251)
     for (int g = tid; g < ng; g += kPreThreads) {

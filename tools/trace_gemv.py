@@ -24,7 +24,9 @@ t = buf[:n].astype(np.float64)
 d = t - t[:, :1]
 d[d < 0] = np.nan
 import warnings; warnings.simplefilter("ignore")
-names = ["entry", "loads issued", "pdl wait done", "lut staged", "loop done", "cta reduced", "cluster synced", "stored(leader)"]
+names = ["entry", "loads issued", "pdl wait done", "lut staged", "loop done", "cta reduced", "cluster synced"]
+g0 = buf[:n, 7].astype(np.float64); g0 -= g0.min()
+print("CTA entry time spread (globaltimer ns): mean %.0f  p50 %.0f  p90 %.0f  max %.0f" % (g0.mean(), np.percentile(g0, 50), np.percentile(g0, 90), g0.max()))
 print("ctas", n, "SM cycles since entry (mean / min / max):")
-for i, nm in enumerate(names):
+for i, nm in enumerate(names[:7]):
     print("  %-12s %8.0f %8.0f %8.0f" % (nm, np.nanmean(d[:, i]), np.nanmin(d[:, i]), np.nanmax(d[:, i])))
