@@ -89,7 +89,7 @@ struct Context {
     std::set<const void *> sym_qluts;    // device QLUT buffers last written by our preprocessor
     // workspaces
     DevBuf d_b, d_qlut, d_ls, d_lb, d_c, d_part, d_cnt, d_cbits, d_trace;
-    int trace = 0, trace_ctas = 0;
+    int trace = 0, trace_ctas = 0, trace_seq = 0;
     PinBuf h_in, h_out;
     cudaEvent_t stage_ev = nullptr;      // last H2D that read h_in
     bool stage_pending = false;
@@ -223,9 +223,10 @@ int launch_gemv3(const Resident &R, int row_begin, int row_end, int N, const int
     if (g.cs_override > 0) { p.cs = g.cs_override; }
     if (g.wpc_override > 0) { p.wpc = std::min(g.wpc_override, kG3MaxWarps); }
     if (g.cs_override > 0 || g.wpc_override > 0) p.bpw = (L.nchunk + p.cs * p.wpc - 1) / (p.cs * p.wpc);
-    if (g.trace) {
-        if (g.d_trace.ensure((size_t)nrsb * p.cs * 8 * sizeof(long long))) return fail("out of device memory (trace)");
-        p.trace = (long long *)g.d_trace.p;
+    if (g.trace) {   // ring of 8 launches
+        const size_t per = (size_t)nrsb * p.cs * 8;
+        if (g.d_trace.ensure(per * 8 * sizeof(long long))) return fail("out of device memory (trace)");
+        p.trace = (long long *)g.d_trace.p + per * (size_t)(g.trace_seq++ % 8);
         g.trace_ctas = nrsb * p.cs;
     }
     gemv3_fn fn = pick_gemv3(L.pb, sym, L.qch, agq);
@@ -715,9 +716,9 @@ int tmac_b200_debug_trace(long long *dst, int cap_ctas) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g.trace || !g.d_trace.p) return fail("trace disabled (TMAC_B200_TRACE=1)");
     CUDA_OK(cudaStreamSynchronize(g.stream()));
-    const int n = std::min(cap_ctas, g.trace_ctas);
+    const int n = std::min(cap_ctas, g.trace_ctas * 8);   // ring of 8 launches x ctas
     CUDA_OK(cudaMemcpy(dst, g.d_trace.p, (size_t)n * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
-    return n;
+    return g.trace_ctas;
 }
 
 int tmac_b200_set_lut_mode(int mode) {

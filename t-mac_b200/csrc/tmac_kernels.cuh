@@ -46,6 +46,16 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) {
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(s));
     return r;
 }
+// x >> 16 on the FMA pipe (IMAD.HI) instead of the ALU pipe (SHF): the PRMT/LOP3 work of the lookup
+// loop saturates the ALU pipe, the FMA pipe only carries the DP4As.
+#ifdef TMAC_HI16_SHF
+__device__ __forceinline__ uint32_t hi16(uint32_t x) { return x >> 16; }
+#else
+__device__ __forceinline__ uint32_t hi16(uint32_t x) { return __umulhi(x, 65536u); }
+#endif
+#ifndef TMAC_G3_MINB
+#define TMAC_G3_MINB 4
+#endif
 __device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];"
@@ -73,13 +83,13 @@ template <bool SYM> struct Quad<4, SYM> {
             uint32_t v0, v1;
             if (SYM) {
                 v0 = prmt(tab[2 * k], tab[2 * k + 1], wj);
-                v1 = prmt(tab[2 * k], tab[2 * k + 1], wj >> 16);
+                v1 = prmt(tab[2 * k], tab[2 * k + 1], hi16(wj));
                 acc[0] = __dp4a((int)v0, (int)prmt(wtx, wty, ws), acc[0]);
-                acc[1] = __dp4a((int)v1, (int)prmt(wtx, wty, ws >> 16), acc[1]);
+                acc[1] = __dp4a((int)v1, (int)prmt(wtx, wty, hi16(ws)), acc[1]);
             } else {
                 const uint32_t *g = tab + 4 * k;
                 v0 = prmt(prmt(g[0], g[1], wj), prmt(g[2], g[3], wj), ws);
-                v1 = prmt(prmt(g[0], g[1], wj >> 16), prmt(g[2], g[3], wj >> 16), ws >> 16);
+                v1 = prmt(prmt(g[0], g[1], hi16(wj)), prmt(g[2], g[3], hi16(wj)), hi16(ws));
                 acc[0] = __dp4a((int)v0, (int)wtx, acc[0]);
                 acc[1] = __dp4a((int)v1, (int)wtx, acc[1]);
             }
@@ -99,23 +109,23 @@ template <bool SYM> struct Quad<2, SYM> {
             const uint32_t so = ((wo >> 1) & 0x44444444u) | 0x32103210u;
             if (SYM) {
                 const uint32_t *te = tab + 4 * pr, *to = tab + 4 * pr + 2;
-                const uint32_t v0a = prmt(te[0], te[1], je), v0b = prmt(te[0], te[1], je >> 16);
-                const uint32_t v1a = prmt(to[0], to[1], jo), v1b = prmt(to[0], to[1], jo >> 16);
+                const uint32_t v0a = prmt(te[0], te[1], je), v0b = prmt(te[0], te[1], hi16(je));
+                const uint32_t v1a = prmt(to[0], to[1], jo), v1b = prmt(to[0], to[1], hi16(jo));
                 acc[0] = __dp4a((int)prmt(v0a, v1a, 0x5410), (int)prmt(wtx, wty, se), acc[0]);
-                acc[1] = __dp4a((int)prmt(v0a, v1a, 0x7632), (int)prmt(wtx, wty, se >> 16), acc[1]);
+                acc[1] = __dp4a((int)prmt(v0a, v1a, 0x7632), (int)prmt(wtx, wty, hi16(se)), acc[1]);
                 acc[2] = __dp4a((int)prmt(v0b, v1b, 0x5410), (int)prmt(wtx, wty, so), acc[2]);
-                acc[3] = __dp4a((int)prmt(v0b, v1b, 0x7632), (int)prmt(wtx, wty, so >> 16), acc[3]);
+                acc[3] = __dp4a((int)prmt(v0b, v1b, 0x7632), (int)prmt(wtx, wty, hi16(so)), acc[3]);
             } else {
                 const uint32_t *ge = tab + 8 * pr, *go = tab + 8 * pr + 4;
-                const uint32_t l0a = prmt(ge[0], ge[1], je), l0b = prmt(ge[0], ge[1], je >> 16);
-                const uint32_t h0a = prmt(ge[2], ge[3], je), h0b = prmt(ge[2], ge[3], je >> 16);
-                const uint32_t l1a = prmt(go[0], go[1], jo), l1b = prmt(go[0], go[1], jo >> 16);
-                const uint32_t h1a = prmt(go[2], go[3], jo), h1b = prmt(go[2], go[3], jo >> 16);
+                const uint32_t l0a = prmt(ge[0], ge[1], je), l0b = prmt(ge[0], ge[1], hi16(je));
+                const uint32_t h0a = prmt(ge[2], ge[3], je), h0b = prmt(ge[2], ge[3], hi16(je));
+                const uint32_t l1a = prmt(go[0], go[1], jo), l1b = prmt(go[0], go[1], hi16(jo));
+                const uint32_t h1a = prmt(go[2], go[3], jo), h1b = prmt(go[2], go[3], hi16(jo));
                 // transpose lo and hi candidates, then pick by the (row-ordered) sign bits
                 acc[0] = __dp4a((int)prmt(prmt(l0a, l1a, 0x5410), prmt(h0a, h1a, 0x5410), se), (int)wtx, acc[0]);
-                acc[1] = __dp4a((int)prmt(prmt(l0a, l1a, 0x7632), prmt(h0a, h1a, 0x7632), se >> 16), (int)wtx, acc[1]);
+                acc[1] = __dp4a((int)prmt(prmt(l0a, l1a, 0x7632), prmt(h0a, h1a, 0x7632), hi16(se)), (int)wtx, acc[1]);
                 acc[2] = __dp4a((int)prmt(prmt(l0b, l1b, 0x5410), prmt(h0b, h1b, 0x5410), so), (int)wtx, acc[2]);
-                acc[3] = __dp4a((int)prmt(prmt(l0b, l1b, 0x7632), prmt(h0b, h1b, 0x7632), so >> 16), (int)wtx, acc[3]);
+                acc[3] = __dp4a((int)prmt(prmt(l0b, l1b, 0x7632), prmt(h0b, h1b, 0x7632), hi16(so)), (int)wtx, acc[3]);
             }
         }
     }
@@ -144,14 +154,14 @@ template <bool SYM> struct Quad<1, SYM> {
             for (int k = 0; k < 4; ++k) {
                 const uint32_t j = ww[k] & 0x77777777u;
                 va[k] = prmt(tab[2 * k], tab[2 * k + 1], j);
-                vb[k] = prmt(tab[2 * k], tab[2 * k + 1], j >> 16);
+                vb[k] = prmt(tab[2 * k], tab[2 * k + 1], hi16(j));
             }
             transpose4(va[0], va[1], va[2], va[3], xa);
             transpose4(vb[0], vb[1], vb[2], vb[3], xb);
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                const uint32_t sa = (r & 1) ? (s[r >> 1] >> 16) : s[r >> 1];           // rows 0..3: words 0,0,1,1
-                const uint32_t sb = (r & 1) ? (s[2 + (r >> 1)] >> 16) : s[2 + (r >> 1)]; // rows 4..7: words 2,2,3,3
+                const uint32_t sa = (r & 1) ? (hi16(s[r >> 1])) : s[r >> 1];           // rows 0..3: words 0,0,1,1
+                const uint32_t sb = (r & 1) ? (hi16(s[2 + (r >> 1)])) : s[2 + (r >> 1)]; // rows 4..7: words 2,2,3,3
                 acc[r] = __dp4a((int)xa[r], (int)prmt(wtx, wty, sa), acc[r]);
                 acc[4 + r] = __dp4a((int)xb[r], (int)prmt(wtx, wty, sb), acc[4 + r]);
             }
@@ -161,8 +171,8 @@ template <bool SYM> struct Quad<1, SYM> {
             for (int k = 0; k < 4; ++k) {
                 const uint32_t j = ww[k] & 0x77777777u;
                 const uint32_t *g = tab + 4 * k;
-                la[k] = prmt(g[0], g[1], j); lb[k] = prmt(g[0], g[1], j >> 16);
-                ha[k] = prmt(g[2], g[3], j); hb[k] = prmt(g[2], g[3], j >> 16);
+                la[k] = prmt(g[0], g[1], j); lb[k] = prmt(g[0], g[1], hi16(j));
+                ha[k] = prmt(g[2], g[3], j); hb[k] = prmt(g[2], g[3], hi16(j));
             }
             transpose4(la[0], la[1], la[2], la[3], xla);
             transpose4(ha[0], ha[1], ha[2], ha[3], xha);
@@ -170,8 +180,8 @@ template <bool SYM> struct Quad<1, SYM> {
             transpose4(hb[0], hb[1], hb[2], hb[3], xhb);
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                const uint32_t sa = (r & 1) ? (s[r >> 1] >> 16) : s[r >> 1];
-                const uint32_t sb = (r & 1) ? (s[2 + (r >> 1)] >> 16) : s[2 + (r >> 1)];
+                const uint32_t sa = (r & 1) ? (hi16(s[r >> 1])) : s[r >> 1];
+                const uint32_t sb = (r & 1) ? (hi16(s[2 + (r >> 1)])) : s[2 + (r >> 1)];
                 acc[r] = __dp4a((int)prmt(xla[r], xha[r], sa), (int)wtx, acc[r]);
                 acc[4 + r] = __dp4a((int)prmt(xlb[r], xhb[r], sb), (int)wtx, acc[4 + r]);
             }
@@ -400,7 +410,7 @@ struct Gemv3Params {
 #ifdef TMAC_ENABLE_TRACE
 __device__ __forceinline__ long long globaltimer_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 // slots 0..6: clock64 (SM cycles) since entry; slot 7: globaltimer (ns) at entry.
-#define TMAC_TRACE(slot) do { if (p.trace) p.trace[(size_t)blockIdx.x * 8 + (slot)] = ((slot) == 7) ? globaltimer_ns() : clock64(); } while (0)
+#define TMAC_TRACE(slot) do { if (p.trace) p.trace[(size_t)blockIdx.x * 8 + (slot)] = globaltimer_ns(); } while (0)
 #else
 #define TMAC_TRACE(slot) do { } while (0)
 #endif
@@ -434,7 +444,7 @@ __device__ __forceinline__ void st_cluster_f32(float *local_ptr, uint32_t rank, 
 constexpr int kG3MaxWarps = 8;
 
 template <int PB, bool SYM, int QCH, int AGQ>
-__global__ void __launch_bounds__(kG3MaxWarps * 32, 5) gemv3_kernel(const Gemv3Params p, const uint32_t wtx, const uint32_t wty) {
+__global__ void __launch_bounds__(kG3MaxWarps * 32, TMAC_G3_MINB) gemv3_kernel(const Gemv3Params p, const uint32_t wtx, const uint32_t wty) {
     constexpr int RW = 8 / PB;
     constexpr int RSB = 32 * RW;
     constexpr int TB = SYM ? 8 : 16;              // table bytes per group in shared memory
@@ -455,7 +465,7 @@ __global__ void __launch_bounds__(kG3MaxWarps * 32, 5) gemv3_kernel(const Gemv3P
     unsigned char *tab = stage + p.blk_bytes;
     float *red = reinterpret_cast<float *>(wbase);
 
-    if (tid == 0) { TMAC_TRACE(0); TMAC_TRACE(7); }
+    if (tid == 0) { TMAC_TRACE(0); }
     pdl_launch_dependents();                      // the next launch may start its weight stream now
 
     const int c_first = (rank * WPC + warp) * p.bpw;
@@ -589,6 +599,7 @@ __global__ void __launch_bounds__(kG3MaxWarps * 32, 5) gemv3_kernel(const Gemv3P
             else reinterpret_cast<float *>(p.C)[o] = out;
         }
     }
+    if (tid == 0) TMAC_TRACE(7);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -14,7 +14,7 @@ from dataclasses import dataclass
 from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtmac_b200.so")
+LIB_PATH = os.environ.get("TMAC_B200_LIB", os.path.join(HERE, "libtmac_b200.so"))
 
 F32, F16 = 0, 1
 
