@@ -81,7 +81,7 @@ struct Context {
     int ks_override = 0;
     int kernel_version = 3;              // 3 = gemv3_kernel (clusters + DSMEM + PDL), 1 = gemv_kernel (split-K scratch)
     int use_pdl = 1;
-    int cs_override = 0, wpc_override = 0;
+    int cs_override = 0, wpc_override = 0, pdl_late = 0;
     int64_t next_hint = 0;               // one-shot: tensor whose blocks the next launch prefetches into L2
     std::map<int64_t, Resident> res;
     int64_t next_handle = 1;
@@ -127,6 +127,7 @@ int ensure_init() {
     if (const char *e = getenv("TMAC_B200_PDL")) g.use_pdl = atoi(e);
     if (const char *e = getenv("TMAC_B200_TRACE")) g.trace = atoi(e);
     if (const char *e = getenv("TMAC_B200_CS")) g.cs_override = atoi(e);
+    if (const char *e = getenv("TMAC_B200_PDL_LATE")) g.pdl_late = atoi(e);
     if (const char *e = getenv("TMAC_B200_WPC")) g.wpc_override = atoi(e);
     g.inited = true;
     return 0;
@@ -219,6 +220,7 @@ int launch_gemv3(const Resident &R, int row_begin, int row_end, int N, const int
     const int agq = int_path ? 0 : std::min(L.act_group_size, L.ck) / 16;
     p.zp = L.zp; p.one_scale = L.one_scale; p.sd = L.sd; p.out_f16 = out_f16;
     p.blk_bytes = (int)L.blk; p.scale0 = L.scale0; p.rsb_stride = L.rsb_stride;
+    p.pdl_late = g.pdl_late;
     choose_decomposition(nrsb, L.nchunk, N, &p.cs, &p.wpc, &p.bpw);
     if (g.cs_override > 0) { p.cs = g.cs_override; }
     if (g.wpc_override > 0) { p.wpc = std::min(g.wpc_override, kG3MaxWarps); }

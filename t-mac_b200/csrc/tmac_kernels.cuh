@@ -41,6 +41,12 @@ struct GemvParams {
     float scale0;
 };
 
+// (a & b) | c in ONE LOP3 (the compiler splits it in two when b and c are immediates)
+__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) {
     uint32_t r;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(s));
@@ -79,7 +85,7 @@ template <bool SYM> struct Quad<4, SYM> {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const uint32_t wj = ww[k] & 0x77777777u;
-            const uint32_t ws = ((ww[k] >> 1) & 0x44444444u) | 0x32103210u;
+            const uint32_t ws = and_or(ww[k] >> 1, 0x44444444u, 0x32103210u);
             uint32_t v0, v1;
             if (SYM) {
                 v0 = prmt(tab[2 * k], tab[2 * k + 1], wj);
@@ -105,8 +111,8 @@ template <bool SYM> struct Quad<2, SYM> {
         for (int pr = 0; pr < 2; ++pr) {
             const uint32_t we = ww[2 * pr], wo = ww[2 * pr + 1];
             const uint32_t je = we & 0x77777777u, jo = wo & 0x77777777u;
-            const uint32_t se = ((we >> 1) & 0x44444444u) | 0x32103210u;
-            const uint32_t so = ((wo >> 1) & 0x44444444u) | 0x32103210u;
+            const uint32_t se = and_or(we >> 1, 0x44444444u, 0x32103210u);
+            const uint32_t so = and_or(wo >> 1, 0x44444444u, 0x32103210u);
             if (SYM) {
                 const uint32_t *te = tab + 4 * pr, *to = tab + 4 * pr + 2;
                 const uint32_t v0a = prmt(te[0], te[1], je), v0b = prmt(te[0], te[1], hi16(je));
@@ -146,7 +152,7 @@ template <bool SYM> struct Quad<1, SYM> {
         const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
         uint32_t s[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) s[k] = ((ww[k] >> 1) & 0x44444444u) | 0x32103210u;
+        for (int k = 0; k < 4; ++k) s[k] = and_or(ww[k] >> 1, 0x44444444u, 0x32103210u);
         uint32_t xa[4], xb[4];
         if (SYM) {
             uint32_t va[4], vb[4];
@@ -403,6 +409,7 @@ struct Gemv3Params {
     int zp, one_scale, sd, out_f16;
     int blk_bytes;                 // bytes per block (weights + scales)
     int cs, wpc, bpw;              // cluster size, warps per CTA, chunks per warp
+    int pdl_late;                  // trigger dependents after the math instead of at entry
     size_t rsb_stride;
     float scale0;
     long long *trace;
@@ -466,7 +473,7 @@ __global__ void __launch_bounds__(kG3MaxWarps * 32, TMAC_G3_MINB) gemv3_kernel(c
     float *red = reinterpret_cast<float *>(wbase);
 
     if (tid == 0) { TMAC_TRACE(0); }
-    pdl_launch_dependents();                      // the next launch may start its weight stream now
+    if (!p.pdl_late) pdl_launch_dependents();     // the next launch may start its weight stream now
 
     const int c_first = (rank * WPC + warp) * p.bpw;
     const int c_end = min(p.nchunk, c_first + p.bpw);
@@ -552,6 +559,7 @@ __global__ void __launch_bounds__(kG3MaxWarps * 32, TMAC_G3_MINB) gemv3_kernel(c
         }
     }
     if (tid == 0) TMAC_TRACE(4);
+    if (p.pdl_late) pdl_launch_dependents();
 
     // ---- CTA reduction (fixed warp order); red aliases the consumed stages ----------------------
     __syncthreads();
