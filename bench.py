@@ -250,6 +250,16 @@ def main():
 
     g_step = capture(True)
     g_gemv = capture(False)
+
+    def grouped_calls():
+        tb.qgemm_lut_grouped(layers, 1, [qlut[i] for i in range(LAYERS)], [ls[i] for i in range(LAYERS)],
+                             [lb[i] for i in range(LAYERS)], [out[i] for i in range(LAYERS)])
+    g_grouped = None
+    if not args.eager:
+        grouped_calls(); tb.check(lib.tmac_b200_sync(), "sync")
+        tb.check(lib.tmac_b200_graph_begin(), "graph_begin")
+        grouped_calls()
+        g_grouped = lib.tmac_b200_graph_end(); tb.check(g_grouped, "graph_end")
     kernels_per_step = 2 * LAYERS
 
     def run_steps(graph, n):
@@ -311,6 +321,14 @@ def main():
             roofline["traffic"] = json.load(open(tp)).get("gemv_kernel_dram_bytes_per_launch")
         except Exception:
             pass
+
+    if g_grouped:
+        timed(g_grouped, 3, False)
+        ms_gr = timed(g_grouped, args.steps, False)
+        t_gr = ms_gr / args.steps * 1e-3
+        roofline["grouped_launch"] = {"what": "ONE launch for the step's %d independent GEMVs (tmac_b200_qgemm_lut_grouped)" % LAYERS,
+                                      "achieved": LAYERS * algorithmic_bytes() / t_gr / 1e9, "frac": LAYERS * algorithmic_bytes() / t_gr / 1e9 / peak,
+                                      "us_per_gemv": t_gr / LAYERS * 1e6}
 
     # ---- e2e: host buffers through the reference-facing call -----------------------------------
     hx = torch.randn((LAYERS, K)).half().float().pin_memory().numpy()

@@ -129,6 +129,12 @@ TMAC_B200_API int tmac_b200_preprocessor(int K, int N, int act_group_size, int d
 TMAC_B200_API int tmac_b200_qgemm_lut(int64_t handle, int row0, int rows, int N, int dtype,
                                       const void *QLUT, const void *LUT_Scales,
                                       const void *LUT_Biases, void *C);
+/* Grouped launch: `count` qgemm_lut problems of identical geometry (same M, K, bits, grouping) in
+ * ONE kernel launch -- the q/k/v or gate/up projections of a layer, MoE experts, ...  Host arrays of
+ * per-problem DEVICE pointers; C[i] is [N][M]. */
+TMAC_B200_API int tmac_b200_qgemm_lut_grouped(const int64_t *handles, int count, int N, int dtype,
+                                              const void *const *QLUT, const void *const *LUT_Scales,
+                                              const void *const *LUT_Biases, void *const *C);
 /* Fused convenience (llama_cpp_init + llama_cpp_compute of the whole tensor in one call,
  * workspaces owned by the library): C [N][M] = qgemm_lut(preprocessor(B)). */
 TMAC_B200_API int tmac_b200_gemv(int64_t handle, int N, int dtype, const void *B, void *C);

@@ -87,6 +87,7 @@ struct Context {
     int64_t next_handle = 1;
     std::vector<tmac_b200_kcfg> kcfgs;
     std::set<const void *> sym_qluts;    // device QLUT buffers last written by our preprocessor
+    std::vector<std::pair<std::vector<const void *>, void *>> ptr_tables;   // grouped-launch pointer tables
     // workspaces
     DevBuf d_b, d_qlut, d_ls, d_lb, d_c, d_part, d_cnt, d_cbits, d_trace;
     int trace = 0, trace_ctas = 0, trace_seq = 0;
@@ -199,8 +200,11 @@ void choose_decomposition(int nrsb, int nchunk, int N, int *cs_out, int *wpc_out
 }
 
 // Production launch: clusters + DSMEM reduction + PDL (gemv3_kernel).
+struct BatchPtrs { int n = 0; const unsigned char *const *W = nullptr; const int8_t *const *q = nullptr; const float *const *ls = nullptr,
+                   *const *lb = nullptr; void *const *C = nullptr; };
+
 int launch_gemv3(const Resident &R, int row_begin, int row_end, int N, const int8_t *qlut, const float *ls, const float *lb, void *C,
-                 int ldc, int c_row0, int out_f16, bool sym) {
+                 int ldc, int c_row0, int out_f16, bool sym, const BatchPtrs *batch = nullptr) {
     const StreamLayout &L = R.L;
     if (row_begin < 0 || row_end > L.Mout || row_begin >= row_end) return fail("qgemm_lut: bad row range");
     const int rsb0 = row_begin / L.rsb, rsb1 = (row_end + L.rsb - 1) / L.rsb, nrsb = rsb1 - rsb0;
@@ -221,7 +225,9 @@ int launch_gemv3(const Resident &R, int row_begin, int row_end, int N, const int
     p.zp = L.zp; p.one_scale = L.one_scale; p.sd = L.sd; p.out_f16 = out_f16;
     p.blk_bytes = (int)L.blk; p.scale0 = L.scale0; p.rsb_stride = L.rsb_stride;
     p.pdl_late = g.pdl_late;
-    choose_decomposition(nrsb, L.nchunk, N, &p.cs, &p.wpc, &p.bpw);
+    const int nb = batch ? batch->n : 0;
+    if (batch) { p.nbatch = nb; p.Wv = batch->W; p.qlutv = batch->q; p.lsv = batch->ls; p.lbv = batch->lb; p.Cv = batch->C; }
+    choose_decomposition(nrsb, L.nchunk, N * std::max(1, nb), &p.cs, &p.wpc, &p.bpw);
     if (g.cs_override > 0) { p.cs = g.cs_override; }
     if (g.wpc_override > 0) { p.wpc = std::min(g.wpc_override, kG3MaxWarps); }
     if (g.cs_override > 0 || g.wpc_override > 0) p.bpw = (L.nchunk + p.cs * p.wpc - 1) / (p.cs * p.wpc);
@@ -239,7 +245,7 @@ int launch_gemv3(const Resident &R, int row_begin, int row_end, int N, const int
     uint32_t wtx, wty;
     plane_weight_regs(L.bits, sym, &wtx, &wty);
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(nrsb * p.cs, N, 1);
+    cfg.gridDim = dim3(nrsb * p.cs, N, std::max(1, nb));
     cfg.blockDim = dim3(p.wpc * 32, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = g.stream();
@@ -816,6 +822,52 @@ int tmac_b200_qgemm_lut(int64_t handle, int row0, int rows, int N, int dtype, co
     auto it = g.res.find(handle);
     if (it == g.res.end()) return fail("qgemm_lut: bad weight handle");
     return qgemm_impl(it->second, row0, rows, N, dtype, QLUT, LUT_Scales, LUT_Biases, C);
+}
+
+// Grouped launch: `count` qgemm_lut problems with identical geometry (same M, K, bits, grouping;
+// e.g. the q/k/v or gate/up projections of a layer, the experts of an MoE layer, or any set of
+// GEMVs whose LUTs are already available) in ONE kernel launch.  Device pointers only.
+// QLUT[i], LUT_Scales[i], LUT_Biases[i], C[i] are per-problem device pointers (host arrays of pointers).
+int tmac_b200_qgemm_lut_grouped(const int64_t *handles, int count, int N, int dtype, const void *const *QLUT,
+                                const void *const *LUT_Scales, const void *const *LUT_Biases, void *const *C) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    if (!handles || count <= 0 || count > 65535 || !QLUT || !LUT_Scales || !LUT_Biases || !C) return fail("grouped: bad arguments");
+    std::vector<const Resident *> rs(count);
+    for (int i = 0; i < count; ++i) {
+        auto it = g.res.find(handles[i]);
+        if (it == g.res.end()) return fail("grouped: bad weight handle");
+        rs[i] = &it->second;
+        const StreamLayout &a = rs[0]->L, &b = rs[i]->L;
+        if (a.Mout != b.Mout || a.K != b.K || a.bits != b.bits || a.blk != b.blk || a.nchunk != b.nchunk || a.zp != b.zp ||
+            a.one_scale != b.one_scale || a.sd != b.sd || a.act_group_size != b.act_group_size || a.scale0 != b.scale0)
+            return fail("grouped: all tensors must share one geometry");
+        if (!is_device_ptr(QLUT[i]) || !is_device_ptr(C[i])) return fail("grouped: device pointers only");
+    }
+    bool sym = true;
+    for (int i = 0; i < count; ++i) sym = sym && g.sym_qluts.count(QLUT[i]) != 0;
+    if (g.lut_mode == 1) sym = false;
+    if (g.lut_mode == 2) sym = true;
+    // pointer tables: one device allocation per distinct call signature (stable under graph capture)
+    std::vector<const void *> tab(5 * (size_t)count);
+    for (int i = 0; i < count; ++i) {
+        tab[i] = rs[i]->d; tab[count + i] = QLUT[i]; tab[2 * count + i] = LUT_Scales[i]; tab[3 * count + i] = LUT_Biases[i]; tab[4 * count + i] = C[i];
+    }
+    void *dtab = nullptr;
+    for (auto &e : g.ptr_tables)
+        if (e.first == tab) { dtab = e.second; break; }
+    if (!dtab) {
+        if (cudaMalloc(&dtab, tab.size() * sizeof(void *)) != cudaSuccess) { cudaGetLastError(); return fail("out of device memory (pointer table)"); }
+        CUDA_OK(cudaMemcpy(dtab, tab.data(), tab.size() * sizeof(void *), cudaMemcpyHostToDevice));
+        g.ptr_tables.emplace_back(tab, dtab);
+    }
+    const void **dt = (const void **)dtab;
+    BatchPtrs bp;
+    bp.n = count;
+    bp.W = (const unsigned char *const *)dt; bp.q = (const int8_t *const *)(dt + count);
+    bp.ls = (const float *const *)(dt + 2 * count); bp.lb = (const float *const *)(dt + 3 * count); bp.C = (void *const *)(dt + 4 * count);
+    const StreamLayout &L = rs[0]->L;
+    return launch_gemv3(*rs[0], 0, L.Mout, N, nullptr, nullptr, nullptr, nullptr, L.Mout, 0, dtype == TMAC_B200_F16, sym, &bp);
 }
 
 int tmac_b200_gemv(int64_t handle, int N, int dtype, const void *B, void *C) {

@@ -410,6 +410,12 @@ struct Gemv3Params {
     int blk_bytes;                 // bytes per block (weights + scales)
     int cs, wpc, bpw;              // cluster size, warps per CTA, chunks per warp
     int pdl_late;                  // trigger dependents after the math instead of at entry
+    // grouped launch: blockIdx.z selects one of `nbatch` problems with identical geometry
+    int nbatch;
+    const unsigned char *const *Wv;
+    const int8_t *const *qlutv;
+    const float *const *lsv, *const *lbv;
+    void *const *Cv;
     size_t rsb_stride;
     float scale0;
     long long *trace;
@@ -477,7 +483,12 @@ __global__ void __launch_bounds__(kG3MaxWarps * 32, TMAC_G3_MINB) gemv3_kernel(c
 
     const int c_first = (rank * WPC + warp) * p.bpw;
     const int c_end = min(p.nchunk, c_first + p.bpw);
-    const unsigned char *rsb_base = p.W + (size_t)rsb * p.rsb_stride;
+    const unsigned char *Wb = p.W;
+    const int8_t *qb = p.qlut;
+    const float *lsb = p.lut_scales, *lbb = p.lut_biases;
+    void *Cb = p.C;
+    if (p.nbatch > 0) { const int z = blockIdx.z; Wb = p.Wv[z]; qb = p.qlutv[z]; lsb = p.lsv[z]; lbb = p.lbv[z]; Cb = p.Cv[z]; }
+    const unsigned char *rsb_base = Wb + (size_t)rsb * p.rsb_stride;
     const int nag = p.K / p.ags;
     const uint64_t pol = policy_evict_first();
     const int n16 = p.blk_bytes >> 4;
@@ -499,8 +510,8 @@ __global__ void __launch_bounds__(kG3MaxWarps * 32, TMAC_G3_MINB) gemv3_kernel(c
     int iacc[RW];
 #pragma unroll
     for (int i = 0; i < RW; ++i) { cacc[i] = 0.f; iacc[i] = 0; }
-    const uint4 *qrow = reinterpret_cast<const uint4 *>(p.qlut + (size_t)n * p.K * 4);
-    const float *lsg = p.lut_scales + (size_t)n * nag, *lbg = p.lut_biases + (size_t)n * nag;
+    const uint4 *qrow = reinterpret_cast<const uint4 *>(qb + (size_t)n * p.K * 4);
+    const float *lsg = lsb + (size_t)n * nag, *lbg = lbb + (size_t)n * nag;
 
     for (int c = c_first; c < c_end; ++c) {
         // ---- LUT slice of this chunk -> warp-private table (lane = group) ---------------------
@@ -603,8 +614,8 @@ __global__ void __launch_bounds__(kG3MaxWarps * 32, TMAC_G3_MINB) gemv3_kernel(c
             } else
                 out = fsum;
             const size_t o = (size_t)n * p.ldc + (size_t)(row - p.c_row0);
-            if (p.out_f16) reinterpret_cast<__half *>(p.C)[o] = __float2half_rn(out);
-            else reinterpret_cast<float *>(p.C)[o] = out;
+            if (p.out_f16) reinterpret_cast<__half *>(Cb)[o] = __float2half_rn(out);
+            else reinterpret_cast<float *>(Cb)[o] = out;
         }
     }
     if (tid == 0) TMAC_TRACE(7);

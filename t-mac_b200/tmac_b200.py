@@ -38,7 +38,7 @@ EXPORTS = [
     "tmac_b200_find_kcfg", "tmac_b200_clear_kcfg", "tmac_b200_upload_weights", "tmac_b200_upload_plain",
     "tmac_b200_upload_plain_rows", "tmac_b200_debug_encode", "tmac_b200_free_weights", "tmac_b200_clone_weights", "tmac_b200_hint_next_weights",
     "tmac_b200_graph_begin", "tmac_b200_graph_end", "tmac_b200_graph_launch", "tmac_b200_graph_free", "tmac_b200_sync", "tmac_b200_debug_trace", "tmac_b200_weights_nbytes", "tmac_b200_preprocessor",
-    "tmac_b200_qgemm_lut", "tmac_b200_gemv", "tmac_b200_cbits", "qgemm_lut_int8", "preprocessor_int8",
+    "tmac_b200_qgemm_lut", "tmac_b200_qgemm_lut_grouped", "tmac_b200_gemv", "tmac_b200_cbits", "qgemm_lut_int8", "preprocessor_int8",
     "ggml_tmac_init", "ggml_tmac_free", "ggml_tmac_mul_mat_task_init", "ggml_tmac_mul_mat_task_compute",
     "ggml_tmac_set_n_threads", "ggml_tmac_get_type_bits", "ggml_tmac_b200_can_mul_mat",
     "ggml_tmac_b200_mul_mat_get_wsize", "ggml_tmac_b200_get_nbytes", "ggml_tmac_b200_transform_tensor",
@@ -72,6 +72,7 @@ def load() -> C.CDLL:
         "tmac_b200_graph_free": (i, [i64]), "tmac_b200_sync": (i, []), "tmac_b200_debug_trace": (i, [vp, i]), "tmac_b200_weights_nbytes": (sz, [i64]),
         "tmac_b200_preprocessor": (i, [i, i, i, i, vp, vp, vp, vp]),
         "tmac_b200_qgemm_lut": (i, [i64, i, i, i, i, vp, vp, vp, vp]),
+        "tmac_b200_qgemm_lut_grouped": (i, [vp, i, i, i, vp, vp, vp, vp]),
         "tmac_b200_gemv": (i, [i64, i, i, vp, vp]), "tmac_b200_cbits": (i, [i64, i, vp, vp]),
         "qgemm_lut_int8": (i, [i, i, i, i, vp, vp, vp, vp, vp, vp]),
         "preprocessor_int8": (i, [i, i, i, i, vp, vp, vp, vp]),
@@ -165,6 +166,16 @@ def qgemm_lut(wt: Weights, N, qlut, lut_scales, lut_biases, Cout, row0=0, rows=N
     rows = wt.cfg.M - row0 if rows is None else rows
     check(load().tmac_b200_qgemm_lut(wt.handle, row0, rows, N, dtype, ptr(qlut), ptr(lut_scales), ptr(lut_biases), ptr(Cout)),
           "tmac_b200_qgemm_lut")
+
+
+def qgemm_lut_grouped(wts, N, qluts, lut_scales, lut_biases, outs, dtype=F32):
+    """One launch for len(wts) problems of identical geometry (device tensors)."""
+    n = len(wts)
+    H = (C.c_int64 * n)(*[w.handle for w in wts])
+    def arr(xs):
+        return (C.c_void_p * n)(*[ptr(x) for x in xs])
+    check(load().tmac_b200_qgemm_lut_grouped(H, n, N, dtype, arr(qluts), arr(lut_scales), arr(lut_biases), arr(outs)),
+          "tmac_b200_qgemm_lut_grouped")
 
 
 def gemv(wt: Weights, N, B, Cout, dtype=F32):

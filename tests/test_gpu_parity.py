@@ -250,6 +250,31 @@ def test_full_size_properties(lib, oracle):
         wt.free(); wt2.free()
 
 
+def test_grouped_launch_equals_single_launches(lib, oracle):
+    """tmac_b200_qgemm_lut_grouped (q/k/v-style fused launch) is bit-identical to per-tensor launches."""
+    cfg = T.Config(512, 2048, 2, zero_point=True).resolved()
+    wts, outs_single, qs, lss, lbs = [], [], [], [], []
+    try:
+        for seed in range(3):
+            w, sc, z, x = T.make_problem(cfg, seed=40 + seed)
+            wts.append(tb.upload_plain(kc(cfg), w, sc, z))
+            dx = torch.from_numpy(x).cuda()
+            q = torch.zeros((1, cfg.K // 4, 16), dtype=torch.int8, device="cuda")
+            ls = torch.zeros((1, cfg.K // cfg.act_group_size), device="cuda"); lb = torch.zeros_like(ls)
+            tb.preprocessor(cfg.K, 1, cfg.act_group_size, dx, ls, lb, q)
+            o = torch.zeros((1, cfg.Mout), device="cuda")
+            tb.qgemm_lut(wts[-1], 1, q, ls, lb, o)
+            qs.append(q); lss.append(ls); lbs.append(lb); outs_single.append(o)
+        outs = [torch.zeros((1, cfg.Mout), device="cuda") for _ in range(3)]
+        tb.qgemm_lut_grouped(wts, 1, qs, lss, lbs, outs)
+        torch.cuda.synchronize()
+        for a, b in zip(outs, outs_single):
+            assert torch.equal(a, b)
+    finally:
+        for wt in wts:
+            wt.free()
+
+
 def test_errors_follow_reference_convention(lib):
     """0 / -1 return codes (kernels.h:27,37), no exceptions across the C ABI."""
     x = torch.zeros((1, 96), device="cuda")
