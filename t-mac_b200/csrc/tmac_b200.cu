@@ -81,7 +81,7 @@ struct Context {
     int ks_override = 0;
     int kernel_version = 3;              // 3 = gemv3_kernel (clusters + DSMEM + PDL), 1 = gemv_kernel (split-K scratch)
     int use_pdl = 1;
-    int cs_override = 0, wpc_override = 0, pdl_late = 0;
+    int cs_override = 0, wpc_override = 0, pdl_late = 1, minb_override = 0;
     int64_t next_hint = 0;               // one-shot: tensor whose blocks the next launch prefetches into L2
     std::map<int64_t, Resident> res;
     int64_t next_handle = 1;
@@ -129,6 +129,7 @@ int ensure_init() {
     if (const char *e = getenv("TMAC_B200_TRACE")) g.trace = atoi(e);
     if (const char *e = getenv("TMAC_B200_CS")) g.cs_override = atoi(e);
     if (const char *e = getenv("TMAC_B200_PDL_LATE")) g.pdl_late = atoi(e);
+    if (const char *e = getenv("TMAC_B200_MINB")) g.minb_override = atoi(e);
     if (const char *e = getenv("TMAC_B200_WPC")) g.wpc_override = atoi(e);
     g.inited = true;
     return 0;
@@ -153,25 +154,28 @@ gemv_fn pick_gemv(int pb, bool sym, int qch) {
 }
 
 typedef void (*gemv3_fn)(const Gemv3Params, const uint32_t, const uint32_t);
-template <int PB, bool SYM> gemv3_fn pick3_qa(int qch, int agq) {
+template <int PB, bool SYM, int MINB> gemv3_fn pick3_qa(int qch, int agq) {
     switch (qch * 16 + agq) {
-        case 8 * 16 + 8: return gemv3_kernel<PB, SYM, 8, 8>;
-        case 8 * 16 + 4: return gemv3_kernel<PB, SYM, 8, 4>;
-        case 8 * 16 + 2: return gemv3_kernel<PB, SYM, 8, 2>;
-        case 8 * 16 + 0: return gemv3_kernel<PB, SYM, 8, 0>;
-        case 4 * 16 + 4: return gemv3_kernel<PB, SYM, 4, 4>;
-        case 4 * 16 + 2: return gemv3_kernel<PB, SYM, 4, 2>;
-        case 4 * 16 + 0: return gemv3_kernel<PB, SYM, 4, 0>;
-        case 2 * 16 + 2: return gemv3_kernel<PB, SYM, 2, 2>;
-        case 2 * 16 + 0: return gemv3_kernel<PB, SYM, 2, 0>;
+        case 8 * 16 + 8: return gemv3_kernel<PB, SYM, 8, 8, MINB>;
+        case 8 * 16 + 4: return gemv3_kernel<PB, SYM, 8, 4, MINB>;
+        case 8 * 16 + 2: return gemv3_kernel<PB, SYM, 8, 2, MINB>;
+        case 8 * 16 + 0: return gemv3_kernel<PB, SYM, 8, 0, MINB>;
+        case 4 * 16 + 4: return gemv3_kernel<PB, SYM, 4, 4, MINB>;
+        case 4 * 16 + 2: return gemv3_kernel<PB, SYM, 4, 2, MINB>;
+        case 4 * 16 + 0: return gemv3_kernel<PB, SYM, 4, 0, MINB>;
+        case 2 * 16 + 2: return gemv3_kernel<PB, SYM, 2, 2, MINB>;
+        case 2 * 16 + 0: return gemv3_kernel<PB, SYM, 2, 0, MINB>;
     }
     return nullptr;
 }
-gemv3_fn pick_gemv3(int pb, bool sym, int qch, int agq) {
-    if (pb == 4) return sym ? pick3_qa<4, true>(qch, agq) : pick3_qa<4, false>(qch, agq);
-    if (pb == 2) return sym ? pick3_qa<2, true>(qch, agq) : pick3_qa<2, false>(qch, agq);
-    if (pb == 1) return sym ? pick3_qa<1, true>(qch, agq) : pick3_qa<1, false>(qch, agq);
+template <int MINB> gemv3_fn pick_gemv3_m(int pb, bool sym, int qch, int agq) {
+    if (pb == 4) return sym ? pick3_qa<4, true, MINB>(qch, agq) : pick3_qa<4, false, MINB>(qch, agq);
+    if (pb == 2) return sym ? pick3_qa<2, true, MINB>(qch, agq) : pick3_qa<2, false, MINB>(qch, agq);
+    if (pb == 1) return sym ? pick3_qa<1, true, MINB>(qch, agq) : pick3_qa<1, false, MINB>(qch, agq);
     return nullptr;
+}
+gemv3_fn pick_gemv3(int pb, bool sym, int qch, int agq, int minb) {
+    return minb == 3 ? pick_gemv3_m<3>(pb, sym, qch, agq) : pick_gemv3_m<4>(pb, sym, qch, agq);
 }
 
 int ilog2(int v) { int s = 0; while ((1 << (s + 1)) <= v) ++s; return s; }
@@ -228,6 +232,12 @@ int launch_gemv3(const Resident &R, int row_begin, int row_end, int N, const int
     const int nb = batch ? batch->n : 0;
     if (batch) { p.nbatch = nb; p.Wv = batch->W; p.qlutv = batch->q; p.lsv = batch->ls; p.lbv = batch->lb; p.Cv = batch->C; }
     choose_decomposition(nrsb, L.nchunk, N * std::max(1, nb), &p.cs, &p.wpc, &p.bpw);
+    // Measured on B200 (profiles/): a lone launch per tensor is latency bound and prefers fewer, fatter
+    // CTAs with more registers (ILP); grouped / batched launches are ALU-pipe bound and prefer more CTAs.
+    const bool lone = (N * std::max(1, nb) == 1);
+    int minb = lone ? 3 : 4;
+    if (lone && p.cs == 8 && p.wpc == 4 && p.bpw == 1) { p.cs = 4; p.wpc = 8; }
+    if (g.minb_override > 0) minb = g.minb_override;
     if (g.cs_override > 0) { p.cs = g.cs_override; }
     if (g.wpc_override > 0) { p.wpc = std::min(g.wpc_override, kG3MaxWarps); }
     if (g.cs_override > 0 || g.wpc_override > 0) p.bpw = (L.nchunk + p.cs * p.wpc - 1) / (p.cs * p.wpc);
@@ -237,7 +247,7 @@ int launch_gemv3(const Resident &R, int row_begin, int row_end, int N, const int
         p.trace = (long long *)g.d_trace.p + per * (size_t)(g.trace_seq++ % 8);
         g.trace_ctas = nrsb * p.cs;
     }
-    gemv3_fn fn = pick_gemv3(L.pb, sym, L.qch, agq);
+    gemv3_fn fn = pick_gemv3(L.pb, sym, L.qch, agq, minb);
     if (!fn) return fail("qgemm_lut: unsupported chunking (qch=" + std::to_string(L.qch) + ", agq=" + std::to_string(agq) + ")");
     const size_t smem = (size_t)p.cs * L.rsb * 4 +
                         std::max((size_t)p.wpc * (L.blk + (size_t)L.qch * 4 * (sym ? 8 : 16)), (size_t)p.wpc * L.rsb * 4);

@@ -456,8 +456,10 @@ __device__ __forceinline__ void st_cluster_f32(float *local_ptr, uint32_t rank, 
 
 constexpr int kG3MaxWarps = 8;
 
-template <int PB, bool SYM, int QCH, int AGQ>
-__global__ void __launch_bounds__(kG3MaxWarps * 32, TMAC_G3_MINB) gemv3_kernel(const Gemv3Params p, const uint32_t wtx, const uint32_t wty) {
+// MINB = minimum resident CTAs per SM the register allocation is tuned for: 3 (85 registers, more ILP;
+// best for a single launch per tensor) or 4 (64 registers, more CTAs in flight; best for grouped launches).
+template <int PB, bool SYM, int QCH, int AGQ, int MINB>
+__global__ void __launch_bounds__(kG3MaxWarps * 32, MINB) gemv3_kernel(const Gemv3Params p, const uint32_t wtx, const uint32_t wty) {
     constexpr int RW = 8 / PB;
     constexpr int RSB = 32 * RW;
     constexpr int TB = SYM ? 8 : 16;              // table bytes per group in shared memory
