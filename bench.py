@@ -250,6 +250,7 @@ def main():
 
     g_step = capture(True)
     g_gemv = capture(False)
+    lone_cfg = tb.last_launch()
 
     def grouped_calls():
         tb.qgemm_lut_grouped(layers, 1, [qlut[i] for i in range(LAYERS)], [ls[i] for i in range(LAYERS)],
@@ -257,6 +258,7 @@ def main():
     g_grouped = None
     if not args.eager:
         grouped_calls(); tb.check(lib.tmac_b200_sync(), "sync")
+        grouped_cfg = tb.last_launch()
         tb.check(lib.tmac_b200_graph_begin(), "graph_begin")
         grouped_calls()
         g_grouped = lib.tmac_b200_graph_end(); tb.check(g_grouped, "graph_end")
@@ -313,7 +315,7 @@ def main():
     t_gemv = ms_g / args.steps / LAYERS * 1e-3
     peak, peak_src = measured_peak()
     achieved = algorithmic_bytes() / t_gemv / 1e9
-    roofline = {"bound": "hbm", "kernel": "gemv_kernel<2,sym,8>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    roofline = {"bound": "hbm", "kernel": "gemv3_kernel<PB=2,SYM,QCH=8,AGQ=4>", "launch": lone_cfg, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src, "us_per_launch": t_gemv * 1e6, "algorithmic_bytes_per_launch": algorithmic_bytes(), "traffic": None}
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
@@ -328,7 +330,7 @@ def main():
         t_gr = ms_gr / args.steps * 1e-3
         roofline["grouped_launch"] = {"what": "ONE launch for the step's %d independent GEMVs (tmac_b200_qgemm_lut_grouped)" % LAYERS,
                                       "achieved": LAYERS * algorithmic_bytes() / t_gr / 1e9, "frac": LAYERS * algorithmic_bytes() / t_gr / 1e9 / peak,
-                                      "us_per_gemv": t_gr / LAYERS * 1e6}
+                                      "us_per_gemv": t_gr / LAYERS * 1e6, "launch": grouped_cfg}
 
     # ---- e2e: host buffers through the reference-facing call -----------------------------------
     hx = torch.randn((LAYERS, K)).half().float().pin_memory().numpy()

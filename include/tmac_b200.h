@@ -71,6 +71,9 @@ TMAC_B200_API int64_t tmac_b200_graph_end(void);
 TMAC_B200_API int tmac_b200_graph_launch(int64_t graph, int times);
 TMAC_B200_API int tmac_b200_graph_free(int64_t graph);
 TMAC_B200_API int tmac_b200_sync(void);
+/* Reporting: {cluster size, warps/CTA, chunks/warp, register variant, grid.x, planes/word, symmetric LUT,
+ * batch} of the last qgemm_lut launch. */
+TMAC_B200_API int tmac_b200_debug_last_launch(int *out8);
 /* Debug (TMAC_B200_TRACE=1): per-CTA clock64 stamps [ctas][8] of the last qgemm_lut launch. */
 TMAC_B200_API int tmac_b200_debug_trace(long long *dst, int cap_ctas);
 

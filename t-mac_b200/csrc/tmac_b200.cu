@@ -82,6 +82,7 @@ struct Context {
     int kernel_version = 3;              // 3 = gemv3_kernel (clusters + DSMEM + PDL), 1 = gemv_kernel (split-K scratch)
     int use_pdl = 1;
     int cs_override = 0, wpc_override = 0, pdl_late = 1, minb_override = 0;
+    int last_launch[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int64_t next_hint = 0;               // one-shot: tensor whose blocks the next launch prefetches into L2
     std::map<int64_t, Resident> res;
     int64_t next_handle = 1;
@@ -196,7 +197,7 @@ void choose_decomposition(int nrsb, int nchunk, int N, int *cs_out, int *wpc_out
             const long waves = (per_sm + res - 1) / res;
             double cost = (double)per_sm * wpc * bpw;                  // chunk-slots on the busiest SM
             cost *= 1.0 + 0.15 * (waves - 1);                          // later waves lose the overlap
-            cost += 0.02 * bpw * wpc;                                  // prefer short per-warp chains ...
+            cost += 0.02 * bpw * wpc + 0.2 * bpw;                      // prefer short per-warp chains ...
             cost += 0.5 * std::max(0L, 8 - per_sm * wpc);              // ... and at least 8 warps per SM
             if (cost < best_cost) { best_cost = cost; bcs = cs; bwpc = wpc; bbpw = bpw; }
         }
@@ -241,6 +242,8 @@ int launch_gemv3(const Resident &R, int row_begin, int row_end, int N, const int
     if (g.cs_override > 0) { p.cs = g.cs_override; }
     if (g.wpc_override > 0) { p.wpc = std::min(g.wpc_override, kG3MaxWarps); }
     if (g.cs_override > 0 || g.wpc_override > 0) p.bpw = (L.nchunk + p.cs * p.wpc - 1) / (p.cs * p.wpc);
+    g.last_launch[0] = p.cs; g.last_launch[1] = p.wpc; g.last_launch[2] = p.bpw; g.last_launch[3] = minb;
+    g.last_launch[4] = nrsb * p.cs; g.last_launch[5] = L.pb; g.last_launch[6] = sym ? 1 : 0; g.last_launch[7] = std::max(1, nb);
     if (g.trace) {   // ring of 8 launches
         const size_t per = (size_t)nrsb * p.cs * 8;
         if (g.d_trace.ensure(per * 8 * sizeof(long long))) return fail("out of device memory (trace)");
@@ -717,6 +720,15 @@ int tmac_b200_sync(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g.inited) return 0;
     CUDA_OK(cudaStreamSynchronize(g.stream()));
+    return 0;
+}
+
+// Debug / reporting: {cluster size, warps per CTA, chunks per warp, min blocks variant, grid.x, PB, sym, batch}
+// of the last qgemm_lut launch.
+int tmac_b200_debug_last_launch(int *out8) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!out8) return fail("null");
+    std::memcpy(out8, g.last_launch, sizeof g.last_launch);
     return 0;
 }
 
