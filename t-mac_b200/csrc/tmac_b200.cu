@@ -238,6 +238,9 @@ int launch_gemv3(const Resident &R, int row_begin, int row_end, int N, const int
     const bool lone = (N * std::max(1, nb) == 1);
     int minb = lone ? 3 : 4;
     if (lone && p.cs == 8 && p.wpc == 4 && p.bpw == 1) { p.cs = 4; p.wpc = 8; }
+    if (!lone && (long)nrsb * N * std::max(1, nb) >= 4L * g.sms) {   // machine already full of whole super-blocks: no K split
+        p.cs = 1; p.wpc = std::min(kG3MaxWarps, L.nchunk); p.bpw = (L.nchunk + p.wpc - 1) / p.wpc;
+    }
     if (g.minb_override > 0) minb = g.minb_override;
     if (g.cs_override > 0) { p.cs = g.cs_override; }
     if (g.wpc_override > 0) { p.wpc = std::min(g.wpc_override, kG3MaxWarps); }
@@ -253,7 +256,7 @@ int launch_gemv3(const Resident &R, int row_begin, int row_end, int N, const int
     gemv3_fn fn = pick_gemv3(L.pb, sym, L.qch, agq, minb);
     if (!fn) return fail("qgemm_lut: unsupported chunking (qch=" + std::to_string(L.qch) + ", agq=" + std::to_string(agq) + ")");
     const size_t smem = (size_t)p.cs * L.rsb * 4 +
-                        std::max((size_t)p.wpc * (L.blk + (size_t)L.qch * 4 * (sym ? 8 : 16)), (size_t)p.wpc * L.rsb * 4);
+                        std::max((size_t)p.wpc * ((p.bpw > 1 ? 2 : 1) * L.blk + (size_t)L.qch * 4 * (sym ? 8 : 16)), (size_t)p.wpc * L.rsb * 4);
     if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     uint32_t wtx, wty;
     plane_weight_regs(L.bits, sym, &wtx, &wty);

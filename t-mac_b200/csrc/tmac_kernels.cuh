@@ -474,10 +474,11 @@ __global__ void __launch_bounds__(kG3MaxWarps * 32, MINB) gemv3_kernel(const Gem
     // (QCH*4*TB).  The CTA reduction buffer red [WPC][RSB] aliases the stages once they are consumed.
     float *cl = reinterpret_cast<float *>(smem);
     const int tab_bytes = QCH * 4 * TB;
-    const int per_warp = p.blk_bytes + tab_bytes;
+    const int nbuf = p.bpw > 1 ? 2 : 1;           // double-buffered stage when a warp walks several chunks
+    const int per_warp = nbuf * p.blk_bytes + tab_bytes;
     unsigned char *wbase = smem + (size_t)p.cs * RSB * 4;
-    unsigned char *stage = wbase + (size_t)warp * per_warp;
-    unsigned char *tab = stage + p.blk_bytes;
+    unsigned char *stage0 = wbase + (size_t)warp * per_warp;
+    unsigned char *tab = stage0 + nbuf * p.blk_bytes;
     float *red = reinterpret_cast<float *>(wbase);
 
     if (tid == 0) { TMAC_TRACE(0); }
@@ -498,7 +499,7 @@ __global__ void __launch_bounds__(kG3MaxWarps * 32, MINB) gemv3_kernel(const Gem
     // ---- first chunk: HBM -> shared, issued before the dependency wait -------------------------
     if (c_first < c_end) {
         const unsigned char *src = rsb_base + (size_t)c_first * p.blk_bytes;
-        for (int i = lane; i < n16; i += 32) cp_async16(stage + i * 16, src + i * 16, pol);
+        for (int i = lane; i < n16; i += 32) cp_async16(stage0 + i * 16, src + i * 16, pol);
         cp_async_commit();
         if (p.Wnext && lane == 0)                  // pull the next tensor's blocks of this warp into L2
             l2_prefetch_bulk(p.Wnext + (size_t)rsb * p.rsb_stride + (size_t)c_first * p.blk_bytes,
@@ -527,7 +528,15 @@ __global__ void __launch_bounds__(kG3MaxWarps * 32, MINB) gemv3_kernel(const Gem
 #pragma unroll
             for (int a = 0; a < NAG; ++a) { lsv[a] = __ldg(lsg + c * NAG + a); lbsum += __ldg(lbg + c * NAG + a); }
         }
-        cp_async_wait_all();
+        unsigned char *stage = stage0 + (size_t)((c - c_first) & (nbuf - 1)) * p.blk_bytes;
+        if (nbuf == 2 && c + 1 < c_end) {          // request chunk c+1 into the other buffer, then wait for chunk c only
+            unsigned char *nxt = stage0 + (size_t)((c + 1 - c_first) & 1) * p.blk_bytes;
+            const unsigned char *src = rsb_base + (size_t)(c + 1) * p.blk_bytes;
+            for (int i = lane; i < n16; i += 32) cp_async16(nxt + i * 16, src + i * 16, pol);
+            cp_async_commit();
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else
+            cp_async_wait_all();
         __syncwarp();
         if (tid == 0 && c == c_first) TMAC_TRACE(3);
         const uint4 *wp = reinterpret_cast<const uint4 *>(stage) + lane;
@@ -564,12 +573,7 @@ __global__ void __launch_bounds__(kG3MaxWarps * 32, MINB) gemv3_kernel(const Gem
                 cacc[i] = v;
             }
         }
-        __syncwarp();                              // stage / table are rewritten by the next chunk
-        if (c + 1 < c_end) {
-            const unsigned char *src = rsb_base + (size_t)(c + 1) * p.blk_bytes;
-            for (int i = lane; i < n16; i += 32) cp_async16(stage + i * 16, src + i * 16, pol);
-            cp_async_commit();
-        }
+        __syncwarp();                              // stage / table are rewritten by a later chunk
     }
     if (tid == 0) TMAC_TRACE(4);
     if (p.pdl_late) pdl_launch_dependents();
