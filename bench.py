@@ -11,6 +11,7 @@ larger than L2), each with its own activation row.  The step is captured once in
 replayed; time is CUDA events on the launching stream, max over ranks.
 
   value     = algorithmic bytes of all ranks / step time, inputs resident in HBM          [GB/s]
+              (step = one tmac_b200_gemv call per layer: LUT build fused into the GEMV launch)
   roofline  = the dominant kernel (gemv_kernel) alone: algorithmic bytes per launch / its
               average duration (graph of gemv launches only, same rotating buffers) vs the
               measured HBM peak in MEASURED_PEAKS.json
@@ -229,6 +230,12 @@ def main():
         out = torch.zeros((LAYERS, MOUT), device="cuda")
         gathered = torch.zeros((world, LAYERS, MOUT), device="cuda") if world > 1 else None
 
+    def fused_step_calls(_unused=True):
+        for i, wt in enumerate(layers):           # the reference-facing plugin call: init + compute in one (fused LUT build)
+            if PREFETCH_NEXT:
+                lib.tmac_b200_hint_next_weights(layers[(i + 1) % LAYERS].handle)
+            tb.gemv(wt, 1, x[i], out[i])
+
     def step_calls(with_pre=True):
         for i, wt in enumerate(layers):
             if with_pre:
@@ -237,20 +244,22 @@ def main():
                 lib.tmac_b200_hint_next_weights(layers[(i + 1) % LAYERS].handle)
             tb.qgemm_lut(wt, 1, qlut[i], ls[i], lb[i], out[i])
 
-    def capture(with_pre):
-        step_calls(with_pre)                     # eager warm-up allocates every workspace
+    def capture(with_pre, fn=None):
+        fn = fn or step_calls
+        fn(with_pre)                             # eager warm-up allocates every workspace
         tb.check(lib.tmac_b200_sync(), "sync")
         if args.eager:
-            return with_pre
+            return ("eager", fn, with_pre)
         tb.check(lib.tmac_b200_graph_begin(), "graph_begin")
-        step_calls(with_pre)
+        fn(with_pre)
         g = lib.tmac_b200_graph_end()
         tb.check(g, "graph_end")
         return g
 
-    g_step = capture(True)
-    g_gemv = capture(False)
+    g_two = capture(True)                        # two-call path: preprocessor_int8 + qgemm_lut_int8 style
+    g_gemv = capture(False)                      # qgemm_lut launches only (dominant kernel)
     lone_cfg = tb.last_launch()
+    g_step = capture(True, fused_step_calls)     # one call per layer (tmac_b200_gemv, LUT built inside the GEMV)
 
     def grouped_calls():
         tb.qgemm_lut_grouped(layers, 1, [qlut[i] for i in range(LAYERS)], [ls[i] for i in range(LAYERS)],
@@ -262,12 +271,12 @@ def main():
         tb.check(lib.tmac_b200_graph_begin(), "graph_begin")
         grouped_calls()
         g_grouped = lib.tmac_b200_graph_end(); tb.check(g_grouped, "graph_end")
-    kernels_per_step = 2 * LAYERS
+    kernels_per_step = LAYERS
 
     def run_steps(graph, n):
         if args.eager:
             for _ in range(n):
-                step_calls(bool(graph))
+                graph[1](graph[2])
             return
         tb.check(lib.tmac_b200_graph_launch(graph, 1) if n == 1 else lib.tmac_b200_graph_launch(graph, n), "graph_launch")
 
@@ -309,6 +318,8 @@ def main():
     bytes_step = LAYERS * algorithmic_bytes()
     value = world * bytes_step / (ms_per_step * 1e-3) / 1e9
 
+    timed(g_two, 3, False)
+    ms_two = timed(g_two, args.steps, False) / args.steps
     # ---- roofline of the dominant kernel: gemv launches only --------------------------------------
     timed(g_gemv, 3, False)
     ms_g = timed(g_gemv, args.steps, False)
@@ -316,7 +327,9 @@ def main():
     peak, peak_src = measured_peak()
     achieved = algorithmic_bytes() / t_gemv / 1e9
     roofline = {"bound": "hbm", "kernel": "gemv3_kernel<PB=2,SYM,QCH=8,AGQ=4>", "launch": lone_cfg, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": peak_src, "us_per_launch": t_gemv * 1e6, "algorithmic_bytes_per_launch": algorithmic_bytes(), "traffic": None}
+                "peak_source": peak_src, "us_per_launch": t_gemv * 1e6,
+                "two_call_step": {"what": "preprocessor + qgemm_lut as two launches per layer (the reference's init/compute split)",
+                                  "ms_per_step": ms_two, "GBps": bytes_step / (ms_two * 1e-3) / 1e9}, "algorithmic_bytes_per_launch": algorithmic_bytes(), "traffic": None}
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
@@ -407,9 +420,15 @@ def tokens_per_second(tb, lib, torch, stream):
         def token():
             for layer in range(m["L"]):
                 for (hs, cnt, k, ags, xb, q, l1, l2, o) in plan:
-                    tb.preprocessor(k, 1, ags, xb, l1, l2, q)
-                    for c in range(cnt):
-                        tb.qgemm_lut(hs[layer * cnt + c], 1, q, l1, l2, o[c])
+                    if cnt == 1 and not m["os"]:
+                        tb.gemv(hs[layer], 1, xb, o[0])                      # LUT built inside the GEMV
+                    else:                                                  # q/k/v, gate/up share one LUT: one grouped launch
+                        tb.preprocessor(k, 1, ags, xb, l1, l2, q)
+                        if cnt == 1:
+                            tb.qgemm_lut(hs[layer], 1, q, l1, l2, o[0])
+                        else:
+                            tb.qgemm_lut_grouped(hs[layer * cnt:(layer + 1) * cnt], 1, [q] * cnt, [l1] * cnt, [l2] * cnt,
+                                                 [o[c] for c in range(cnt)])
         token()
         tb.check(lib.tmac_b200_sync(), "sync")
         tb.check(lib.tmac_b200_graph_begin(), "graph_begin")

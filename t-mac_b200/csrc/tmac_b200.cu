@@ -83,6 +83,7 @@ struct Context {
     int use_pdl = 1;
     int cs_override = 0, wpc_override = 0, pdl_late = 1, minb_override = 0;
     int last_launch[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int use_fused = 1;                   // tmac_b200_gemv builds the LUT inside the GEMV when the grouping allows
     int64_t next_hint = 0;               // one-shot: tensor whose blocks the next launch prefetches into L2
     std::map<int64_t, Resident> res;
     int64_t next_handle = 1;
@@ -131,6 +132,7 @@ int ensure_init() {
     if (const char *e = getenv("TMAC_B200_CS")) g.cs_override = atoi(e);
     if (const char *e = getenv("TMAC_B200_PDL_LATE")) g.pdl_late = atoi(e);
     if (const char *e = getenv("TMAC_B200_MINB")) g.minb_override = atoi(e);
+    if (const char *e = getenv("TMAC_B200_FUSED")) g.use_fused = atoi(e);
     if (const char *e = getenv("TMAC_B200_WPC")) g.wpc_override = atoi(e);
     g.inited = true;
     return 0;
@@ -178,6 +180,27 @@ template <int MINB> gemv3_fn pick_gemv3_m(int pb, bool sym, int qch, int agq) {
 gemv3_fn pick_gemv3(int pb, bool sym, int qch, int agq, int minb) {
     return minb == 3 ? pick_gemv3_m<3>(pb, sym, qch, agq) : pick_gemv3_m<4>(pb, sym, qch, agq);
 }
+// fused-LUT instantiations (symmetric by construction, activation group inside the chunk)
+template <int PB, int MINB> gemv3_fn pick3_fused_qa(int qch, int agq) {
+    switch (qch * 16 + agq) {
+        case 8 * 16 + 8: return gemv3_kernel<PB, true, 8, 8, MINB, true>;
+        case 8 * 16 + 4: return gemv3_kernel<PB, true, 8, 4, MINB, true>;
+        case 8 * 16 + 2: return gemv3_kernel<PB, true, 8, 2, MINB, true>;
+        case 4 * 16 + 4: return gemv3_kernel<PB, true, 4, 4, MINB, true>;
+        case 4 * 16 + 2: return gemv3_kernel<PB, true, 4, 2, MINB, true>;
+        case 2 * 16 + 2: return gemv3_kernel<PB, true, 2, 2, MINB, true>;
+    }
+    return nullptr;
+}
+template <int MINB> gemv3_fn pick_fused_m(int pb, int qch, int agq) {
+    if (pb == 4) return pick3_fused_qa<4, MINB>(qch, agq);
+    if (pb == 2) return pick3_fused_qa<2, MINB>(qch, agq);
+    if (pb == 1) return pick3_fused_qa<1, MINB>(qch, agq);
+    return nullptr;
+}
+gemv3_fn pick_gemv3_fused(int pb, int qch, int agq, int minb) {
+    return minb == 3 ? pick_fused_m<3>(pb, qch, agq) : pick_fused_m<4>(pb, qch, agq);
+}
 
 int ilog2(int v) { int s = 0; while ((1 << (s + 1)) <= v) ++s; return s; }
 
@@ -209,7 +232,8 @@ struct BatchPtrs { int n = 0; const unsigned char *const *W = nullptr; const int
                    *const *lb = nullptr; void *const *C = nullptr; };
 
 int launch_gemv3(const Resident &R, int row_begin, int row_end, int N, const int8_t *qlut, const float *ls, const float *lb, void *C,
-                 int ldc, int c_row0, int out_f16, bool sym, const BatchPtrs *batch = nullptr) {
+                 int ldc, int c_row0, int out_f16, bool sym, const BatchPtrs *batch = nullptr, const void *fused_act = nullptr,
+                 int act_f16 = 0) {
     const StreamLayout &L = R.L;
     if (row_begin < 0 || row_end > L.Mout || row_begin >= row_end) return fail("qgemm_lut: bad row range");
     const int rsb0 = row_begin / L.rsb, rsb1 = (row_end + L.rsb - 1) / L.rsb, nrsb = rsb1 - rsb0;
@@ -253,7 +277,8 @@ int launch_gemv3(const Resident &R, int row_begin, int row_end, int N, const int
         p.trace = (long long *)g.d_trace.p + per * (size_t)(g.trace_seq++ % 8);
         g.trace_ctas = nrsb * p.cs;
     }
-    gemv3_fn fn = pick_gemv3(L.pb, sym, L.qch, agq, minb);
+    if (fused_act) { p.act = fused_act; p.act_f16 = act_f16; sym = true; }
+    gemv3_fn fn = fused_act ? pick_gemv3_fused(L.pb, L.qch, agq, minb) : pick_gemv3(L.pb, sym, L.qch, agq, minb);
     if (!fn) return fail("qgemm_lut: unsupported chunking (qch=" + std::to_string(L.qch) + ", agq=" + std::to_string(agq) + ")");
     const size_t smem = (size_t)p.cs * L.rsb * 4 +
                         std::max((size_t)p.wpc * ((p.bpw > 1 ? 2 : 1) * L.blk + (size_t)L.qch * 4 * (sym ? 8 : 16)), (size_t)p.wpc * L.rsb * 4);
@@ -915,16 +940,24 @@ int tmac_b200_gemv(int64_t handle, int N, int dtype, const void *B, void *C) {
         stage_mark();
         dB = g.d_b.p;
     }
-    if (g.d_qlut.ensure(qb) || g.d_ls.ensure(sb) || g.d_lb.ensure(sb)) return fail("out of device memory");
-    if (launch_preprocessor(L.K, N, L.act_group_size, dtype, dB, (float *)g.d_ls.p, (float *)g.d_lb.p, (int8_t *)g.d_qlut.p)) return -1;
     void *dC = C;
     if (!dev_c) {
         if (g.d_c.ensure(cb)) return fail("out of device memory");
         dC = g.d_c.p;
     }
-    const bool sym = g.lut_mode != 1;
-    if (launch_gemv(R, 0, L.Mout, N, (const int8_t *)g.d_qlut.p, (const float *)g.d_ls.p, (const float *)g.d_lb.p, dC, L.Mout, 0,
-                    dtype == TMAC_B200_F16, sym, nullptr)) return -1;
+    const bool int_path = L.one_scale && L.act_group_size == L.K;
+    const bool can_fuse = g.use_fused && g.kernel_version != 1 && !int_path && L.act_group_size <= L.ck && g.lut_mode != 1;
+    if (can_fuse) {
+        // one launch: the GEMV builds each chunk's LUT slice itself (bit-identical tables)
+        if (launch_gemv3(R, 0, L.Mout, N, nullptr, nullptr, nullptr, dC, L.Mout, 0, dtype == TMAC_B200_F16, true, nullptr, dB,
+                         dtype == TMAC_B200_F16)) return -1;
+    } else {
+        if (g.d_qlut.ensure(qb) || g.d_ls.ensure(sb) || g.d_lb.ensure(sb)) return fail("out of device memory");
+        if (launch_preprocessor(L.K, N, L.act_group_size, dtype, dB, (float *)g.d_ls.p, (float *)g.d_lb.p, (int8_t *)g.d_qlut.p)) return -1;
+        const bool sym = g.lut_mode != 1;
+        if (launch_gemv(R, 0, L.Mout, N, (const int8_t *)g.d_qlut.p, (const float *)g.d_ls.p, (const float *)g.d_lb.p, dC, L.Mout, 0,
+                        dtype == TMAC_B200_F16, sym, nullptr)) return -1;
+    }
     if (!dev_c) {
         if (g.h_out.ensure(cb)) return fail("out of pinned memory");
         CUDA_OK(cudaMemcpyAsync(g.h_out.p, dC, cb, cudaMemcpyDeviceToHost, g.stream()));

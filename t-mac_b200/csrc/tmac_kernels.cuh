@@ -416,6 +416,9 @@ struct Gemv3Params {
     const int8_t *const *qlutv;
     const float *const *lsv, *const *lbv;
     void *const *Cv;
+    // fused LUT construction (FUSED instantiations): activations [N][K] f32 or f16 instead of qlut / lut_scales / lut_biases
+    const void *act;
+    int act_f16;
     size_t rsb_stride;
     float scale0;
     long long *trace;
@@ -458,7 +461,11 @@ constexpr int kG3MaxWarps = 8;
 
 // MINB = minimum resident CTAs per SM the register allocation is tuned for: 3 (85 registers, more ILP;
 // best for a single launch per tensor) or 4 (64 registers, more CTAs in flight; best for grouped launches).
-template <int PB, bool SYM, int QCH, int AGQ, int MINB>
+// FUSED = build the LUT slice of each chunk inside the GEMV from the activation row (same fp32 operation
+// order as preprocessor_kernel / lut_ctor.cc, so QLUT bytes, LUT scales and LUT biases are bit-identical to
+// the two-kernel path) instead of reading QLUT / LUT_Scales / LUT_Biases.  Requires AGQ > 0 (activation
+// group inside a chunk) and SYM.
+template <int PB, bool SYM, int QCH, int AGQ, int MINB, bool FUSED = false>
 __global__ void __launch_bounds__(kG3MaxWarps * 32, MINB) gemv3_kernel(const Gemv3Params p, const uint32_t wtx, const uint32_t wty) {
     constexpr int RW = 8 / PB;
     constexpr int RSB = 32 * RW;
@@ -518,15 +525,71 @@ __global__ void __launch_bounds__(kG3MaxWarps * 32, MINB) gemv3_kernel(const Gem
 
     for (int c = c_first; c < c_end; ++c) {
         // ---- LUT slice of this chunk -> warp-private table (lane = group) ---------------------
-        if (lane < QCH * 4) {
-            const uint4 L = __ldg(qrow + (size_t)c * QCH * 4 + lane);
-            if (SYM) reinterpret_cast<uint2 *>(tab)[lane] = make_uint2(L.x, L.y);
-            else reinterpret_cast<uint4 *>(tab)[lane] = make_uint4(L.x, L.y, __byte_perm(L.w, 0, 0x0123), __byte_perm(L.z, 0, 0x0123));
-        }
         float lsv[NAG], lbsum = 0.f;
-        if (!INT_PATH) {
+        if (FUSED) {
+            // lane = K-group of the chunk; W = lanes per activation group.  Arithmetic = lut_ctor.cc:119-215
+            // (AVX2 branch) and partial_max_g4_int8_k8 (:242-256), all with explicit round-to-nearest ops.
+            constexpr int NG = QCH * 4, W = (AGQ ? AGQ : 1) * 4;
+            float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+            if (lane < NG) {
+                const size_t k0 = (size_t)n * p.K + ((size_t)c * NG + lane) * 4;
+                if (p.act_f16) {
+                    const uint2 h = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const __half *>(p.act) + k0));
+                    const float2 f01 = __half22float2(*reinterpret_cast<const __half2 *>(&h.x)), f23 = __half22float2(*reinterpret_cast<const __half2 *>(&h.y));
+                    b0 = f01.x; b1 = f01.y; b2 = f23.x; b3 = f23.y;
+                } else {
+                    const float4 f = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p.act) + k0));
+                    b0 = f.x; b1 = f.y; b2 = f.z; b3 = f.w;
+                }
+            }
+            float m = __fadd_rn(__fadd_rn(fabsf(b0), fabsf(b1)), __fadd_rn(fabsf(b2), fabsf(b3)));
 #pragma unroll
-            for (int a = 0; a < NAG; ++a) { lsv[a] = __ldg(lsg + c * NAG + a); lbsum += __ldg(lbg + c * NAG + a); }
+            for (int o = W / 2; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            const float scale = __fdiv_rn(m, 127.0f);
+            const float ts = (scale != 0.0f) ? __fdiv_rn(1.0f, scale) : 0.0f;
+            float od[8];                                   // odd entries 1,3,...,15
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int idx = 2 * e + 1;
+                float v = b0;
+                v = (idx & 2) ? __fadd_rn(v, b1) : __fsub_rn(v, b1);
+                v = (idx & 4) ? __fadd_rn(v, b2) : __fsub_rn(v, b2);
+                v = (idx & 8) ? __fadd_rn(v, b3) : __fsub_rn(v, b3);
+                od[e] = v;
+            }
+            // stored entries 0..7: even e = -LUT[15-e] (= -od[(15-e)/2]), odd e = od[e/2]
+            uint32_t lo = 0, hi = 0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float lv = (e & 1) ? od[e >> 1] : -od[(15 - e) >> 1];
+                int q = __float2int_rn(__fmul_rn(lv, ts));
+                q = max(-128, min(127, q));
+                if (e < 4) lo |= (uint32_t)(q & 0xff) << (8 * e); else hi |= (uint32_t)(q & 0xff) << (8 * (e - 4));
+            }
+            if (lane < NG) reinterpret_cast<uint2 *>(tab)[lane] = make_uint2(lo, hi);
+            // LUT bias: _mm256_addv_ps tree per 8 groups (lut_ctor.cc:24-31), serial over the blocks of a group (:157)
+            float v = -od[7];                              // LUT[0] = -LUT[15]
+            v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 4));
+            v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 2));
+            v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 1));
+#pragma unroll
+            for (int a = 0; a < NAG; ++a) {
+                lsv[a] = __shfl_sync(0xffffffffu, scale, a * W);
+                float bias = 0.f;
+#pragma unroll
+                for (int k = 0; k < W / 8; ++k) bias = __fadd_rn(bias, __shfl_sync(0xffffffffu, v, a * W + 8 * k));
+                lbsum += bias;
+            }
+        } else {
+            if (lane < QCH * 4) {
+                const uint4 L = __ldg(qrow + (size_t)c * QCH * 4 + lane);
+                if (SYM) reinterpret_cast<uint2 *>(tab)[lane] = make_uint2(L.x, L.y);
+                else reinterpret_cast<uint4 *>(tab)[lane] = make_uint4(L.x, L.y, __byte_perm(L.w, 0, 0x0123), __byte_perm(L.z, 0, 0x0123));
+            }
+            if (!INT_PATH) {
+#pragma unroll
+                for (int a = 0; a < NAG; ++a) { lsv[a] = __ldg(lsg + c * NAG + a); lbsum += __ldg(lbg + c * NAG + a); }
+            }
         }
         unsigned char *stage = stage0 + (size_t)((c - c_first) & (nbuf - 1)) * p.blk_bytes;
         if (nbuf == 2 && c + 1 < c_end) {          // request chunk c+1 into the other buffer, then wait for chunk c only

@@ -250,6 +250,35 @@ def test_full_size_properties(lib, oracle):
         wt.free(); wt2.free()
 
 
+@pytest.mark.parametrize("cfg", [T.Config(512, 2048, 2, zero_point=True), T.Config(256, 1024, 4), T.Config(384, 1024, 3, zero_point=True),
+                                 T.Config(512, 1024, 1), T.Config(256, 1024, 4, kfactor=8, group_size=32, act_group_size=32)],
+                         ids=["w2zp", "w4", "w3zp", "w1", "w4g32"])
+def test_fused_gemv_is_bit_identical_to_two_call_path(lib, oracle, cfg):
+    """tmac_b200_gemv builds the LUT inside the GEMV (one launch); the tables, LUT scales and biases it uses are
+    bit-identical to preprocessor_int8's, so the output equals preprocessor + qgemm_lut exactly."""
+    cfg = cfg.resolved()
+    w, sc, z, x = T.make_problem(cfg, seed=13, N=2)
+    wt = tb.upload_plain(kc(cfg), w, sc, z)
+    try:
+        dx = torch.from_numpy(x).cuda()
+        fused = torch.zeros((2, cfg.Mout), device="cuda")
+        tb.gemv(wt, 2, dx, fused)
+        nag = cfg.K // cfg.act_group_size
+        q = torch.zeros((2, cfg.K // 4, 16), dtype=torch.int8, device="cuda")
+        ls = torch.zeros((2, nag), device="cuda"); lb = torch.zeros_like(ls)
+        two = torch.zeros((2, cfg.Mout), device="cuda")
+        tb.preprocessor(cfg.K, 2, cfg.act_group_size, dx, ls, lb, q)
+        tb.qgemm_lut(wt, 2, q, ls, lb, two)
+        torch.cuda.synchronize()
+        assert torch.equal(fused, two)
+        A, S = T.pack_reference_layout(w, sc, z, cfg)
+        qo, lso, lbo = oracle.preprocessor(x, cfg.act_group_size)
+        Co = oracle.qgemm(cfg, A, S, qo, lso, lbo)
+        assert np.abs(fused.cpu().numpy() - Co).max() <= TIGHT_TOL * np.abs(Co).max()
+    finally:
+        wt.free()
+
+
 def test_grouped_launch_equals_single_launches(lib, oracle):
     """tmac_b200_qgemm_lut_grouped (q/k/v-style fused launch) is bit-identical to per-tensor launches."""
     cfg = T.Config(512, 2048, 2, zero_point=True).resolved()
