@@ -81,7 +81,7 @@ struct Context {
     int ks_override = 0;
     int kernel_version = 3;              // 3 = gemv3_kernel (clusters + DSMEM + PDL), 1 = gemv_kernel (split-K scratch)
     int use_pdl = 1;
-    int cs_override = 0, wpc_override = 0, pdl_late = 1, minb_override = 0;
+    int cs_override = 0, wpc_override = 0, pdl_late = -1, minb_override = 0;
     int last_launch[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int use_fused = 1;                   // tmac_b200_gemv builds the LUT inside the GEMV when the grouping allows
     int64_t next_hint = 0;               // one-shot: tensor whose blocks the next launch prefetches into L2
@@ -253,7 +253,7 @@ int launch_gemv3(const Resident &R, int row_begin, int row_end, int N, const int
     const int agq = int_path ? 0 : std::min(L.act_group_size, L.ck) / 16;
     p.zp = L.zp; p.one_scale = L.one_scale; p.sd = L.sd; p.out_f16 = out_f16;
     p.blk_bytes = (int)L.blk; p.scale0 = L.scale0; p.rsb_stride = L.rsb_stride;
-    p.pdl_late = g.pdl_late;
+    p.pdl_late = (g.pdl_late >= 0) ? g.pdl_late : (fused_act ? 0 : 1);   // measured: fused launches prefer the early trigger
     const int nb = batch ? batch->n : 0;
     if (batch) { p.nbatch = nb; p.Wv = batch->W; p.qlutv = batch->q; p.lsv = batch->ls; p.lbv = batch->lb; p.Cv = batch->C; }
     choose_decomposition(nrsb, L.nchunk, N * std::max(1, nb), &p.cs, &p.wpc, &p.bpw);

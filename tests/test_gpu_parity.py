@@ -123,6 +123,10 @@ SHAPES = [
     (T.Config(256, 1024, 4, kfactor=8, group_size=32, act_group_size=32), 1),
     (T.Config(320, 1024, 2, bm=320, group_size=64, act_group_size=64, zero_point=True), 1),
     (T.Config(192, 512, 2, bm=128, zero_point=True), 1),  # 192 rows = 1.5 super-blocks: ragged last super-block
+    (T.Config(512, 18944, 4), 1),                         # Qwen2-7B down-proj K: 148 chunks per super-block
+    (T.Config(1024, 3584, 4, zero_point=True), 3),        # Qwen2-7B hidden size, batch 3
+    (T.Config(64, 128, 4), 1),                            # smallest legal tensor: one super-block, one chunk
+    (T.Config(128, 96, 2, bm=256, kfactor=8, group_size=32, act_group_size=32), 1),  # K = 96: three 32-wide chunks
 ]
 
 
