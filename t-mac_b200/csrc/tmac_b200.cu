@@ -942,8 +942,10 @@ int tmac_b200_gemv(int64_t handle, int N, int dtype, const void *B, void *C) {
     }
     void *dC = C;
     if (!dev_c) {
-        if (g.d_c.ensure(cb)) return fail("out of device memory");
-        dC = g.d_c.p;
+        // the kernel stores the (small) output straight into pinned host memory (UVA-mapped): one DMA-free write
+        // instead of a device buffer + cudaMemcpyAsync D2H
+        if (g.h_out.ensure(cb)) return fail("out of pinned memory");
+        dC = g.h_out.p;
     }
     const bool int_path = L.one_scale && L.act_group_size == L.K;
     const bool can_fuse = g.use_fused && g.kernel_version != 1 && !int_path && L.act_group_size <= L.ck && g.lut_mode != 1;
@@ -959,8 +961,6 @@ int tmac_b200_gemv(int64_t handle, int N, int dtype, const void *B, void *C) {
                         dtype == TMAC_B200_F16, sym, nullptr)) return -1;
     }
     if (!dev_c) {
-        if (g.h_out.ensure(cb)) return fail("out of pinned memory");
-        CUDA_OK(cudaMemcpyAsync(g.h_out.p, dC, cb, cudaMemcpyDeviceToHost, g.stream()));
         CUDA_OK(cudaStreamSynchronize(g.stream()));
         std::memcpy(C, g.h_out.p, cb);
     }
