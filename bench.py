@@ -445,6 +445,27 @@ def tokens_per_second(tb, lib, torch, stream):
         lib.tmac_b200_graph_free(g)
         for h in handles:
             h.free()
+    # Prefill-shaped call (BASELINE config 4: Llama-2-7B W2, seq 256): today the N>1 path runs the GEMV kernel once per
+    # activation row (grid.y = N; weight re-reads hit L2).  Reported so that the tcgen05 tile of a later round has a baseline.
+    try:
+        NB = 256
+        w, sc, z = synth(9)
+        cfg = tb.make_kcfg(MOUT, K, BITS, 128, 16, GS, AGS, ZP, False)
+        wt = tb.upload_plain(cfg, w, sc, z)
+        with torch.cuda.stream(stream):
+            xb = torch.randn((NB, K), device="cuda"); ob = torch.zeros((NB, MOUT), device="cuda")
+        tb.gemv(wt, NB, xb, ob); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(3):
+            tb.gemv(wt, NB, xb, ob)
+        e1.record(stream); torch.cuda.synchronize()
+        s = e0.elapsed_time(e1) / 3 * 1e-3
+        res["prefill_seq256_one_tensor_11008x4096_w2"] = {"ms": s * 1e3, "dense_equivalent_TFLOPs": 2.0 * NB * MOUT * K / s / 1e12,
+                                                          "path": "GEMV kernel per activation row (ALU pipe); tcgen05 int8 tile not built yet"}
+        wt.free()
+    except Exception as ex:
+        res["prefill_seq256_one_tensor_11008x4096_w2"] = {"error": str(ex)[:160]}
     return res
 
 
