@@ -451,6 +451,10 @@ __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Split barrier used to establish "every CTA of the cluster is running" before the first
+// distributed-shared-memory access (required by the programming model), without stalling at entry.
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
 __device__ __forceinline__ void st_cluster_f32(float *local_ptr, uint32_t rank, float v) {
     uint32_t laddr = (uint32_t)__cvta_generic_to_shared(local_ptr), raddr;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(rank));
@@ -489,6 +493,7 @@ __global__ void __launch_bounds__(kG3MaxWarps * 32, MINB) gemv3_kernel(const Gem
     float *red = reinterpret_cast<float *>(wbase);
 
     if (tid == 0) { TMAC_TRACE(0); }
+    if (p.cs > 1) cluster_arrive_relaxed();       // phase 1: "I am running" (waited for right before the DSMEM stores)
     if (!p.pdl_late) pdl_launch_dependents();     // the next launch may start its weight stream now
 
     const int c_first = (rank * WPC + warp) * p.bpw;
@@ -651,6 +656,7 @@ __global__ void __launch_bounds__(kG3MaxWarps * 32, MINB) gemv3_kernel(const Gem
     __syncthreads();
     if (tid == 0) TMAC_TRACE(5);
     const int nthreads = WPC * 32;
+    if (p.cs > 1) cluster_wait();                 // every CTA of the cluster has started: its shared memory may be written
     for (int t = tid; t < RSB; t += nthreads) {
         float fsum = 0.f; int isum = 0;
         for (int w = 0; w < WPC; ++w) {

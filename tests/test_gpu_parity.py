@@ -29,8 +29,14 @@ def lib():
         pytest.fail("-m gpu tests need a CUDA device; libtmac_b200 has no CPU fallback")
     lib = tb.load()
     tb.check(lib.tmac_b200_init(0), "init")
+    # one stream for torch's allocations/fills AND the library's launches: the library's own stream is
+    # non-blocking, i.e. NOT ordered after work that torch enqueues on the legacy default stream
+    st = torch.cuda.Stream()
+    torch.cuda.set_stream(st)
+    tb.check(lib.tmac_b200_set_stream(st.cuda_stream), "set_stream")
+    yield lib
+    torch.cuda.synchronize()
     tb.check(lib.tmac_b200_set_stream(None), "set_stream")
-    return lib
 
 
 def kc(cfg):

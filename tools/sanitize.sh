@@ -1,9 +1,9 @@
-# compute-sanitizer pass over a subset of the GPU parity tests (memcheck + racecheck of the shared-memory LUT / stage / DSMEM code)
 mkdir -p gpurun_out
 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "golden or fused or grouped or general" 2>&1 | tail -6 > gpurun_out/r1_sanitizer.txt
-echo "memcheck rc=$?" >> gpurun_out/r1_sanitizer.txt
-compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "w2_zp_g128 or w4_sym or bitnet_int32 or fused" 2>&1 | tail -6 >> gpurun_out/r1_sanitizer.txt
-echo "racecheck rc=$?" >> gpurun_out/r1_sanitizer.txt
-cat gpurun_out/r1_sanitizer.txt
-python bench.py --steps 10 --warmup 3 2>gpurun_out/b4.err | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('e2e', d['e2e']); print(d['tokens_per_s'].get('prefill_seq256_one_tensor_11008x4096_w2'))"
-tail -3 gpurun_out/b4.err
+echo "memcheck done" >> gpurun_out/r1_sanitizer.txt
+compute-sanitizer --tool racecheck --racecheck-report all --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "w2_zp_g128 or w4_sym or bitnet_int32 or fused" > gpurun_out/r1_racecheck_full.txt 2>&1
+grep -E "hazard|Hazard|passed|failed|SUMMARY" gpurun_out/r1_racecheck_full.txt | sort | uniq -c | sort -rn | head -20 >> gpurun_out/r1_sanitizer.txt
+grep -m2 -B2 -A14 "^E " gpurun_out/r1_racecheck_full.txt | head -40 >> gpurun_out/r1_sanitizer.txt
+compute-sanitizer --tool initcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "w2_zp_g128 or general" 2>&1 | tail -8 >> gpurun_out/r1_sanitizer.txt
+cat gpurun_out/r1_sanitizer.txt | cut -c1-220
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2

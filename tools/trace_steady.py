@@ -10,6 +10,7 @@ import torch
 import tmac_b200 as tb
 import bench
 lib = tb.load(); tb.check(lib.tmac_b200_init(0), "init")
+_st = torch.cuda.Stream(); torch.cuda.set_stream(_st); tb.check(lib.tmac_b200_set_stream(_st.cuda_stream), "set_stream")
 w, sc, z = bench.synth(1)
 cfg = tb.make_kcfg(bench.MOUT, bench.K, 2, 128, 16, 128, 64, True, False)
 base = tb.upload_plain(cfg, w, sc, z)
