@@ -123,7 +123,7 @@ int ensure_init() {
     CUDA_OK(cudaGetDeviceProperties(&prop, dev));
     if (prop.major < 10) return fail("libtmac_b200 is built for sm_100a only (found sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + ")");
     g.sms = prop.multiProcessorCount;
-    CUDA_OK(cudaStreamCreateWithFlags(&g.own, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreate(&g.own));   // blocking stream: ordered after the legacy default stream (safe default for torch/ggml callers)
     if (const char *e = getenv("TMAC_B200_KS")) g.ks_override = atoi(e);
     if (const char *e = getenv("TMAC_B200_LUT_MODE")) g.lut_mode = atoi(e);
     if (const char *e = getenv("TMAC_B200_KERNEL")) g.kernel_version = atoi(e);
