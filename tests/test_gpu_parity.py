@@ -209,6 +209,39 @@ def test_tile_calls_like_ggml(lib, oracle):
         wt.free()
 
 
+def test_ggml_hook_transform_tensor_i2_blob(lib, oracle):
+    """The load-time path of the llama.cpp fork: an I2 tensor blob `permuted weights || fp32 scales`
+    (python/t_mac/model_utils.py:271, ggml-tmac.cpp:336-345) goes through ggml_tmac_b200_transform_tensor, then the
+    whole-tensor task_init / task_compute calls (the TVM-threadpool branch of ggml.c:12610-12630) with host buffers."""
+    cfg = T.Config(768, 1024, 2, bm=128, zero_point=True).resolved()
+    w, sc, z, x = T.make_problem(cfg, seed=17)
+    A, S = T.pack_reference_layout(w, sc, z, cfg)
+    blob = np.concatenate([A.reshape(-1).view(np.uint8), S.view(np.uint8)]).copy()
+    k = kc(cfg)
+    lib.tmac_b200_clear_kcfg()
+    tb.check(lib.tmac_b200_register_kcfg(C.byref(k)), "register")
+    extra = tb.TensorExtra()
+    h = lib.ggml_tmac_b200_transform_tensor(blob.ctypes.data, cfg.K, cfg.Mout, cfg.bits, C.byref(extra))
+    assert h > 0, tb.last_error()
+    try:
+        assert extra.n_tile_num == cfg.n_tile_num and extra.scales_size == cfg.scales_size
+        assert extra.lut_scales_size == cfg.K // cfg.act_group_size and extra.qweights == blob.ctypes.data
+        assert lib.ggml_tmac_b200_get_nbytes(cfg.K, cfg.Mout, cfg.bits) == blob.nbytes
+        nag = cfg.K // cfg.act_group_size
+        q = np.zeros((1, cfg.K // 4, 16), np.int8); ls = np.zeros((1, nag), np.float32); lb = np.zeros_like(ls)
+        out = np.zeros((1, cfg.Mout), np.float32)
+        lib.ggml_tmac_mul_mat_task_init(x.ctypes.data, q.ctypes.data, ls.ctypes.data, lb.ctypes.data, cfg.Mout, cfg.K, 1, cfg.bits)
+        lib.ggml_tmac_mul_mat_task_compute(extra.qweights, extra.scales, q.ctypes.data, ls.ctypes.data, lb.ctypes.data, out.ctypes.data,
+                                           cfg.Mout, cfg.K, 1, cfg.bits)
+        qo, lso, lbo = oracle.preprocessor(x, cfg.act_group_size)
+        Co = oracle.qgemm(cfg, A, S, qo, lso, lbo)
+        assert np.array_equal(q, qo) and np.array_equal(ls, lso) and np.array_equal(lb, lbo)
+        assert np.abs(out - Co).max() <= TIGHT_TOL * np.abs(Co).max()
+    finally:
+        lib.tmac_b200_free_weights(h)
+        lib.tmac_b200_clear_kcfg()
+
+
 def test_fused_gemv_fp16_and_plain_upload(lib, oracle):
     """tmac_b200_gemv (init+compute in one call) with fp16 activations/outputs (the ARM `T`), weights
     uploaded from un-permuted quantised values."""
