@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "tmac_kernels.cuh"
+#include "tmac_prefill.cuh"
 #include "tmac_layout.h"
 
 using namespace tmac_b200;
@@ -83,7 +84,8 @@ struct Context {
     int use_pdl = 1;
     int cs_override = 0, wpc_override = 0, pdl_late = -1, minb_override = 0;
     int last_launch[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int use_fused = 1;                   // tmac_b200_gemv builds the LUT inside the GEMV when the grouping allows
+    int use_fused = 1;
+    int use_prefill = 1, prefill_min_n = 32;   // N >= prefill_min_n: tcgen05 int8 tile (W2 g128 act64)                   // tmac_b200_gemv builds the LUT inside the GEMV when the grouping allows
     int64_t next_hint = 0;               // one-shot: tensor whose blocks the next launch prefetches into L2
     std::map<int64_t, Resident> res;
     int64_t next_handle = 1;
@@ -133,6 +135,8 @@ int ensure_init() {
     if (const char *e = getenv("TMAC_B200_PDL_LATE")) g.pdl_late = atoi(e);
     if (const char *e = getenv("TMAC_B200_MINB")) g.minb_override = atoi(e);
     if (const char *e = getenv("TMAC_B200_FUSED")) g.use_fused = atoi(e);
+    if (const char *e = getenv("TMAC_B200_PREFILL")) g.use_prefill = atoi(e);
+    if (const char *e = getenv("TMAC_B200_PREFILL_MIN_N")) g.prefill_min_n = atoi(e);
     if (const char *e = getenv("TMAC_B200_WPC")) g.wpc_override = atoi(e);
     g.inited = true;
     return 0;
@@ -314,12 +318,39 @@ int choose_ks(const StreamLayout &L, int nrsb, int N) {
     return ks;
 }
 
+// Prefill tile on tcgen05 (tmac_prefill.cuh).  Returns 1 if the shape is not covered (caller falls back to the GEMV
+// kernel per activation row), 0 on launch, -1 on error.
+int launch_prefill(const Resident &R, int N, const int8_t *qlut, const float *ls, const float *lb, void *C, int ldc, int out_f16, bool sym) {
+    const StreamLayout &L = R.L;
+    if (!g.use_prefill || N < g.prefill_min_n || !sym) return 1;
+    if (L.pb != 2 || L.qch != 8 || L.act_group_size != 64 || L.one_scale || L.ck != 128) return 1;
+    const size_t rawsz = (L.blk + 127) & ~(size_t)127;
+    const size_t nag = (size_t)L.K / 64;
+    const size_t smem = 4 * (size_t)kPfStageBytes + 2 * rawsz + 256 * 8 + nag * kPfNT * 4 + (size_t)L.nchunk * kPfNT * 4 + 8 * 8 + 1024;
+    if (smem > 225 * 1024) return 1;
+    PrefillParams p{};
+    p.W = R.d; p.qlut = qlut; p.lut_scales = ls; p.lut_biases = lb; p.C = C;
+    p.N = N; p.K = L.K; p.Mout = L.Mout; p.ldc = ldc; p.out_f16 = out_f16;
+    p.nchunk = L.nchunk; p.zp = L.zp; p.sd = L.sd; p.blk_bytes = (int)L.blk; p.rsb_stride = L.rsb_stride;
+    CUDA_OK(cudaFuncSetAttribute((const void *)prefill_w2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(L.nrsb, (N + kPfNT - 1) / kPfNT);
+    prefill_w2_kernel<<<grid, kPfThreads, smem, g.stream()>>>(p);
+    CUDA_OK(cudaGetLastError());
+    g.last_launch[0] = 1; g.last_launch[1] = 13; g.last_launch[2] = L.nchunk; g.last_launch[3] = 1; g.last_launch[4] = L.nrsb;
+    g.last_launch[5] = L.pb; g.last_launch[6] = 1; g.last_launch[7] = -N;   // batch < 0 marks the tcgen05 prefill tile
+    return 0;
+}
+
 // v1 launch (one CTA per (super-block, K split); kept for A/B comparison: TMAC_B200_KERNEL=1).
 // Launch qgemm_lut over rows [row_begin,row_end) (relative to the resident tensor).
 // All pointers are device pointers; C is [N][ldc] with C[n][row - c_row0].
 int launch_gemv(const Resident &R, int row_begin, int row_end, int N, const int8_t *qlut, const float *ls,
                 const float *lb, void *C, int ldc, int c_row0, int out_f16, bool sym, int32_t *cbits_unused) {
     (void)cbits_unused;
+    if (g.kernel_version != 1 && row_begin == 0 && row_end == R.L.Mout && c_row0 == 0 && ldc == R.L.Mout) {
+        const int rc = launch_prefill(R, N, qlut, ls, lb, C, ldc, out_f16, sym);
+        if (rc <= 0) return rc;
+    }
     if (g.kernel_version != 1) return launch_gemv3(R, row_begin, row_end, N, qlut, ls, lb, C, ldc, c_row0, out_f16, sym);
     const StreamLayout &L = R.L;
     if (row_begin < 0 || row_end > L.Mout || row_begin >= row_end) return fail("qgemm_lut: bad row range");
@@ -948,7 +979,8 @@ int tmac_b200_gemv(int64_t handle, int N, int dtype, const void *B, void *C) {
         dC = g.h_out.p;
     }
     const bool int_path = L.one_scale && L.act_group_size == L.K;
-    const bool can_fuse = g.use_fused && g.kernel_version != 1 && !int_path && L.act_group_size <= L.ck && g.lut_mode != 1;
+    const bool prefill_shape = g.use_prefill && N >= g.prefill_min_n && L.pb == 2 && L.qch == 8 && L.act_group_size == 64 && !L.one_scale;
+    const bool can_fuse = g.use_fused && g.kernel_version != 1 && !int_path && L.act_group_size <= L.ck && g.lut_mode != 1 && !prefill_shape;
     if (can_fuse) {
         // one launch: the GEMV builds each chunk's LUT slice itself (bit-identical tables)
         if (launch_gemv3(R, 0, L.Mout, N, nullptr, nullptr, nullptr, dC, L.Mout, 0, dtype == TMAC_B200_F16, true, nullptr, dB,

@@ -322,6 +322,41 @@ def test_fused_gemv_is_bit_identical_to_two_call_path(lib, oracle, cfg):
         wt.free()
 
 
+@pytest.mark.parametrize("cfg,N", [(T.Config(256, 1024, 2, zero_point=True), 64), (T.Config(384, 2048, 2), 130),
+                                   (T.Config(256, 4096, 2, zero_point=True), 256)], ids=["zp_n64", "sym_n130", "zp_k4096_n256"])
+def test_prefill_tcgen05_tile_matches_oracle(lib, oracle, cfg, N):
+    """N >= 32, W2 g128 act64: the tcgen05 kind::i8 tile (tmac_prefill.cuh).  The int8 contraction over the LUT is the same
+    integer arithmetic as the GEMV, so the result must match the CPU kernel to the fp re-association tolerance and the
+    GEMV-per-row path to the same tolerance."""
+    cfg = cfg.resolved()
+    w, sc, z, x = T.make_problem(cfg, seed=23, N=N)
+    A, S = T.pack_reference_layout(w, sc, z, cfg)
+    wt = tb.upload_plain(kc(cfg), w, sc, z)
+    try:
+        dx = torch.from_numpy(x).cuda()
+        nag = cfg.K // cfg.act_group_size
+        q = torch.zeros((N, cfg.K // 4, 16), dtype=torch.int8, device="cuda")
+        ls = torch.zeros((N, nag), device="cuda"); lb = torch.zeros_like(ls)
+        out = torch.zeros((N, cfg.Mout), device="cuda")
+        tb.preprocessor(cfg.K, N, cfg.act_group_size, dx, ls, lb, q)
+        tb.qgemm_lut(wt, N, q, ls, lb, out)
+        assert tb.last_launch()["batch"] == -N, "the tcgen05 prefill tile did not run"
+        torch.cuda.synchronize()
+        qo, lso, lbo = oracle.preprocessor(x, cfg.act_group_size)
+        Co = oracle.qgemm(cfg, A, S, qo, lso, lbo)
+        got = out.cpu().numpy()
+        assert np.abs(got - Co).max() <= TIGHT_TOL * np.abs(Co).max()
+        # same call through the one-shot API (preprocessor + tile) and with the tile disabled (GEMV per row)
+        out2 = torch.zeros_like(out)
+        tb.gemv(wt, N, dx, out2)
+        torch.cuda.synchronize()
+        assert torch.equal(out, out2)
+        os.environ["TMAC_B200_PREFILL"] = "0"
+    finally:
+        os.environ.pop("TMAC_B200_PREFILL", None)
+        wt.free()
+
+
 def test_grouped_launch_equals_single_launches(lib, oracle):
     """tmac_b200_qgemm_lut_grouped (q/k/v-style fused launch) is bit-identical to per-tensor launches."""
     cfg = T.Config(512, 2048, 2, zero_point=True).resolved()
