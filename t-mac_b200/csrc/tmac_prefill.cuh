@@ -131,9 +131,8 @@ __global__ void __launch_bounds__(kPfThreads, 1) prefill_w2_kernel(const Prefill
         // ======================= producers: thread = weight row r of the tile =======================
         const int r = tid;                           // 0..127
         const int wl = r >> 2, wi = r & 3;           // lane / row-in-lane of the stream layout (RW = 4)
-        const uint64_t pol = policy_evict_first();
         const int n16 = p.blk_bytes >> 4;
-        for (int i = tid; i < n16; i += 128) cp_async16(raw + i * 16, rsb_base + i * 16, pol);
+        for (int i = tid; i < n16; i += 128) cp_async16_plain(raw + i * 16, rsb_base + i * 16);
         cp_async_commit();
         const uint2 *qrow8 = reinterpret_cast<const uint2 *>(p.qlut);      // 8-byte halves of the 16-byte LUT rows
         for (int c = 0; c < p.nchunk; ++c) {
@@ -141,7 +140,7 @@ __global__ void __launch_bounds__(kPfThreads, 1) prefill_w2_kernel(const Prefill
             if (c + 1 < p.nchunk) {
                 unsigned char *nb = raw + (size_t)((c + 1) & 1) * rawsz;
                 const unsigned char *src = rsb_base + (size_t)(c + 1) * p.blk_bytes;
-                for (int i = tid; i < n16; i += 128) cp_async16(nb + i * 16, src + i * 16, pol);
+                for (int i = tid; i < n16; i += 128) cp_async16_plain(nb + i * 16, src + i * 16);
                 cp_async_commit();
                 asm volatile("cp.async.wait_group 1;" ::: "memory");
             } else
@@ -187,6 +186,7 @@ __global__ void __launch_bounds__(kPfThreads, 1) prefill_w2_kernel(const Prefill
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) pf_mbar_arrive(full + s);
+                __syncwarp();
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");                 // nobody still reads rb when it is refilled
         }
@@ -241,6 +241,7 @@ __global__ void __launch_bounds__(kPfThreads, 1) prefill_w2_kernel(const Prefill
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) pf_mbar_arrive(accempty + b);   // the accumulator buffer may be overwritten
+                    __syncwarp();                                  // reconverge before the next .aligned tcgen05.ld
                 }
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
@@ -281,9 +282,13 @@ __global__ void __launch_bounds__(kPfThreads, 1) prefill_w2_kernel(const Prefill
             }
         }
     }
+    __syncwarp();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+    if (warp == 4) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+    }
 }
 
 }  // namespace tmac_b200
