@@ -325,8 +325,7 @@ int launch_prefill(const Resident &R, int N, const int8_t *qlut, const float *ls
     if (!g.use_prefill || N < g.prefill_min_n || !sym) return 1;
     if (L.pb != 2 || L.qch != 8 || L.act_group_size != 64 || L.one_scale || L.ck != 128) return 1;
     const size_t rawsz = (L.blk + 127) & ~(size_t)127;
-    const size_t nag = (size_t)L.K / 64;
-    const size_t smem = 4 * (size_t)kPfStageBytes + 2 * rawsz + 256 * 8 + nag * kPfNT * 4 + (size_t)L.nchunk * kPfNT * 4 + 8 * 8 + 1024;
+    const size_t smem = 2 * (size_t)kPfStages * kPfStageBytes + 2 * rawsz + 256 * 8 + (size_t)kPfSlots * kPfNT * 12 + (2 * kPfStages + 4) * 8 + 1024;
     if (smem > 225 * 1024) return 1;
     PrefillParams p{};
     p.W = R.d; p.qlut = qlut; p.lut_scales = ls; p.lut_biases = lb; p.C = C;

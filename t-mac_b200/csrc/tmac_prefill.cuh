@@ -72,25 +72,35 @@ __device__ __forceinline__ void pf_commit(uint64_t *b) {
                    "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                                                                 \
                  : "r"(taddr))
 
+__device__ __forceinline__ void pf_cp_async8(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(pf_s32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void pf_cp_async4(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(pf_s32(dst)), "l"(src) : "memory");
+}
+
+constexpr int kPfStages = 4;                     // operand stages (A 16 KB + B 16 KB each)
+constexpr int kPfSlots = 8;                      // ring of per-step LUT scales / per-chunk LUT-bias pairs (1.5 KB each)
+constexpr int kPfAhead = 2;                      // producers request the B / scale data this many steps ahead
+
 // grid = (row super-blocks of 128 rows, ceil(N / 128)), block = 416 threads, 1 CTA per SM.
 __global__ void __launch_bounds__(kPfThreads, 1) prefill_w2_kernel(const PrefillParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    // carve-up
-    unsigned char *sA = smem;                                  // [2][16 KB]
-    unsigned char *sB = sA + 2 * kPfStageBytes;                // [2][16 KB]
-    unsigned char *raw = sB + 2 * kPfStageBytes;               // [2][blk_bytes] packed block (codes + scales)
+    unsigned char *sA = smem;                                              // [S][16 KB]
+    unsigned char *sB = sA + kPfStages * kPfStageBytes;                    // [S][16 KB]
+    unsigned char *raw = sB + kPfStages * kPfStageBytes;                   // [2][blk_bytes] packed block (codes + scales)
     const int rawsz = (p.blk_bytes + 127) & ~127;
     uint64_t *xtab = reinterpret_cast<uint64_t *>(raw + 2 * rawsz);        // [256] expansion table
-    float *ls_s = reinterpret_cast<float *>(xtab + 256);                   // [nag][128] lut scales of this token tile
-    const int nag = p.K / 64, nwg = p.nchunk;
-    float *lb_s = ls_s + (size_t)nag * kPfNT;                              // [nwg][128] per-chunk bias sums
-    uint64_t *bars = reinterpret_cast<uint64_t *>(lb_s + (size_t)nwg * kPfNT);
-    uint64_t *full = bars, *empty = bars + 2, *accfull = bars + 4, *accempty = bars + 6;
+    float *ls_ring = reinterpret_cast<float *>(xtab + 256);                // [slots][128]   lut scale of (token, step)
+    float2 *lb_ring = reinterpret_cast<float2 *>(ls_ring + kPfSlots * kPfNT);   // [slots][128] lut biases of the chunk's two groups
+    uint64_t *bars = reinterpret_cast<uint64_t *>(lb_ring + kPfSlots * kPfNT);
+    uint64_t *full = bars, *empty = bars + kPfStages, *accfull = bars + 2 * kPfStages, *accempty = accfull + 2;
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rsb = blockIdx.x, n0 = blockIdx.y * kPfNT;
     const int ntok = min(kPfNT, p.N - n0);
+    const int nag = p.K / 64;
 
     // ---- one-time setup ---------------------------------------------------------------------------
     for (int e = tid; e < 256; e += kPfThreads) {
@@ -102,18 +112,12 @@ __global__ void __launch_bounds__(kPfThreads, 1) prefill_w2_kernel(const Prefill
         for (int i = 0; i < 8; ++i) x |= (uint64_t)(uint8_t)(int8_t)v[i] << (8 * i);
         xtab[e] = x;
     }
-    for (int i = tid; i < nag * kPfNT; i += kPfThreads) {
-        const int a = i / kPfNT, t = i % kPfNT;
-        ls_s[i] = (t < ntok) ? p.lut_scales[(size_t)(n0 + t) * nag + a] : 0.f;
-    }
-    for (int i = tid; i < nwg * kPfNT; i += kPfThreads) {
-        const int c = i / kPfNT, t = i % kPfNT;
-        float s = 0.f;
-        if (t < ntok) { const float *lb = p.lut_biases + (size_t)(n0 + t) * nag + 2 * c; s = lb[0] + lb[1]; }
-        lb_s[i] = s;
-    }
+    // token rows >= ntok of the B stages and of the rings are never written again: zero them once
+    for (int i = tid; i < kPfStages * kPfStageBytes / 16; i += kPfThreads) reinterpret_cast<uint4 *>(sB)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < kPfSlots * kPfNT; i += kPfThreads) { ls_ring[i] = 0.f; lb_ring[i] = make_float2(0.f, 0.f); }
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) { pf_mbar_init(full + i, 4); pf_mbar_init(empty + i, 1); pf_mbar_init(accfull + i, 1); pf_mbar_init(accempty + i, 8); }
+        for (int i = 0; i < kPfStages; ++i) { pf_mbar_init(full + i, 4); pf_mbar_init(empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { pf_mbar_init(accfull + i, 1); pf_mbar_init(accempty + i, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 4) {
@@ -128,32 +132,54 @@ __global__ void __launch_bounds__(kPfThreads, 1) prefill_w2_kernel(const Prefill
     const int nsteps = 2 * p.nchunk;                 // activation groups (two per chunk)
 
     if (warp < 4) {
-        // ======================= producers: thread = weight row r of the tile =======================
+        // ======================= producers: thread = weight row r of the tile AND token t of the tile =======================
         const int r = tid;                           // 0..127
         const int wl = r >> 2, wi = r & 3;           // lane / row-in-lane of the stream layout (RW = 4)
         const int n16 = p.blk_bytes >> 4;
+        const uint2 *qrow8 = reinterpret_cast<const uint2 *>(p.qlut) + (size_t)(n0 + tid) * (p.K / 4) * 2;   // this token's LUT rows
+        const float *ls_tok = p.lut_scales + (size_t)(n0 + tid) * nag, *lb_tok = p.lut_biases + (size_t)(n0 + tid) * nag;
+        const bool live = tid < ntok;
+        // request the B tile / LUT scale / LUT biases of one step (asynchronously, one cp.async group per step)
+        auto request = [&](int step) {
+            if (step < nsteps) {
+                const int s = step % kPfStages;
+                pf_mbar_wait(empty + s, ((step / kPfStages) & 1) ^ 1);          // stage free (immediately for the first S steps)
+                if (live) {
+                    unsigned char *b_dst = sB + (size_t)s * kPfStageBytes + ((size_t)(tid >> 3) * 128 + (tid & 7) * 16);
+                    const uint2 *src = qrow8 + (size_t)step * 16 * 2;          // 16 groups per step, 2 uint2 per group
+#pragma unroll
+                    for (int kc = 0; kc < 8; ++kc) {
+                        pf_cp_async8(b_dst + (size_t)kc * 2048, src + kc * 4);      // group 2kc: stored entries 0..7
+                        pf_cp_async8(b_dst + (size_t)kc * 2048 + 8, src + kc * 4 + 2);  // group 2kc+1
+                    }
+                    const int slot = step % kPfSlots;
+                    pf_cp_async4(ls_ring + slot * kPfNT + tid, ls_tok + step);
+                    if ((step & 1) == 0) pf_cp_async8(lb_ring + slot * kPfNT + tid, lb_tok + step);
+                }
+            }
+            cp_async_commit();                                                  // (possibly empty) group: keeps the group count uniform
+        };
         for (int i = tid; i < n16; i += 128) cp_async16_plain(raw + i * 16, rsb_base + i * 16);
         cp_async_commit();
-        const uint2 *qrow8 = reinterpret_cast<const uint2 *>(p.qlut);      // 8-byte halves of the 16-byte LUT rows
+        cp_async_wait_all();
+        for (int st = 0; st < kPfAhead; ++st) request(st);
         for (int c = 0; c < p.nchunk; ++c) {
             unsigned char *rb = raw + (size_t)(c & 1) * rawsz;
-            if (c + 1 < p.nchunk) {
+            // packed block c travelled in the group committed two requests ago: everything but the newest group must have landed
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");                 // block c is visible to all producer threads; block c-1 is dead
+            if (c + 1 < p.nchunk) {                                         // next packed block, double-buffered
                 unsigned char *nb = raw + (size_t)((c + 1) & 1) * rawsz;
                 const unsigned char *src = rsb_base + (size_t)(c + 1) * p.blk_bytes;
                 for (int i = tid; i < n16; i += 128) cp_async16_plain(nb + i * 16, src + i * 16);
-                cp_async_commit();
-                asm volatile("cp.async.wait_group 1;" ::: "memory");
-            } else
-                cp_async_wait_all();
-            asm volatile("bar.sync 1, 128;" ::: "memory");                 // the block is visible to all producer threads
+            }
             const uint32_t *words = reinterpret_cast<const uint32_t *>(rb);
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {                                  // two activation groups per chunk
-                const int step = 2 * c + h, s = step & 1;
-                pf_mbar_wait(empty + s, ((step >> 1) & 1) ^ 1);            // stage free (passes immediately the first time)
+                const int step = 2 * c + h, s = step % kPfStages;
+                request(step + kPfAhead);                                  // (its group also carries the raw block copy issued above)
                 unsigned char *a_dst = sA + (size_t)s * kPfStageBytes;
-                unsigned char *b_dst = sB + (size_t)s * kPfStageBytes;
-                // ---- A: one-hot-signed expansion of this row's 16 groups -----------------------------
+                // ---- A: one-hot-signed expansion of this row's 16 groups (stage s was acquired by request(step)) ----
 #pragma unroll
                 for (int kc = 0; kc < 8; ++kc) {
                     uint64_t v2[2];
@@ -169,34 +195,23 @@ __global__ void __launch_bounds__(kPfThreads, 1) prefill_w2_kernel(const Prefill
                     *reinterpret_cast<uint4 *>(a_dst + ((size_t)(kc * 16 + (r >> 3)) * 128 + (r & 7) * 16)) =
                         make_uint4((uint32_t)v2[0], (uint32_t)(v2[0] >> 32), (uint32_t)v2[1], (uint32_t)(v2[1] >> 32));
                 }
-                // ---- B: the 8 stored LUT entries of 16 groups for 128 tokens (thread = token) --------
-                {
-                    const int t = tid;
-                    const size_t g0 = (size_t)(2 * c + h) * 16;
-#pragma unroll
-                    for (int kc = 0; kc < 8; ++kc) {
-                        uint2 lo = make_uint2(0, 0), hi = make_uint2(0, 0);
-                        if (t < ntok) {
-                            const uint2 *src = qrow8 + ((size_t)(n0 + t) * (p.K / 4) + g0 + 2 * kc) * 2;
-                            lo = __ldg(src); hi = __ldg(src + 2);
-                        }
-                        *reinterpret_cast<uint4 *>(b_dst + ((size_t)(kc * 16 + (t >> 3)) * 128 + (t & 7) * 16)) = make_uint4(lo.x, lo.y, hi.x, hi.y);
-                    }
-                }
+                // the groups of steps step+1 .. step+kPfAhead may still be in flight; everything older (this step's B, scales,
+                // and the raw block needed next) has landed
+                asm volatile("cp.async.wait_group %0;" ::"n"(kPfAhead) : "memory");
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) pf_mbar_arrive(full + s);
                 __syncwarp();
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");                 // nobody still reads rb when it is refilled
         }
+        cp_async_wait_all();
     } else if (warp == 4) {
         // ======================= MMA issuer ===========================================================
         if (lane == 0) {
             const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kPfNT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             for (int step = 0; step < nsteps; ++step) {
-                const int s = step & 1, b = step & 1;
-                pf_mbar_wait(full + s, (step >> 1) & 1);
+                const int s = step % kPfStages, b = step & 1;
+                pf_mbar_wait(full + s, (step / kPfStages) & 1);
                 pf_mbar_wait(accempty + b, ((step >> 1) & 1) ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a0 = pf_s32(sA + (size_t)s * kPfStageBytes), b0 = pf_s32(sB + (size_t)s * kPfStageBytes);
@@ -221,17 +236,16 @@ __global__ void __launch_bounds__(kPfThreads, 1) prefill_w2_kernel(const Prefill
         float cacc[64];
 #pragma unroll
         for (int j = 0; j < 64; ++j) cacc[j] = 0.f;
-        float corr_s = 0.f;                          // unused placeholder keeps the scale loads below simple
-        (void)corr_s;
         for (int step = 0; step < nsteps; ++step) {
-            const int b = step & 1, c = step >> 1;
-            // 0.5 * weight scale of (row, chunk): read from the resident block (L2 hit; the producers staged it moments ago)
+            const int b = step & 1, c = step >> 1, slot = step % kPfSlots;
+            // 0.5 * weight scale (+ zero point) of (row, chunk): read from the resident block (L2 hit)
             const unsigned char *sp = rsb_base + (size_t)c * p.blk_bytes + 4096;
             const float hs = 0.5f * load_scale(sp, p.sd, wl * 4 + wi);
+            const float wz = (step & 1) ? (hs + (p.zp ? load_scale(sp + (size_t)128 * p.sd, p.sd, wl * 4 + wi) : 0.f)) : 0.f;
             pf_mbar_wait(accfull + b, (step >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + b * kPfNT + half * 64;
-            const float4 *ls4 = reinterpret_cast<const float4 *>(ls_s + (size_t)step * kPfNT + half * 64);
+            const float4 *ls4 = reinterpret_cast<const float4 *>(ls_ring + slot * kPfNT + half * 64);
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {                 // two 32-column slices: keeps 32 (not 64) TMEM words live
                 uint32_t v[32];
@@ -253,20 +267,16 @@ __global__ void __launch_bounds__(kPfThreads, 1) prefill_w2_kernel(const Prefill
                     cc[3] = fmaf(hs * l.w, (float)(int)v[4 * j4 + 3], cc[3]);
                 }
             }
-        }
-        // ---- LUT-bias / zero-point correction: sum_chunks (0.5*s + z)[row, chunk] * LB[token, chunk] ----
-        for (int c = 0; c < p.nchunk; ++c) {
-            const unsigned char *sp = rsb_base + (size_t)c * p.blk_bytes + 4096;
-            float w = 0.5f * load_scale(sp, p.sd, wl * 4 + wi);
-            if (p.zp) w += load_scale(sp + (size_t)128 * p.sd, p.sd, wl * 4 + wi);
-            const float4 *lb4 = reinterpret_cast<const float4 *>(lb_s + (size_t)c * kPfNT + half * 64);
+            if (step & 1) {
+                // LUT-bias / zero-point term of this chunk: (0.5*s + z)[row] * (lb[2c] + lb[2c+1])[token]; the pair sits in the
+                // slot of the chunk's first step
+                const float4 *lb4 = reinterpret_cast<const float4 *>(lb_ring + ((step - 1) % kPfSlots) * kPfNT + half * 64);
 #pragma unroll
-            for (int j4 = 0; j4 < 16; ++j4) {
-                const float4 l = lb4[j4];
-                cacc[4 * j4 + 0] = fmaf(w, l.x, cacc[4 * j4 + 0]);
-                cacc[4 * j4 + 1] = fmaf(w, l.y, cacc[4 * j4 + 1]);
-                cacc[4 * j4 + 2] = fmaf(w, l.z, cacc[4 * j4 + 2]);
-                cacc[4 * j4 + 3] = fmaf(w, l.w, cacc[4 * j4 + 3]);
+                for (int j2 = 0; j2 < 32; ++j2) {
+                    const float4 l = lb4[j2];                 // two tokens: (lb0, lb1), (lb0, lb1)
+                    cacc[2 * j2 + 0] = fmaf(wz, l.x + l.y, cacc[2 * j2 + 0]);
+                    cacc[2 * j2 + 1] = fmaf(wz, l.z + l.w, cacc[2 * j2 + 1]);
+                }
             }
         }
         const int row = rsb * 128 + r;
