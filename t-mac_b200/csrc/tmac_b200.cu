@@ -93,7 +93,7 @@ struct Context {
     std::set<const void *> sym_qluts;    // device QLUT buffers last written by our preprocessor
     std::vector<std::pair<std::vector<const void *>, void *>> ptr_tables;   // grouped-launch pointer tables
     // workspaces
-    DevBuf d_b, d_qlut, d_ls, d_lb, d_c, d_part, d_cnt, d_cbits, d_trace;
+    DevBuf d_b, d_qlut, d_ls, d_lb, d_c, d_part, d_cnt, d_cbits, d_trace, d_tiles;
     int trace = 0, trace_ctas = 0, trace_seq = 0;
     PinBuf h_in, h_out;
     cudaEvent_t stage_ev = nullptr;      // last H2D that read h_in
@@ -325,17 +325,27 @@ int launch_prefill(const Resident &R, int N, const int8_t *qlut, const float *ls
     if (!g.use_prefill || N < g.prefill_min_n || !sym) return 1;
     if (L.pb != 2 || L.qch != 8 || L.act_group_size != 64 || L.one_scale || L.ck != 128) return 1;
     const size_t rawsz = (L.blk + 127) & ~(size_t)127;
-    const size_t smem = 2 * (size_t)kPfStages * kPfStageBytes + 2 * rawsz + 256 * 8 + (size_t)kPfSlots * kPfNT * 12 + (2 * kPfStages + 4) * 8 + 1024;
+    const size_t smem = (size_t)kPfStages * (kPfStageBytes + kPfRec) + 2 * rawsz + 256 * 8 + (2 * kPfStages + 4) * 8 + 1024;
     if (smem > 225 * 1024) return 1;
+    const int nag = L.K / 64, ntile = (N + kPfNT - 1) / kPfNT;
+    if (g.d_tiles.ensure((size_t)ntile * nag * kPfRec)) return fail("out of device memory (LUT tiles)");
+    lut_tile_kernel<<<dim3(nag, ntile), 128, 0, g.stream()>>>(qlut, ls, lb, (unsigned char *)g.d_tiles.p, N, L.K);
+    CUDA_OK(cudaGetLastError());
     PrefillParams p{};
     p.W = R.d; p.qlut = qlut; p.lut_scales = ls; p.lut_biases = lb; p.C = C;
+    p.lut_tiles = (const unsigned char *)g.d_tiles.p;
     p.N = N; p.K = L.K; p.Mout = L.Mout; p.ldc = ldc; p.out_f16 = out_f16;
     p.nchunk = L.nchunk; p.zp = L.zp; p.sd = L.sd; p.blk_bytes = (int)L.blk; p.rsb_stride = L.rsb_stride;
+    if (g.trace) {
+        if (g.d_trace.ensure(8192)) return fail("out of device memory (trace)");
+        CUDA_OK(cudaMemsetAsync(g.d_trace.p, 0, 3 * 32 * 4 * sizeof(long long), g.stream()));
+        p.dbg = (long long *)g.d_trace.p; g.trace_ctas = 12;   // 96 rows of 4 = 48 rows of 8
+    }
     CUDA_OK(cudaFuncSetAttribute((const void *)prefill_w2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(L.nrsb, (N + kPfNT - 1) / kPfNT);
-    prefill_w2_kernel<<<grid, kPfThreads, smem, g.stream()>>>(p);
+    dim3 grid(L.nrsb, ntile);
+    prefill_w2_kernel<<<grid, kPfThreads2, smem, g.stream()>>>(p);
     CUDA_OK(cudaGetLastError());
-    g.last_launch[0] = 1; g.last_launch[1] = 13; g.last_launch[2] = L.nchunk; g.last_launch[3] = 1; g.last_launch[4] = L.nrsb;
+    g.last_launch[0] = 1; g.last_launch[1] = 18; g.last_launch[2] = L.nchunk; g.last_launch[3] = 1; g.last_launch[4] = L.nrsb;
     g.last_launch[5] = L.pb; g.last_launch[6] = 1; g.last_launch[7] = -N;   // batch < 0 marks the tcgen05 prefill tile
     return 0;
 }

@@ -37,10 +37,16 @@ struct PrefillParams {
     int N, K, Mout, ldc, out_f16;
     int nchunk, zp, sd, blk_bytes;
     size_t rsb_stride;
+    const unsigned char *lut_tiles; // output of lut_tile_kernel: [token tile][step][kPfRec]
+    long long *dbg;                // optional trace [role][step][4] (TMAC_ENABLE_TRACE builds)
 };
+#ifdef TMAC_ENABLE_TRACE
+#define PF_TRACE(role, step, k) do { if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && (step) < 32) p.dbg[((role) * 32 + (step)) * 4 + (k)] = clock64(); } while (0)
+#else
+#define PF_TRACE(role, step, k) do { } while (0)
+#endif
 
 constexpr int kPfNT = 128;                       // tokens per CTA pass (MMA N)
-constexpr int kPfThreads = 13 * 32;
 constexpr int kPfStageBytes = 128 * 128;         // one operand tile: 128 rows x 128 contraction bytes
 
 __device__ __forceinline__ uint32_t pf_s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -72,38 +78,68 @@ __device__ __forceinline__ void pf_commit(uint64_t *b) {
                    "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                                                                 \
                  : "r"(taddr))
 
-__device__ __forceinline__ void pf_cp_async8(void *dst, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(pf_s32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void pf_cp_async4(void *dst, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(pf_s32(dst)), "l"(src) : "memory");
+// ---------------------------------------------------------------------------------------------------
+// lut_tile_kernel: QLUT [N][K/4][16] + LUT_Scales/Biases [N][K/64]  ->  per (token tile of 128, activation group) one
+// contiguous 17920-byte record that the GEMM stage receives with ONE bulk copy (TMA):
+//     [16384 B]  the 8 stored LUT entries of the 16 groups of the step for 128 tokens, already in the UMMA K-major
+//                canonical order: chunk kc (groups 2kc, 2kc+1), token t at ((kc*16 + t/8)*128 + (t%8)*16)
+//     [  512 B]  lut_scale[token][step]
+//     [ 1024 B]  (lut_bias[token][2c], lut_bias[token][2c+1]) of the step's chunk c = step/2
+// Tokens >= N are zero.  grid = (steps, token tiles), block = 128 (thread = token).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kPfRec = 16384 + 512 + 1024;
+__global__ void __launch_bounds__(128) lut_tile_kernel(const int8_t *qlut, const float *ls, const float *lb, unsigned char *out, int N, int K) {
+    const int step = blockIdx.x, tile = blockIdx.y, t = threadIdx.x, n = tile * 128 + t;
+    const int nag = K / 64;
+    unsigned char *rec = out + ((size_t)tile * nag + step) * kPfRec;
+    const uint2 *src = reinterpret_cast<const uint2 *>(qlut) + ((size_t)n * (K / 4) + (size_t)step * 16) * 2;
+#pragma unroll
+    for (int kc = 0; kc < 8; ++kc) {
+        uint2 lo = make_uint2(0, 0), hi = make_uint2(0, 0);
+        if (n < N) { lo = __ldg(src + kc * 4); hi = __ldg(src + kc * 4 + 2); }
+        *reinterpret_cast<uint4 *>(rec + ((size_t)(kc * 16 + (t >> 3)) * 128 + (t & 7) * 16)) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+    }
+    float l = 0.f; float2 b2 = make_float2(0.f, 0.f);
+    if (n < N) { l = ls[(size_t)n * nag + step]; b2 = make_float2(lb[(size_t)n * nag + (step & ~1)], lb[(size_t)n * nag + (step | 1)]); }
+    reinterpret_cast<float *>(rec + 16384)[t] = l;
+    reinterpret_cast<float2 *>(rec + 16384 + 512)[t] = b2;
 }
 
-constexpr int kPfStages = 4;                     // operand stages (A 16 KB + B 16 KB each)
-constexpr int kPfSlots = 8;                      // ring of per-step LUT scales / per-chunk LUT-bias pairs (1.5 KB each)
-constexpr int kPfAhead = 2;                      // producers request the B / scale data this many steps ahead
+constexpr int kPfStages = 4;                     // stages: A tile 16 KB (expanded by the producers) + record 17.5 KB (TMA)
+constexpr int kPfProdWarps = 8;
+constexpr int kPfWarpMma = 8, kPfWarpTma = 9, kPfWarpEpi = 10;
+#undef PF_THREADS
+constexpr int kPfThreads2 = 18 * 32;
 
-// grid = (row super-blocks of 128 rows, ceil(N / 128)), block = 416 threads, 1 CTA per SM.
-__global__ void __launch_bounds__(kPfThreads, 1) prefill_w2_kernel(const PrefillParams p) {
+__device__ __forceinline__ void pf_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(pf_s32(dst)), "l"(src), "r"(bytes), "r"(pf_s32(bar)) : "memory");
+}
+__device__ __forceinline__ void pf_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pf_s32(bar)), "r"(bytes) : "memory");
+}
+
+// grid = (row super-blocks of 128 rows, ceil(N / 128)), block = 576 threads, 1 CTA per SM.
+//   warps 0..7  : A producers, thread = (weight row, half of the step's 16 groups)
+//   warp  8     : MMA issuer (one thread)        warp 9 : TMA issuer (one thread): one bulk copy per step
+//   warps 10..17: epilogue, thread = (weight row, 64-token half)
+__global__ void __maxnreg__(112) prefill_w2_kernel(const PrefillParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *sA = smem;                                              // [S][16 KB]
-    unsigned char *sB = sA + kPfStages * kPfStageBytes;                    // [S][16 KB]
-    unsigned char *raw = sB + kPfStages * kPfStageBytes;                   // [2][blk_bytes] packed block (codes + scales)
+    unsigned char *sR = sA + kPfStages * kPfStageBytes;                    // [S][kPfRec] B tile + lut scales + lut bias pairs
+    unsigned char *raw = sR + kPfStages * kPfRec;                          // [2][blk_bytes] packed block (codes + scales)
     const int rawsz = (p.blk_bytes + 127) & ~127;
     uint64_t *xtab = reinterpret_cast<uint64_t *>(raw + 2 * rawsz);        // [256] expansion table
-    float *ls_ring = reinterpret_cast<float *>(xtab + 256);                // [slots][128]   lut scale of (token, step)
-    float2 *lb_ring = reinterpret_cast<float2 *>(ls_ring + kPfSlots * kPfNT);   // [slots][128] lut biases of the chunk's two groups
-    uint64_t *bars = reinterpret_cast<uint64_t *>(lb_ring + kPfSlots * kPfNT);
+    uint64_t *bars = xtab + 256;
     uint64_t *full = bars, *empty = bars + kPfStages, *accfull = bars + 2 * kPfStages, *accempty = accfull + 2;
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int rsb = blockIdx.x, n0 = blockIdx.y * kPfNT;
+    const int rsb = blockIdx.x, tile = blockIdx.y, n0 = tile * kPfNT;
     const int ntok = min(kPfNT, p.N - n0);
     const int nag = p.K / 64;
 
-    // ---- one-time setup ---------------------------------------------------------------------------
-    for (int e = tid; e < 256; e += kPfThreads) {
+    for (int e = tid; e < 256; e += kPfThreads2) {
         // index byte: low nibble = plane 0 (neg<<3 | j), high nibble = plane 1; value = +-1 at byte j0, +-2 at byte j1
         int v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         v[e & 7] += (e & 8) ? -1 : 1;
@@ -112,15 +148,12 @@ __global__ void __launch_bounds__(kPfThreads, 1) prefill_w2_kernel(const Prefill
         for (int i = 0; i < 8; ++i) x |= (uint64_t)(uint8_t)(int8_t)v[i] << (8 * i);
         xtab[e] = x;
     }
-    // token rows >= ntok of the B stages and of the rings are never written again: zero them once
-    for (int i = tid; i < kPfStages * kPfStageBytes / 16; i += kPfThreads) reinterpret_cast<uint4 *>(sB)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < kPfSlots * kPfNT; i += kPfThreads) { ls_ring[i] = 0.f; lb_ring[i] = make_float2(0.f, 0.f); }
     if (tid == 0) {
-        for (int i = 0; i < kPfStages; ++i) { pf_mbar_init(full + i, 4); pf_mbar_init(empty + i, 1); }
+        for (int i = 0; i < kPfStages; ++i) { pf_mbar_init(full + i, kPfProdWarps + 1); pf_mbar_init(empty + i, 8); }
         for (int i = 0; i < 2; ++i) { pf_mbar_init(accfull + i, 1); pf_mbar_init(accempty + i, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == kPfWarpMma) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(pf_s32(&tmem_base_s)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -131,57 +164,34 @@ __global__ void __launch_bounds__(kPfThreads, 1) prefill_w2_kernel(const Prefill
     const unsigned char *rsb_base = p.W + (size_t)rsb * p.rsb_stride;
     const int nsteps = 2 * p.nchunk;                 // activation groups (two per chunk)
 
-    if (warp < 4) {
-        // ======================= producers: thread = weight row r of the tile AND token t of the tile =======================
-        const int r = tid;                           // 0..127
+    if (warp < kPfProdWarps) {
+        // ======================= A producers =======================
+        const int r = tid & 127, gh = tid >> 7;      // weight row of the tile, which 8 of the step's 16 groups
         const int wl = r >> 2, wi = r & 3;           // lane / row-in-lane of the stream layout (RW = 4)
         const int n16 = p.blk_bytes >> 4;
-        const uint2 *qrow8 = reinterpret_cast<const uint2 *>(p.qlut) + (size_t)(n0 + tid) * (p.K / 4) * 2;   // this token's LUT rows
-        const float *ls_tok = p.lut_scales + (size_t)(n0 + tid) * nag, *lb_tok = p.lut_biases + (size_t)(n0 + tid) * nag;
-        const bool live = tid < ntok;
-        // request the B tile / LUT scale / LUT biases of one step (asynchronously, one cp.async group per step)
-        auto request = [&](int step) {
-            if (step < nsteps) {
-                const int s = step % kPfStages;
-                pf_mbar_wait(empty + s, ((step / kPfStages) & 1) ^ 1);          // stage free (immediately for the first S steps)
-                if (live) {
-                    unsigned char *b_dst = sB + (size_t)s * kPfStageBytes + ((size_t)(tid >> 3) * 128 + (tid & 7) * 16);
-                    const uint2 *src = qrow8 + (size_t)step * 16 * 2;          // 16 groups per step, 2 uint2 per group
-#pragma unroll
-                    for (int kc = 0; kc < 8; ++kc) {
-                        pf_cp_async8(b_dst + (size_t)kc * 2048, src + kc * 4);      // group 2kc: stored entries 0..7
-                        pf_cp_async8(b_dst + (size_t)kc * 2048 + 8, src + kc * 4 + 2);  // group 2kc+1
-                    }
-                    const int slot = step % kPfSlots;
-                    pf_cp_async4(ls_ring + slot * kPfNT + tid, ls_tok + step);
-                    if ((step & 1) == 0) pf_cp_async8(lb_ring + slot * kPfNT + tid, lb_tok + step);
-                }
-            }
-            cp_async_commit();                                                  // (possibly empty) group: keeps the group count uniform
-        };
-        for (int i = tid; i < n16; i += 128) cp_async16_plain(raw + i * 16, rsb_base + i * 16);
+        for (int i = tid; i < n16; i += 256) cp_async16_plain(raw + i * 16, rsb_base + i * 16);
         cp_async_commit();
-        cp_async_wait_all();
-        for (int st = 0; st < kPfAhead; ++st) request(st);
         for (int c = 0; c < p.nchunk; ++c) {
             unsigned char *rb = raw + (size_t)(c & 1) * rawsz;
-            // packed block c travelled in the group committed two requests ago: everything but the newest group must have landed
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-            asm volatile("bar.sync 1, 128;" ::: "memory");                 // block c is visible to all producer threads; block c-1 is dead
-            if (c + 1 < p.nchunk) {                                         // next packed block, double-buffered
+            cp_async_wait_all();
+            asm volatile("bar.sync 1, 256;" ::: "memory");                 // block c visible to all producers; block c-1 dead
+            if (c + 1 < p.nchunk) {
                 unsigned char *nb = raw + (size_t)((c + 1) & 1) * rawsz;
                 const unsigned char *src = rsb_base + (size_t)(c + 1) * p.blk_bytes;
-                for (int i = tid; i < n16; i += 128) cp_async16_plain(nb + i * 16, src + i * 16);
+                for (int i = tid; i < n16; i += 256) cp_async16_plain(nb + i * 16, src + i * 16);
+                cp_async_commit();
             }
             const uint32_t *words = reinterpret_cast<const uint32_t *>(rb);
 #pragma unroll 1
-            for (int h = 0; h < 2; ++h) {                                  // two activation groups per chunk
+            for (int h = 0; h < 2; ++h) {
                 const int step = 2 * c + h, s = step % kPfStages;
-                request(step + kPfAhead);                                  // (its group also carries the raw block copy issued above)
+                if (tid == 0) PF_TRACE(0, step, 0);
+                pf_mbar_wait(empty + s, ((step / kPfStages) & 1) ^ 1);     // stage released by the epilogue of step - S
+                if (tid == 0) PF_TRACE(0, step, 1);
                 unsigned char *a_dst = sA + (size_t)s * kPfStageBytes;
-                // ---- A: one-hot-signed expansion of this row's 16 groups (stage s was acquired by request(step)) ----
 #pragma unroll
-                for (int kc = 0; kc < 8; ++kc) {
+                for (int kk = 0; kk < 4; ++kk) {
+                    const int kc = gh * 4 + kk;
                     uint64_t v2[2];
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
@@ -195,26 +205,37 @@ __global__ void __launch_bounds__(kPfThreads, 1) prefill_w2_kernel(const Prefill
                     *reinterpret_cast<uint4 *>(a_dst + ((size_t)(kc * 16 + (r >> 3)) * 128 + (r & 7) * 16)) =
                         make_uint4((uint32_t)v2[0], (uint32_t)(v2[0] >> 32), (uint32_t)v2[1], (uint32_t)(v2[1] >> 32));
                 }
-                // the groups of steps step+1 .. step+kPfAhead may still be in flight; everything older (this step's B, scales,
-                // and the raw block needed next) has landed
-                asm volatile("cp.async.wait_group %0;" ::"n"(kPfAhead) : "memory");
+                if (tid == 0) PF_TRACE(0, step, 2);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) pf_mbar_arrive(full + s);
                 __syncwarp();
             }
         }
-        cp_async_wait_all();
-    } else if (warp == 4) {
-        // ======================= MMA issuer ===========================================================
+    } else if (warp == kPfWarpTma) {
+        // ======================= TMA issuer: one record per step =======================
+        if (lane == 0) {
+            const unsigned char *src = p.lut_tiles + (size_t)tile * nag * kPfRec;
+            for (int step = 0; step < nsteps; ++step) {
+                const int s = step % kPfStages;
+                pf_mbar_wait(empty + s, ((step / kPfStages) & 1) ^ 1);
+                pf_expect_tx(full + s, kPfRec);
+                pf_bulk_g2s(sR + (size_t)s * kPfRec, src + (size_t)step * kPfRec, kPfRec, full + s);
+            }
+        }
+    } else if (warp == kPfWarpMma) {
+        // ======================= MMA issuer =======================
         if (lane == 0) {
             const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kPfNT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             for (int step = 0; step < nsteps; ++step) {
                 const int s = step % kPfStages, b = step & 1;
+                PF_TRACE(1, step, 0);
                 pf_mbar_wait(full + s, (step / kPfStages) & 1);
+                PF_TRACE(1, step, 1);
                 pf_mbar_wait(accempty + b, ((step >> 1) & 1) ^ 1);
+                PF_TRACE(1, step, 2);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a0 = pf_s32(sA + (size_t)s * kPfStageBytes), b0 = pf_s32(sB + (size_t)s * kPfStageBytes);
+                const uint32_t a0 = pf_s32(sA + (size_t)s * kPfStageBytes), b0 = pf_s32(sR + (size_t)s * kPfRec);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const uint64_t da = pf_desc(a0 + i * 4096), db = pf_desc(b0 + i * 4096);
@@ -222,30 +243,33 @@ __global__ void __launch_bounds__(kPfThreads, 1) prefill_w2_kernel(const Prefill
                     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n"
                                  ::"r"(tmem + b * kPfNT), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
                 }
-                pf_commit(empty + s);            // stage may be refilled when these MMAs have read it
-                pf_commit(accfull + b);          // accumulator complete
+                pf_commit(accfull + b);          // accumulator complete (the stage itself is released by the epilogue)
+                PF_TRACE(1, step, 3);
             }
         }
     } else {
-        // ======================= epilogue: thread = (weight row, 64-token half) =========================
-        const int ew = warp - 5;                     // 0..7
+        // ======================= epilogue: thread = (weight row, 64-token half) =======================
+        const int ew = warp - kPfWarpEpi;            // 0..7
         const int lq = warp & 3;                     // TMEM lane quarter this warp may access
-        const int half = ew >> 2;                    // warps 5..8 -> columns 0..63, warps 9..12 -> 64..127
+        const int half = ew >> 2;
         const int r = lq * 32 + lane;                // weight row of the tile
         const int wl = r >> 2, wi = r & 3;
         float cacc[64];
 #pragma unroll
         for (int j = 0; j < 64; ++j) cacc[j] = 0.f;
         for (int step = 0; step < nsteps; ++step) {
-            const int b = step & 1, c = step >> 1, slot = step % kPfSlots;
+            const int b = step & 1, c = step >> 1, s = step % kPfStages;
             // 0.5 * weight scale (+ zero point) of (row, chunk): read from the resident block (L2 hit)
             const unsigned char *sp = rsb_base + (size_t)c * p.blk_bytes + 4096;
             const float hs = 0.5f * load_scale(sp, p.sd, wl * 4 + wi);
             const float wz = (step & 1) ? (hs + (p.zp ? load_scale(sp + (size_t)128 * p.sd, p.sd, wl * 4 + wi) : 0.f)) : 0.f;
+            if (warp == kPfWarpEpi && lane == 0) PF_TRACE(2, step, 0);
             pf_mbar_wait(accfull + b, (step >> 1) & 1);
+            if (warp == kPfWarpEpi && lane == 0) PF_TRACE(2, step, 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + b * kPfNT + half * 64;
-            const float4 *ls4 = reinterpret_cast<const float4 *>(ls_ring + slot * kPfNT + half * 64);
+            const unsigned char *rec = sR + (size_t)s * kPfRec;
+            const float4 *ls4 = reinterpret_cast<const float4 *>(rec + 16384) + half * 16;
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {                 // two 32-column slices: keeps 32 (not 64) TMEM words live
                 uint32_t v[32];
@@ -268,9 +292,8 @@ __global__ void __launch_bounds__(kPfThreads, 1) prefill_w2_kernel(const Prefill
                 }
             }
             if (step & 1) {
-                // LUT-bias / zero-point term of this chunk: (0.5*s + z)[row] * (lb[2c] + lb[2c+1])[token]; the pair sits in the
-                // slot of the chunk's first step
-                const float4 *lb4 = reinterpret_cast<const float4 *>(lb_ring + ((step - 1) % kPfSlots) * kPfNT + half * 64);
+                // LUT-bias / zero-point term of the chunk: (0.5*s + z)[row] * (lb[2c] + lb[2c+1])[token]
+                const float4 *lb4 = reinterpret_cast<const float4 *>(rec + 16384 + 512) + half * 32;
 #pragma unroll
                 for (int j2 = 0; j2 < 32; ++j2) {
                     const float4 l = lb4[j2];                 // two tokens: (lb0, lb1), (lb0, lb1)
@@ -278,6 +301,10 @@ __global__ void __launch_bounds__(kPfThreads, 1) prefill_w2_kernel(const Prefill
                     cacc[2 * j2 + 1] = fmaf(wz, l.z + l.w, cacc[2 * j2 + 1]);
                 }
             }
+            if (warp == kPfWarpEpi && lane == 0) PF_TRACE(2, step, 2);
+            __syncwarp();
+            if (lane == 0) pf_mbar_arrive(empty + s);        // A tile and record of this step are dead: the stage may be refilled
+            __syncwarp();
         }
         const int row = rsb * 128 + r;
         if (row < p.Mout) {
@@ -295,7 +322,7 @@ __global__ void __launch_bounds__(kPfThreads, 1) prefill_w2_kernel(const Prefill
     __syncwarp();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 4) {
+    if (warp == kPfWarpMma) {
         __syncwarp();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
     }
