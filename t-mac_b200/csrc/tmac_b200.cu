@@ -345,7 +345,7 @@ int launch_prefill(const Resident &R, int N, const int8_t *qlut, const float *ls
     dim3 grid(L.nrsb, ntile);
     prefill_w2_kernel<<<grid, kPfThreads2, smem, g.stream()>>>(p);
     CUDA_OK(cudaGetLastError());
-    g.last_launch[0] = 1; g.last_launch[1] = 18; g.last_launch[2] = L.nchunk; g.last_launch[3] = 1; g.last_launch[4] = L.nrsb;
+    g.last_launch[0] = 1; g.last_launch[1] = kPfThreads2 / 32; g.last_launch[2] = L.nchunk; g.last_launch[3] = 1; g.last_launch[4] = L.nrsb;
     g.last_launch[5] = L.pb; g.last_launch[6] = 1; g.last_launch[7] = -N;   // batch < 0 marks the tcgen05 prefill tile
     return 0;
 }

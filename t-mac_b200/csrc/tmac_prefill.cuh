@@ -69,6 +69,11 @@ __device__ __forceinline__ void pf_mbar_wait(uint64_t *b, uint32_t parity) {
 __device__ __forceinline__ void pf_commit(uint64_t *b) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(pf_s32(b)) : "memory");
 }
+#define PF_TMEM_LD16(r, taddr)                                                                                                        \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"             \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),      \
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])                                       \
+                 : "r"(taddr))
 #define PF_TMEM_LD32(r, taddr)                                                                                                        \
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21," \
                  "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                                                                   \
@@ -109,7 +114,12 @@ constexpr int kPfStages = 4;                     // stages: A tile 16 KB (expand
 constexpr int kPfProdWarps = 8;
 constexpr int kPfWarpMma = 8, kPfWarpTma = 9, kPfWarpEpi = 10;
 #undef PF_THREADS
-constexpr int kPfThreads2 = 18 * 32;
+constexpr int kPfEpiWarps = 16;                  // 4 lane quarters x 4 column groups of 32 tokens
+constexpr int kPfThreads2 = (10 + kPfEpiWarps) * 32;
+
+__device__ __forceinline__ uint64_t pf_pack2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ uint64_t pf_fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ uint64_t pf_mul2(uint64_t a, uint64_t b) { uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
 __device__ __forceinline__ void pf_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -119,11 +129,11 @@ __device__ __forceinline__ void pf_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pf_s32(bar)), "r"(bytes) : "memory");
 }
 
-// grid = (row super-blocks of 128 rows, ceil(N / 128)), block = 576 threads, 1 CTA per SM.
+// grid = (row super-blocks of 128 rows, ceil(N / 128)), block = 832 threads, 1 CTA per SM.
 //   warps 0..7  : A producers, thread = (weight row, half of the step's 16 groups)
 //   warp  8     : MMA issuer (one thread)        warp 9 : TMA issuer (one thread): one bulk copy per step
-//   warps 10..17: epilogue, thread = (weight row, 64-token half)
-__global__ void __maxnreg__(112) prefill_w2_kernel(const PrefillParams p) {
+//   warps 10..25: epilogue, thread = (weight row, 32-token column group)
+__global__ void __launch_bounds__(kPfThreads2, 1) prefill_w2_kernel(const PrefillParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *sA = smem;                                              // [S][16 KB]
     unsigned char *sR = sA + kPfStages * kPfStageBytes;                    // [S][kPfRec] B tile + lut scales + lut bias pairs
@@ -149,8 +159,8 @@ __global__ void __maxnreg__(112) prefill_w2_kernel(const PrefillParams p) {
         xtab[e] = x;
     }
     if (tid == 0) {
-        for (int i = 0; i < kPfStages; ++i) { pf_mbar_init(full + i, kPfProdWarps + 1); pf_mbar_init(empty + i, 8); }
-        for (int i = 0; i < 2; ++i) { pf_mbar_init(accfull + i, 1); pf_mbar_init(accempty + i, 8); }
+        for (int i = 0; i < kPfStages; ++i) { pf_mbar_init(full + i, kPfProdWarps + 1); pf_mbar_init(empty + i, kPfEpiWarps); }
+        for (int i = 0; i < 2; ++i) { pf_mbar_init(accfull + i, 1); pf_mbar_init(accempty + i, kPfEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kPfWarpMma) {
@@ -248,32 +258,34 @@ __global__ void __maxnreg__(112) prefill_w2_kernel(const PrefillParams p) {
             }
         }
     } else {
-        // ======================= epilogue: thread = (weight row, 64-token half) =======================
-        const int ew = warp - kPfWarpEpi;            // 0..7
+        // ======================= epilogue: thread = (weight row, 32-token column group) =======================
+        const int ew = warp - kPfWarpEpi;            // 0..15
         const int lq = warp & 3;                     // TMEM lane quarter this warp may access
-        const int half = ew >> 2;
+        const int cg = ew >> 2;                      // column group: tokens 32*cg .. 32*cg+31
         const int r = lq * 32 + lane;                // weight row of the tile
         const int wl = r >> 2, wi = r & 3;
-        float cacc[64];
+        uint64_t acc2[16];                           // 32 fp32 accumulators as f32x2 pairs (FFMA2 / FMUL2)
 #pragma unroll
-        for (int j = 0; j < 64; ++j) cacc[j] = 0.f;
+        for (int j = 0; j < 16; ++j) acc2[j] = 0ull;
+        // weight scale / zero point of (row, chunk), prefetched one chunk ahead (L2 hits, latency off the critical path)
+        auto ld_s = [&](int c) { return 0.5f * load_scale(rsb_base + (size_t)c * p.blk_bytes + 4096, p.sd, wl * 4 + wi); };
+        auto ld_z = [&](int c) { return p.zp ? load_scale(rsb_base + (size_t)c * p.blk_bytes + 4096 + (size_t)128 * p.sd, p.sd, wl * 4 + wi) : 0.f; };
+        float hs = ld_s(0), zz = ld_z(0), hs_n = hs, zz_n = zz;
         for (int step = 0; step < nsteps; ++step) {
             const int b = step & 1, c = step >> 1, s = step % kPfStages;
-            // 0.5 * weight scale (+ zero point) of (row, chunk): read from the resident block (L2 hit)
-            const unsigned char *sp = rsb_base + (size_t)c * p.blk_bytes + 4096;
-            const float hs = 0.5f * load_scale(sp, p.sd, wl * 4 + wi);
-            const float wz = (step & 1) ? (hs + (p.zp ? load_scale(sp + (size_t)128 * p.sd, p.sd, wl * 4 + wi) : 0.f)) : 0.f;
+            if (!(step & 1) && c + 1 < p.nchunk) { hs_n = ld_s(c + 1); zz_n = ld_z(c + 1); }
             if (warp == kPfWarpEpi && lane == 0) PF_TRACE(2, step, 0);
             pf_mbar_wait(accfull + b, (step >> 1) & 1);
             if (warp == kPfWarpEpi && lane == 0) PF_TRACE(2, step, 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + b * kPfNT + half * 64;
+            const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + b * kPfNT + cg * 32;
             const unsigned char *rec = sR + (size_t)s * kPfRec;
-            const float4 *ls4 = reinterpret_cast<const float4 *>(rec + 16384) + half * 16;
+            const uint64_t *ls2 = reinterpret_cast<const uint64_t *>(rec + 16384) + cg * 16;     // (ls[t], ls[t+1]) pairs
+            const uint64_t hs2 = pf_pack2(hs, hs);
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {                 // two 32-column slices: keeps 32 (not 64) TMEM words live
-                uint32_t v[32];
-                PF_TMEM_LD32(v, taddr + hh * 32);
+            for (int hh = 0; hh < 2; ++hh) {                 // two 16-column slices
+                uint32_t v[16];
+                PF_TMEM_LD16(v, taddr + hh * 16);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (hh == 1) {
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -282,24 +294,22 @@ __global__ void __maxnreg__(112) prefill_w2_kernel(const PrefillParams p) {
                     __syncwarp();                                  // reconverge before the next .aligned tcgen05.ld
                 }
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 l = ls4[hh * 8 + j4];
-                    float *cc = cacc + hh * 32 + 4 * j4;
-                    cc[0] = fmaf(hs * l.x, (float)(int)v[4 * j4 + 0], cc[0]);
-                    cc[1] = fmaf(hs * l.y, (float)(int)v[4 * j4 + 1], cc[1]);
-                    cc[2] = fmaf(hs * l.z, (float)(int)v[4 * j4 + 2], cc[2]);
-                    cc[3] = fmaf(hs * l.w, (float)(int)v[4 * j4 + 3], cc[3]);
+                for (int j = 0; j < 8; ++j) {
+                    const uint64_t w2 = pf_mul2(hs2, ls2[hh * 8 + j]);
+                    acc2[hh * 8 + j] = pf_fma2(w2, pf_pack2((float)(int)v[2 * j], (float)(int)v[2 * j + 1]), acc2[hh * 8 + j]);
                 }
             }
             if (step & 1) {
                 // LUT-bias / zero-point term of the chunk: (0.5*s + z)[row] * (lb[2c] + lb[2c+1])[token]
-                const float4 *lb4 = reinterpret_cast<const float4 *>(rec + 16384 + 512) + half * 32;
+                const float wz = hs + zz;
+                const uint64_t wz2 = pf_pack2(wz, wz);
+                const float4 *lb4 = reinterpret_cast<const float4 *>(rec + 16384 + 512) + cg * 16;
 #pragma unroll
-                for (int j2 = 0; j2 < 32; ++j2) {
-                    const float4 l = lb4[j2];                 // two tokens: (lb0, lb1), (lb0, lb1)
-                    cacc[2 * j2 + 0] = fmaf(wz, l.x + l.y, cacc[2 * j2 + 0]);
-                    cacc[2 * j2 + 1] = fmaf(wz, l.z + l.w, cacc[2 * j2 + 1]);
+                for (int j = 0; j < 16; ++j) {
+                    const float4 l = lb4[j];                 // two tokens: (lb0, lb1), (lb0, lb1)
+                    acc2[j] = pf_fma2(wz2, pf_pack2(l.x + l.y, l.z + l.w), acc2[j]);
                 }
+                hs = hs_n; zz = zz_n;
             }
             if (warp == kPfWarpEpi && lane == 0) PF_TRACE(2, step, 2);
             __syncwarp();
@@ -309,12 +319,18 @@ __global__ void __maxnreg__(112) prefill_w2_kernel(const PrefillParams p) {
         const int row = rsb * 128 + r;
         if (row < p.Mout) {
 #pragma unroll
-            for (int j = 0; j < 64; ++j) {
-                const int t = half * 64 + j;
-                if (t < ntok) {
-                    const size_t o = (size_t)(n0 + t) * p.ldc + row;
-                    if (p.out_f16) reinterpret_cast<__half *>(p.C)[o] = __float2half_rn(cacc[j]);
-                    else reinterpret_cast<float *>(p.C)[o] = cacc[j];
+            for (int j = 0; j < 16; ++j) {
+                float lo, hi;
+                asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc2[j]));
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int t = cg * 32 + 2 * j + u;
+                    if (t < ntok) {
+                        const size_t o = (size_t)(n0 + t) * p.ldc + row;
+                        const float val = u ? hi : lo;
+                        if (p.out_f16) reinterpret_cast<__half *>(p.C)[o] = __float2half_rn(val);
+                        else reinterpret_cast<float *>(p.C)[o] = val;
+                    }
                 }
             }
         }
