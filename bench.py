@@ -445,8 +445,8 @@ def tokens_per_second(tb, lib, torch, stream):
         lib.tmac_b200_graph_free(g)
         for h in handles:
             h.free()
-    # Prefill-shaped call (BASELINE config 4: Llama-2-7B W2, seq 256): today the N>1 path runs the GEMV kernel once per
-    # activation row (grid.y = N; weight re-reads hit L2).  Reported so that the tcgen05 tile of a later round has a baseline.
+    # Prefill-shaped call (BASELINE config 4: Llama-2-7B W2, seq 256): N >= 32 takes the tcgen05 kind::i8 tile
+    # (tmac_prefill.cuh): preprocessor + LUT tiling + GEMM.  Tensor-pipe utilisation = int8 MMA rate / 4500 TOP/s (dense peak).
     try:
         NB = 256
         w, sc, z = synth(9)
@@ -461,8 +461,12 @@ def tokens_per_second(tb, lib, torch, stream):
             tb.gemv(wt, NB, xb, ob)
         e1.record(stream); torch.cuda.synchronize()
         s = e0.elapsed_time(e1) / 3 * 1e-3
-        res["prefill_seq256_one_tensor_11008x4096_w2"] = {"ms": s * 1e3, "dense_equivalent_TFLOPs": 2.0 * NB * MOUT * K / s / 1e12,
-                                                          "path": "GEMV kernel per activation row (ALU pipe); tcgen05 int8 tile not built yet"}
+        ll = tb.last_launch()
+        mma_tops = 2.0 * NB * MOUT * (2 * K) / s / 1e12       # contraction length = 8 LUT entries per K-group = 2K
+        res["prefill_seq256_one_tensor_11008x4096_w2"] = {
+            "ms": s * 1e3, "tokens_per_s_this_tensor": NB / s, "dense_equivalent_TFLOPs": 2.0 * NB * MOUT * K / s / 1e12,
+            "int8_mma_TOPs": mma_tops, "tensor_pipe_utilisation": mma_tops / 4500.0,
+            "path": "tcgen05.mma kind::i8 tile (one-hot-signed LUT contraction)" if ll["batch"] < 0 else "GEMV kernel per activation row"}
         wt.free()
     except Exception as ex:
         res["prefill_seq256_one_tensor_11008x4096_w2"] = {"error": str(ex)[:160]}
