@@ -326,7 +326,9 @@ def main():
     t_gemv = ms_g / args.steps / LAYERS * 1e-3
     peak, peak_src = measured_peak()
     achieved = algorithmic_bytes() / t_gemv / 1e9
-    roofline = {"bound": "hbm", "kernel": "gemv3_kernel<PB=2,SYM,QCH=8,AGQ=4>", "launch": lone_cfg, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    kname = ("gemv4_kernel<PB=2,SYM,QCH=8,AGQ=4> (stream-K grid, one CTA per SM)" if lone_cfg["cluster"] == 0
+             else "gemv3_kernel<PB=2,SYM,QCH=8,AGQ=4>")
+    roofline = {"bound": "hbm", "kernel": kname, "launch": lone_cfg, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src, "us_per_launch": t_gemv * 1e6,
                 "two_call_step": {"what": "preprocessor + qgemm_lut as two launches per layer (the reference's init/compute split)",
                                   "ms_per_step": ms_two, "GBps": bytes_step / (ms_two * 1e-3) / 1e9}, "algorithmic_bytes_per_launch": algorithmic_bytes(), "traffic": None}

@@ -61,7 +61,10 @@ TMAC_B200_API int tmac_b200_set_stream(void *stream);
 TMAC_B200_API int tmac_b200_set_float_type(int dtype); /* TMAC_B200_F32 (default) or _F16 */
 /* LUT handling in qgemm_lut: 0 = auto (device QLUTs written by tmac_b200_preprocessor and host
  * QLUTs that pass the odd-symmetry check LUT[15-i] == -LUT[i] take the 8-entry fast path, any
- * other QLUT the general 16-entry path), 1 = always general, 2 = always symmetric. */
+ * other QLUT the general 16-entry path), 1 = always general, 2 = always symmetric.
+ * A DEVICE QLUT buffer is recognised by address: if a caller overwrites a buffer that tmac_b200_preprocessor filled
+ * earlier with a table of its own (the reference never does; its QLUT always comes from preprocessor_int8), it must
+ * select mode 1 for that call. */
 TMAC_B200_API int tmac_b200_set_lut_mode(int mode);
 
 /* CUDA-graph helpers: capture the library calls issued between begin/end (device pointers only,
@@ -72,8 +75,12 @@ TMAC_B200_API int tmac_b200_graph_launch(int64_t graph, int times);
 TMAC_B200_API int tmac_b200_graph_free(int64_t graph);
 TMAC_B200_API int tmac_b200_sync(void);
 /* Reporting: {cluster size, warps/CTA, chunks/warp, register variant, grid.x, planes/word, symmetric LUT,
- * batch} of the last qgemm_lut launch. */
+ * batch} of the last qgemm_lut launch.  cluster size 0 = the stream-K lone-launch kernel (gemv4_kernel; chunks/warp then
+ * holds blocks per CTA); batch < 0 = the tcgen05 prefill tile over -batch activation rows. */
 TMAC_B200_API int tmac_b200_debug_last_launch(int *out8);
+/* Tuning / A-B knobs at run time: key = a TMAC_B200_* environment variable name in lower case without the prefix
+ * ("g4", "g4_grid", "fused", "prefill", "prefill_min_n", "pdl", "pdl_late", "cs", "wpc", "minb", "kernel"). */
+TMAC_B200_API int tmac_b200_debug_set(const char *key, int value);
 /* Debug (TMAC_B200_TRACE=1): per-CTA clock64 stamps [ctas][8] of the last qgemm_lut launch. */
 TMAC_B200_API int tmac_b200_debug_trace(long long *dst, int cap_ctas);
 

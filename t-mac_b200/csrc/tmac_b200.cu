@@ -22,6 +22,7 @@
 
 #include "tmac_kernels.cuh"
 #include "tmac_prefill.cuh"
+#include "tmac_gemv4.cuh"
 #include "tmac_layout.h"
 
 using namespace tmac_b200;
@@ -82,9 +83,11 @@ struct Context {
     int ks_override = 0;
     int kernel_version = 3;              // 3 = gemv3_kernel (clusters + DSMEM + PDL), 1 = gemv_kernel (split-K scratch)
     int use_pdl = 1;
-    int cs_override = 0, wpc_override = 0, pdl_late = -1, minb_override = 0;
+    int cs_override = 0, wpc_override = 0, pdl_late = -1, minb_override = 0, nbuf_override = 0;
     int last_launch[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int use_fused = 1;
+    int use_g4 = 0, g4_grid = 0;         // lone launches: stream-K kernel (0 off, 1 auto, 2 whenever the shape allows); grid override
+    std::map<cudaStream_t, void *> xchg; // gemv4 exchange slots, one buffer per stream that ever launched it
     int use_prefill = 1, prefill_min_n = 32;   // N >= prefill_min_n: tcgen05 int8 tile (W2 g128 act64)                   // tmac_b200_gemv builds the LUT inside the GEMV when the grouping allows
     int64_t next_hint = 0;               // one-shot: tensor whose blocks the next launch prefetches into L2
     std::map<int64_t, Resident> res;
@@ -138,6 +141,9 @@ int ensure_init() {
     if (const char *e = getenv("TMAC_B200_PREFILL")) g.use_prefill = atoi(e);
     if (const char *e = getenv("TMAC_B200_PREFILL_MIN_N")) g.prefill_min_n = atoi(e);
     if (const char *e = getenv("TMAC_B200_WPC")) g.wpc_override = atoi(e);
+    if (const char *e = getenv("TMAC_B200_NBUF")) g.nbuf_override = atoi(e);
+    if (const char *e = getenv("TMAC_B200_G4")) g.use_g4 = atoi(e);
+    if (const char *e = getenv("TMAC_B200_G4_GRID")) g.g4_grid = atoi(e);
     g.inited = true;
     return 0;
 }
@@ -235,10 +241,17 @@ void choose_decomposition(int nrsb, int nchunk, int N, int *cs_out, int *wpc_out
 struct BatchPtrs { int n = 0; const unsigned char *const *W = nullptr; const int8_t *const *q = nullptr; const float *const *ls = nullptr,
                    *const *lb = nullptr; void *const *C = nullptr; };
 
+int launch_gemv4(const Resident &R, int row_begin, int row_end, const int8_t *qlut, const float *ls, const float *lb, void *C,
+                 int c_row0, int out_f16, bool sym, const void *fused_act, int act_f16);
+
 int launch_gemv3(const Resident &R, int row_begin, int row_end, int N, const int8_t *qlut, const float *ls, const float *lb, void *C,
                  int ldc, int c_row0, int out_f16, bool sym, const BatchPtrs *batch = nullptr, const void *fused_act = nullptr,
                  int act_f16 = 0) {
     const StreamLayout &L = R.L;
+    if (N == 1 && !batch) {   // one tensor, one activation row: the stream-K kernel when the shape is worth it
+        const int rc = launch_gemv4(R, row_begin, row_end, qlut, ls, lb, C, c_row0, out_f16, sym, fused_act, act_f16);
+        if (rc <= 0) return rc;
+    }
     if (row_begin < 0 || row_end > L.Mout || row_begin >= row_end) return fail("qgemm_lut: bad row range");
     const int rsb0 = row_begin / L.rsb, rsb1 = (row_end + L.rsb - 1) / L.rsb, nrsb = rsb1 - rsb0;
     const bool int_path = L.one_scale && L.act_group_size == L.K;
@@ -264,7 +277,8 @@ int launch_gemv3(const Resident &R, int row_begin, int row_end, int N, const int
     // Measured on B200 (profiles/): a lone launch per tensor is latency bound and prefers fewer, fatter
     // CTAs with more registers (ILP); grouped / batched launches are ALU-pipe bound and prefer more CTAs.
     const bool lone = (N * std::max(1, nb) == 1);
-    int minb = lone ? 3 : 4;
+    int minb = 3;   // 85-register variant everywhere: shared memory caps residency at 3 CTAs per SM anyway, and the extra ILP measured +6 % on grouped launches
+    (void)lone;
     if (lone && p.cs == 8 && p.wpc == 4 && p.bpw == 1) { p.cs = 4; p.wpc = 8; }
     if (!lone && (long)nrsb * N * std::max(1, nb) >= 4L * g.sms) {   // machine already full of whole super-blocks: no K split
         p.cs = 1; p.wpc = std::min(kG3MaxWarps, L.nchunk); p.bpw = (L.nchunk + p.wpc - 1) / p.wpc;
@@ -284,8 +298,10 @@ int launch_gemv3(const Resident &R, int row_begin, int row_end, int N, const int
     if (fused_act) { p.act = fused_act; p.act_f16 = act_f16; sym = true; }
     gemv3_fn fn = fused_act ? pick_gemv3_fused(L.pb, L.qch, agq, minb) : pick_gemv3(L.pb, sym, L.qch, agq, minb);
     if (!fn) return fail("qgemm_lut: unsupported chunking (qch=" + std::to_string(L.qch) + ", agq=" + std::to_string(agq) + ")");
-    const size_t smem = (size_t)p.cs * L.rsb * 4 +
-                        std::max((size_t)p.wpc * ((p.bpw > 1 ? 2 : 1) * L.blk + (size_t)L.qch * 4 * (sym ? 8 : 16)), (size_t)p.wpc * L.rsb * 4);
+    p.nbuf = (p.bpw > 1) ? 2 : 1;
+    if (g.nbuf_override > 0) p.nbuf = std::min(p.nbuf, g.nbuf_override);
+    const size_t wregion = std::max((size_t)p.wpc * (p.nbuf * L.blk + (size_t)L.qch * 4 * (sym ? 8 : 16)), (size_t)p.wpc * L.rsb * 4);
+    const size_t smem = (size_t)p.cs * L.rsb * 4 + ((wregion + 15) & ~(size_t)15) + (size_t)p.wpc * 16;   // + warp-private mbarriers
     if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     uint32_t wtx, wty;
     plane_weight_regs(L.bits, sym, &wtx, &wty);
@@ -305,6 +321,81 @@ int launch_gemv3(const Resident &R, int row_begin, int row_end, int N, const int
         ++na;
     }
     cfg.attrs = attr; cfg.numAttrs = na;
+    CUDA_OK(cudaLaunchKernelEx(&cfg, fn, p, wtx, wty));
+    return 0;
+}
+
+// Lone launch (N = 1, one tensor): stream-K grid, one CTA per SM per launch (gemv4_kernel, tmac_gemv4.cuh).
+// Returns 1 when the shape is left to gemv3 (small tensors, chunkings that are not instantiated, shares that do not
+// fit two CTAs per SM), 0 on launch, -1 on error.
+constexpr size_t kG4SmemBudget = 112 * 1024;   // two CTAs per SM: 2 * (budget + 1 KB reserved) <= 227 KB
+int launch_gemv4(const Resident &R, int row_begin, int row_end, const int8_t *qlut, const float *ls, const float *lb, void *C,
+                 int c_row0, int out_f16, bool sym, const void *fused_act, int act_f16) {
+    const StreamLayout &L = R.L;
+    if (!g.use_g4 || g.kernel_version != 3) return 1;
+    if (row_begin < 0 || row_end > L.Mout || row_begin >= row_end) return fail("qgemm_lut: bad row range");
+    const int rsb0 = row_begin / L.rsb, rsb1 = (row_end + L.rsb - 1) / L.rsb, nrsb = rsb1 - rsb0;
+    const long total = (long)nrsb * L.nchunk;
+    if (g.use_g4 == 1 && (total < 4L * g.sms || L.nchunk < 4)) return 1;
+    const bool int_path = L.one_scale && L.act_group_size == L.K;
+    const int agq = int_path ? 0 : std::min(L.act_group_size, L.ck) / 16;
+    if (fused_act) sym = true;
+    gemv4_fn fn = pick_gemv4(L.pb, sym, L.qch, agq, fused_act != nullptr);
+    if (!fn) return 1;
+    const int tab = L.qch * 4 * (sym ? 8 : 16);
+    int G = 0, per = 0, nseg = 0, ntab = 0; size_t stage = 0, smem = 0;
+    const long cands[3] = {g.g4_grid > 0 ? std::min<long>(g.g4_grid, 2L * g.sms) : 0L, (long)g.sms, 2L * g.sms};
+    for (long cl : cands) {
+        if (cl <= 0) continue;
+        const int cand = (int)std::min(cl, total);
+        const int per_c = (int)((total + cand - 1) / cand);
+        const int nseg_c = (per_c - 1 + L.nchunk - 1) / L.nchunk + 1;
+        const size_t stage_c = ((size_t)per_c * L.blk + 127) & ~(size_t)127;
+        const int ntab_c = std::min(per_c, L.nchunk);
+        const size_t smem_c = stage_c + (size_t)nseg_c * kG4Warps * L.rsb * 4 + (size_t)ntab_c * (tab + 5 * 4) + kG4Warps * 8;
+        if (smem_c <= kG4SmemBudget) { G = cand; per = per_c; nseg = nseg_c; stage = stage_c; smem = smem_c; ntab = ntab_c; break; }
+    }
+    if (!G) return 1;
+    void *&xchg = g.xchg[g.stream()];
+    if (!xchg) {   // first use on this stream (not capturable: run once before capturing a graph)
+        const size_t bytes = (size_t)2 * g.sms * kG4MaxRsb * sizeof(uint2);
+        if (cudaMalloc(&xchg, bytes) != cudaSuccess) { cudaGetLastError(); xchg = nullptr; return fail("out of device memory (exchange slots)"); }
+        CUDA_OK(cudaMemset(xchg, 0, bytes));
+    }
+    Gemv4Params p{};
+    p.W = R.d + (size_t)rsb0 * L.rsb_stride;
+    p.Wnext = nullptr;
+    if (g.next_hint) {
+        auto it = g.res.find(g.next_hint);
+        if (it != g.res.end() && it->second.L.total == L.total && it->second.L.blk == L.blk) p.Wnext = it->second.d + (size_t)rsb0 * L.rsb_stride;
+        g.next_hint = 0;
+    }
+    p.qlut = qlut; p.lut_scales = ls; p.lut_biases = lb; p.C = C; p.act = fused_act; p.act_f16 = act_f16;
+    p.K = L.K; p.row_begin = row_begin; p.row_end = row_end; p.c_row0 = c_row0;
+    p.nrsb = nrsb; p.rsb0 = rsb0; p.nchunk = L.nchunk; p.ags = L.act_group_size;
+    p.zp = L.zp; p.one_scale = L.one_scale; p.sd = L.sd; p.out_f16 = out_f16; p.blk_bytes = (int)L.blk;
+    p.total = (int)total; p.per_max = per; p.nseg_max = nseg; p.stage_bytes = (int)stage; p.ntab = ntab;
+    p.rsb_stride = L.rsb_stride; p.scale0 = L.scale0; p.xchg = (uint2 *)xchg;
+    g.last_launch[0] = 0; g.last_launch[1] = kG4Warps; g.last_launch[2] = per; g.last_launch[3] = 2;
+    g.last_launch[4] = G; g.last_launch[5] = L.pb; g.last_launch[6] = sym ? 1 : 0; g.last_launch[7] = 1;
+    if (g.trace) {   // ring of 8 launches
+        const size_t pl = (size_t)G * 8;
+        if (g.d_trace.ensure(std::max((size_t)8192, pl * 8 * sizeof(long long)))) return fail("out of device memory (trace)");
+        p.trace = (long long *)g.d_trace.p + pl * (size_t)(g.trace_seq++ % 8);
+        g.trace_ctas = G;
+    }
+    if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint32_t wtx, wty;
+    plane_weight_regs(L.bits, sym, &wtx, &wty);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(G, 1, 1);
+    cfg.blockDim = dim3(kG4Warps * 32, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = g.stream();
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g.use_pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
     CUDA_OK(cudaLaunchKernelEx(&cfg, fn, p, wtx, wty));
     return 0;
 }
@@ -817,6 +908,27 @@ int tmac_b200_debug_trace(long long *dst, int cap_ctas) {
     const int n = std::min(cap_ctas, g.trace_ctas * 8);   // ring of 8 launches x ctas
     CUDA_OK(cudaMemcpy(dst, g.d_trace.p, (size_t)n * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
     return g.trace_ctas;
+}
+
+// Tuning / A-B knobs at run time (same names as the TMAC_B200_* environment variables, lower case, without the prefix).
+int tmac_b200_debug_set(const char *key, int value) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    const std::string k = key ? key : "";
+    if (k == "g4") g.use_g4 = value;
+    else if (k == "g4_grid") g.g4_grid = value;
+    else if (k == "fused") g.use_fused = value;
+    else if (k == "prefill") g.use_prefill = value;
+    else if (k == "prefill_min_n") g.prefill_min_n = value;
+    else if (k == "pdl") g.use_pdl = value;
+    else if (k == "pdl_late") g.pdl_late = value;
+    else if (k == "cs") g.cs_override = value;
+    else if (k == "wpc") g.wpc_override = value;
+    else if (k == "minb") g.minb_override = value;
+    else if (k == "nbuf") g.nbuf_override = value;
+    else if (k == "kernel") g.kernel_version = value;
+    else return fail("tmac_b200_debug_set: unknown key '" + k + "'");
+    return 0;
 }
 
 int tmac_b200_set_lut_mode(int mode) {

@@ -74,6 +74,19 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
 // ------------------------------------------------------------------------------------------
 template <int PB, bool SYM> struct Quad;
 
+// Sign handling of the symmetric (8 stored entries) path without a shift: the selector nibble of the sign PRMT is
+// neg << 3 | byte position, i.e. the weight word ANDed in place.  PRMT's replicate mode (selector bit 3) turns the
+// selected byte 2*w (msb clear) into 0x00, so prmt(2w, sel) = 2*w*(1 - neg); with the constant vector -w,
+//   dp4a(v, 2w(1-neg)) + dp4a(v, -w) = sum v*w*(1 - 2*neg)
+// exactly.  One LOP3 per word instead of SHF + LOP3 on the saturated ALU pipe; the extra DP4A rides the FMA pipe.
+// The general (16 stored entries) path keeps neg << 2 | position: it selects between two looked-up candidates.
+template <bool SYM> __device__ __forceinline__ uint32_t sign_sel(uint32_t w) {
+    return SYM ? and_or(w, 0x88888888u, 0x32103210u) : and_or(w >> 1, 0x44444444u, 0x32103210u);
+}
+__device__ __forceinline__ int dp4a_signed(uint32_t v, uint32_t w2, uint32_t wneg, uint32_t sel, int acc) {
+    return __dp4a((int)v, (int)prmt(w2, w2, sel), __dp4a((int)v, (int)wneg, acc));
+}
+
 // sign/plane-weight tables (bytes): index = plane-position | neg << 2
 //   PB 4: {1,2,4,8 | -1,-2,-4,-8}   (bits 3: plane 3 weight 0)
 //   PB 2: {1,2,1,2 | -1,-2,-1,-2}
@@ -85,13 +98,14 @@ template <bool SYM> struct Quad<4, SYM> {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const uint32_t wj = ww[k] & 0x77777777u;
-            const uint32_t ws = and_or(ww[k] >> 1, 0x44444444u, 0x32103210u);
+            const uint32_t ws = sign_sel<SYM>(ww[k]);
             uint32_t v0, v1;
             if (SYM) {
+                const uint32_t w2 = wtx << 1;
                 v0 = prmt(tab[2 * k], tab[2 * k + 1], wj);
                 v1 = prmt(tab[2 * k], tab[2 * k + 1], hi16(wj));
-                acc[0] = __dp4a((int)v0, (int)prmt(wtx, wty, ws), acc[0]);
-                acc[1] = __dp4a((int)v1, (int)prmt(wtx, wty, hi16(ws)), acc[1]);
+                acc[0] = dp4a_signed(v0, w2, wty, ws, acc[0]);
+                acc[1] = dp4a_signed(v1, w2, wty, hi16(ws), acc[1]);
             } else {
                 const uint32_t *g = tab + 4 * k;
                 v0 = prmt(prmt(g[0], g[1], wj), prmt(g[2], g[3], wj), ws);
@@ -111,16 +125,16 @@ template <bool SYM> struct Quad<2, SYM> {
         for (int pr = 0; pr < 2; ++pr) {
             const uint32_t we = ww[2 * pr], wo = ww[2 * pr + 1];
             const uint32_t je = we & 0x77777777u, jo = wo & 0x77777777u;
-            const uint32_t se = and_or(we >> 1, 0x44444444u, 0x32103210u);
-            const uint32_t so = and_or(wo >> 1, 0x44444444u, 0x32103210u);
+            const uint32_t se = sign_sel<SYM>(we), so = sign_sel<SYM>(wo);
             if (SYM) {
+                const uint32_t w2 = wtx << 1;
                 const uint32_t *te = tab + 4 * pr, *to = tab + 4 * pr + 2;
                 const uint32_t v0a = prmt(te[0], te[1], je), v0b = prmt(te[0], te[1], hi16(je));
                 const uint32_t v1a = prmt(to[0], to[1], jo), v1b = prmt(to[0], to[1], hi16(jo));
-                acc[0] = __dp4a((int)prmt(v0a, v1a, 0x5410), (int)prmt(wtx, wty, se), acc[0]);
-                acc[1] = __dp4a((int)prmt(v0a, v1a, 0x7632), (int)prmt(wtx, wty, hi16(se)), acc[1]);
-                acc[2] = __dp4a((int)prmt(v0b, v1b, 0x5410), (int)prmt(wtx, wty, so), acc[2]);
-                acc[3] = __dp4a((int)prmt(v0b, v1b, 0x7632), (int)prmt(wtx, wty, hi16(so)), acc[3]);
+                acc[0] = dp4a_signed(prmt(v0a, v1a, 0x5410), w2, wty, se, acc[0]);
+                acc[1] = dp4a_signed(prmt(v0a, v1a, 0x7632), w2, wty, hi16(se), acc[1]);
+                acc[2] = dp4a_signed(prmt(v0b, v1b, 0x5410), w2, wty, so, acc[2]);
+                acc[3] = dp4a_signed(prmt(v0b, v1b, 0x7632), w2, wty, hi16(so), acc[3]);
             } else {
                 const uint32_t *ge = tab + 8 * pr, *go = tab + 8 * pr + 4;
                 const uint32_t l0a = prmt(ge[0], ge[1], je), l0b = prmt(ge[0], ge[1], hi16(je));
@@ -152,7 +166,7 @@ template <bool SYM> struct Quad<1, SYM> {
         const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
         uint32_t s[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) s[k] = and_or(ww[k] >> 1, 0x44444444u, 0x32103210u);
+        for (int k = 0; k < 4; ++k) s[k] = sign_sel<SYM>(ww[k]);
         uint32_t xa[4], xb[4];
         if (SYM) {
             uint32_t va[4], vb[4];
@@ -168,8 +182,8 @@ template <bool SYM> struct Quad<1, SYM> {
             for (int r = 0; r < 4; ++r) {
                 const uint32_t sa = (r & 1) ? (hi16(s[r >> 1])) : s[r >> 1];           // rows 0..3: words 0,0,1,1
                 const uint32_t sb = (r & 1) ? (hi16(s[2 + (r >> 1)])) : s[2 + (r >> 1)]; // rows 4..7: words 2,2,3,3
-                acc[r] = __dp4a((int)xa[r], (int)prmt(wtx, wty, sa), acc[r]);
-                acc[4 + r] = __dp4a((int)xb[r], (int)prmt(wtx, wty, sb), acc[4 + r]);
+                acc[r] = dp4a_signed(xa[r], wtx << 1, wty, sa, acc[r]);
+                acc[4 + r] = dp4a_signed(xb[r], wtx << 1, wty, sb, acc[4 + r]);
             }
         } else {
             uint32_t la[4], lb[4], ha[4], hb[4], xla[4], xlb[4], xha[4], xhb[4];
@@ -409,6 +423,7 @@ struct Gemv3Params {
     int zp, one_scale, sd, out_f16;
     int blk_bytes;                 // bytes per block (weights + scales)
     int cs, wpc, bpw;              // cluster size, warps per CTA, chunks per warp
+    int nbuf;                      // stage buffers per warp (1 or 2)
     int pdl_late;                  // trigger dependents after the math instead of at entry
     // grouped launch: blockIdx.z selects one of `nbatch` problems with identical geometry
     int nbatch;
@@ -464,6 +479,27 @@ __device__ __forceinline__ void st_cluster_f32(float *local_ptr, uint32_t rank, 
     asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(raddr), "f"(v) : "memory");
 }
 
+// One bulk (TMA) copy per block instead of a per-lane cp.async loop: 1 instruction from one lane instead of
+// ~4 per 16 bytes on the ALU pipe that the lookup loop saturates; completion on a warp-private mbarrier.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init1(uint64_t *b) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint64_t *b, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}\n"
+        ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+
 constexpr int kG3MaxWarps = 8;
 
 // MINB = minimum resident CTAs per SM the register allocation is tuned for: 3 (85 registers, more ILP;
@@ -488,12 +524,15 @@ __global__ void __launch_bounds__(kG3MaxWarps * 32, MINB) gemv3_kernel(const Gem
     // (QCH*4*TB).  The CTA reduction buffer red [WPC][RSB] aliases the stages once they are consumed.
     float *cl = reinterpret_cast<float *>(smem);
     const int tab_bytes = QCH * 4 * TB;
-    const int nbuf = p.bpw > 1 ? 2 : 1;           // double-buffered stage when a warp walks several chunks
+    const int nbuf = p.nbuf;                      // 2 = double-buffered stage when a warp walks several chunks, 1 = single
     const int per_warp = nbuf * p.blk_bytes + tab_bytes;
     unsigned char *wbase = smem + (size_t)p.cs * RSB * 4;
     unsigned char *stage0 = wbase + (size_t)warp * per_warp;
     unsigned char *tab = stage0 + nbuf * p.blk_bytes;
     float *red = reinterpret_cast<float *>(wbase);
+    // warp-private mbarriers (one per stage buffer) behind the region that red aliases
+    const size_t wregion = max((size_t)WPC * per_warp, (size_t)WPC * RSB * 4);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(wbase + ((wregion + 15) & ~(size_t)15)) + warp * 2;
 
     if (tid == 0) { TMAC_TRACE(0); }
     if (p.cs > 1) cluster_arrive_relaxed();       // phase 1: "I am running" (waited for right before the DSMEM stores)
@@ -508,18 +547,19 @@ __global__ void __launch_bounds__(kG3MaxWarps * 32, MINB) gemv3_kernel(const Gem
     if (p.nbatch > 0) { const int z = blockIdx.z; Wb = p.Wv[z]; qb = p.qlutv[z]; lsb = p.lsv[z]; lbb = p.lbv[z]; Cb = p.Cv[z]; }
     const unsigned char *rsb_base = Wb + (size_t)rsb * p.rsb_stride;
     const int nag = p.K / p.ags;
-    const uint64_t pol = policy_evict_first();
-    const int n16 = p.blk_bytes >> 4;
 
     // ---- first chunk: HBM -> shared, issued before the dependency wait -------------------------
-    if (c_first < c_end) {
-        const unsigned char *src = rsb_base + (size_t)c_first * p.blk_bytes;
-        for (int i = lane; i < n16; i += 32) cp_async16(stage0 + i * 16, src + i * 16, pol);
-        cp_async_commit();
-        if (p.Wnext && lane == 0)                  // pull the next tensor's blocks of this warp into L2
-            l2_prefetch_bulk(p.Wnext + (size_t)rsb * p.rsb_stride + (size_t)c_first * p.blk_bytes,
-                             (uint32_t)((c_end - c_first) * p.blk_bytes));
+    if (lane == 0) {
+        mbar_init1(mbar); mbar_init1(mbar + 1);
+        mbar_fence_init();
+        if (c_first < c_end) {
+            bulk_load(stage0, rsb_base + (size_t)c_first * p.blk_bytes, (uint32_t)p.blk_bytes, mbar);
+            if (p.Wnext)                           // pull the next tensor's blocks of this warp into L2
+                l2_prefetch_bulk(p.Wnext + (size_t)rsb * p.rsb_stride + (size_t)c_first * p.blk_bytes,
+                                 (uint32_t)((c_end - c_first) * p.blk_bytes));
+        }
     }
+    __syncwarp();
     if (tid == 0) TMAC_TRACE(1);
     pdl_wait();                                   // LUT / LUT scales come from the previous kernel
     if (tid == 0) TMAC_TRACE(2);
@@ -599,15 +639,18 @@ __global__ void __launch_bounds__(kG3MaxWarps * 32, MINB) gemv3_kernel(const Gem
                 for (int a = 0; a < NAG; ++a) { lsv[a] = __ldg(lsg + c * NAG + a); lbsum += __ldg(lbg + c * NAG + a); }
             }
         }
-        unsigned char *stage = stage0 + (size_t)((c - c_first) & (nbuf - 1)) * p.blk_bytes;
-        if (nbuf == 2 && c + 1 < c_end) {          // request chunk c+1 into the other buffer, then wait for chunk c only
-            unsigned char *nxt = stage0 + (size_t)((c + 1 - c_first) & 1) * p.blk_bytes;
-            const unsigned char *src = rsb_base + (size_t)(c + 1) * p.blk_bytes;
-            for (int i = lane; i < n16; i += 32) cp_async16(nxt + i * 16, src + i * 16, pol);
-            cp_async_commit();
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else
-            cp_async_wait_all();
+        const int li = c - c_first, buf = li & (nbuf - 1);
+        unsigned char *stage = stage0 + (size_t)buf * p.blk_bytes;
+        if (nbuf == 2) {
+            if (c + 1 < c_end && lane == 0) {      // request chunk c+1 into the other buffer (consumed at c-1, see the __syncwarp below)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                bulk_load(stage0 + (size_t)((li + 1) & 1) * p.blk_bytes, rsb_base + (size_t)(c + 1) * p.blk_bytes, (uint32_t)p.blk_bytes, mbar + ((li + 1) & 1));
+            }
+        } else if (li > 0 && lane == 0) {          // single buffer: the other resident warps cover this warp's load latency
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            bulk_load(stage0, rsb_base + (size_t)c * p.blk_bytes, (uint32_t)p.blk_bytes, mbar);
+        }
+        mbar_wait_parity(mbar + buf, nbuf == 2 ? ((li >> 1) & 1) : (li & 1));
         __syncwarp();
         if (tid == 0 && c == c_first) TMAC_TRACE(3);
         const uint4 *wp = reinterpret_cast<const uint4 *>(stage) + lane;
@@ -704,7 +747,7 @@ __global__ void __launch_bounds__(kG3MaxWarps * 32, MINB) gemv3_kernel(const Gem
 // One thread per (row, plane); straightforward lookups in the full 16-entry table, decoding the
 // stream layout nibble by nibble.  Not a performance path.
 // ------------------------------------------------------------------------------------------
-__global__ void cbits_kernel(const unsigned char *W, const int8_t *qlut, int32_t *cbits, int Mout, int K, int bits,
+static __global__ void cbits_kernel(const unsigned char *W, const int8_t *qlut, int32_t *cbits, int Mout, int K, int bits,
                              int pb, int qch, int nchunk, size_t rsb_stride, size_t blk_stride, int N) {
     const int rw = 8 / pb, rsbsz = 32 * rw;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -37,7 +37,7 @@ EXPORTS = [
     "tmac_b200_set_float_type", "tmac_b200_set_lut_mode", "tmac_b200_register_kcfg", "tmac_b200_load_kcfg_file",
     "tmac_b200_find_kcfg", "tmac_b200_clear_kcfg", "tmac_b200_upload_weights", "tmac_b200_upload_plain",
     "tmac_b200_upload_plain_rows", "tmac_b200_debug_encode", "tmac_b200_free_weights", "tmac_b200_clone_weights", "tmac_b200_hint_next_weights",
-    "tmac_b200_graph_begin", "tmac_b200_graph_end", "tmac_b200_graph_launch", "tmac_b200_graph_free", "tmac_b200_sync", "tmac_b200_debug_trace", "tmac_b200_debug_last_launch", "tmac_b200_weights_nbytes", "tmac_b200_preprocessor",
+    "tmac_b200_graph_begin", "tmac_b200_graph_end", "tmac_b200_graph_launch", "tmac_b200_graph_free", "tmac_b200_sync", "tmac_b200_debug_trace", "tmac_b200_debug_last_launch", "tmac_b200_debug_set", "tmac_b200_weights_nbytes", "tmac_b200_preprocessor",
     "tmac_b200_qgemm_lut", "tmac_b200_qgemm_lut_grouped", "tmac_b200_gemv", "tmac_b200_cbits", "qgemm_lut_int8", "preprocessor_int8",
     "ggml_tmac_init", "ggml_tmac_free", "ggml_tmac_mul_mat_task_init", "ggml_tmac_mul_mat_task_compute",
     "ggml_tmac_set_n_threads", "ggml_tmac_get_type_bits", "ggml_tmac_b200_can_mul_mat",
@@ -69,7 +69,7 @@ def load() -> C.CDLL:
         "tmac_b200_debug_encode": (i64, [C.POINTER(KCfg), vp, vp, vp, sz, C.POINTER(C.c_int)]),
         "tmac_b200_free_weights": (i, [i64]), "tmac_b200_clone_weights": (i64, [i64]), "tmac_b200_hint_next_weights": (i, [i64]),
         "tmac_b200_graph_begin": (i, []), "tmac_b200_graph_end": (i64, []), "tmac_b200_graph_launch": (i, [i64, i]),
-        "tmac_b200_graph_free": (i, [i64]), "tmac_b200_sync": (i, []), "tmac_b200_debug_trace": (i, [vp, i]), "tmac_b200_debug_last_launch": (i, [C.POINTER(C.c_int)]), "tmac_b200_weights_nbytes": (sz, [i64]),
+        "tmac_b200_graph_free": (i, [i64]), "tmac_b200_sync": (i, []), "tmac_b200_debug_trace": (i, [vp, i]), "tmac_b200_debug_last_launch": (i, [C.POINTER(C.c_int)]), "tmac_b200_debug_set": (i, [C.c_char_p, i]), "tmac_b200_weights_nbytes": (sz, [i64]),
         "tmac_b200_preprocessor": (i, [i, i, i, i, vp, vp, vp, vp]),
         "tmac_b200_qgemm_lut": (i, [i64, i, i, i, i, vp, vp, vp, vp]),
         "tmac_b200_qgemm_lut_grouped": (i, [vp, i, i, i, vp, vp, vp, vp]),
@@ -140,6 +140,10 @@ def last_launch() -> dict:
     v = (C.c_int * 8)()
     load().tmac_b200_debug_last_launch(v)
     return dict(zip(["cluster", "warps_per_cta", "chunks_per_warp", "min_blocks", "grid_x", "planes_per_word", "sym_lut", "batch"], list(v)))
+
+
+def debug_set(key: str, value: int) -> None:
+    check(load().tmac_b200_debug_set(key.encode(), int(value)), "tmac_b200_debug_set")
 
 
 def clone(wt: "Weights") -> "Weights":

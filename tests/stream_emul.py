@@ -56,15 +56,22 @@ def _tables(qlut_g, sym):
 
 def quad(pb, sym, w, tabs, acc, wtx, wty):
     """w: uint32 [4][lanes]; tabs: per word k list of register arrays; acc: int64 [RW][lanes]."""
-    M7, M4, C = np.uint32(0x77777777), np.uint32(0x44444444), np.uint32(0x32103210)
+    M7, M4, M8, C = np.uint32(0x77777777), np.uint32(0x44444444), np.uint32(0x88888888), np.uint32(0x32103210)
     sh16 = np.uint32(16)
+    w2 = np.uint32(int(wtx) << 1)
+
+    def sign_sel(x):       # tmac_kernels.cuh sign_sel<SYM>
+        return ((x & M8) | C) if sym else (((x >> np.uint32(1)) & M4) | C)
+
+    def dp4a_signed(v, sel_, acc_):   # tmac_kernels.cuh dp4a_signed: v*2w(1-neg) - v*w
+        return dp4a(v, prmt(w2, w2, sel_), dp4a(v, wty, acc_))
     if pb == 4:
         for k in range(4):
-            wj = w[k] & M7; ws = ((w[k] >> np.uint32(1)) & M4) | C
+            wj = w[k] & M7; ws = sign_sel(w[k])
             t = tabs[k]
             if sym:
-                acc[0] = dp4a(prmt(t[0], t[1], wj), prmt(wtx, wty, ws), acc[0])
-                acc[1] = dp4a(prmt(t[0], t[1], wj >> sh16), prmt(wtx, wty, ws >> sh16), acc[1])
+                acc[0] = dp4a_signed(prmt(t[0], t[1], wj), ws, acc[0])
+                acc[1] = dp4a_signed(prmt(t[0], t[1], wj >> sh16), ws >> sh16, acc[1])
             else:
                 acc[0] = dp4a(prmt(prmt(t[0], t[1], wj), prmt(t[2], t[3], wj), ws), wtx, acc[0])
                 acc[1] = dp4a(prmt(prmt(t[0], t[1], wj >> sh16), prmt(t[2], t[3], wj >> sh16), ws >> sh16), wtx, acc[1])
@@ -72,15 +79,15 @@ def quad(pb, sym, w, tabs, acc, wtx, wty):
         for pr in range(2):
             we, wo = w[2 * pr], w[2 * pr + 1]
             je, jo = we & M7, wo & M7
-            se, so = ((we >> np.uint32(1)) & M4) | C, ((wo >> np.uint32(1)) & M4) | C
+            se, so = sign_sel(we), sign_sel(wo)
             te, to = tabs[2 * pr], tabs[2 * pr + 1]
             if sym:
                 v0a, v0b = prmt(te[0], te[1], je), prmt(te[0], te[1], je >> sh16)
                 v1a, v1b = prmt(to[0], to[1], jo), prmt(to[0], to[1], jo >> sh16)
-                acc[0] = dp4a(prmt(v0a, v1a, 0x5410), prmt(wtx, wty, se), acc[0])
-                acc[1] = dp4a(prmt(v0a, v1a, 0x7632), prmt(wtx, wty, se >> sh16), acc[1])
-                acc[2] = dp4a(prmt(v0b, v1b, 0x5410), prmt(wtx, wty, so), acc[2])
-                acc[3] = dp4a(prmt(v0b, v1b, 0x7632), prmt(wtx, wty, so >> sh16), acc[3])
+                acc[0] = dp4a_signed(prmt(v0a, v1a, 0x5410), se, acc[0])
+                acc[1] = dp4a_signed(prmt(v0a, v1a, 0x7632), se >> sh16, acc[1])
+                acc[2] = dp4a_signed(prmt(v0b, v1b, 0x5410), so, acc[2])
+                acc[3] = dp4a_signed(prmt(v0b, v1b, 0x7632), so >> sh16, acc[3])
             else:
                 l0a, l0b = prmt(te[0], te[1], je), prmt(te[0], te[1], je >> sh16)
                 h0a, h0b = prmt(te[2], te[3], je), prmt(te[2], te[3], je >> sh16)
@@ -95,7 +102,7 @@ def quad(pb, sym, w, tabs, acc, wtx, wty):
             t01, t23 = prmt(v[0], v[1], 0x5140), prmt(v[2], v[3], 0x5140)
             u01, u23 = prmt(v[0], v[1], 0x7362), prmt(v[2], v[3], 0x7362)
             return [prmt(t01, t23, 0x5410), prmt(t01, t23, 0x7632), prmt(u01, u23, 0x5410), prmt(u01, u23, 0x7632)]
-        s = [((w[k] >> np.uint32(1)) & M4) | C for k in range(4)]
+        s = [sign_sel(w[k]) for k in range(4)]
         j = [w[k] & M7 for k in range(4)]
         def sel(r, base):
             x = s[base + (r >> 1)]
@@ -104,8 +111,8 @@ def quad(pb, sym, w, tabs, acc, wtx, wty):
             xa = transpose4([prmt(tabs[k][0], tabs[k][1], j[k]) for k in range(4)])
             xb = transpose4([prmt(tabs[k][0], tabs[k][1], j[k] >> sh16) for k in range(4)])
             for r in range(4):
-                acc[r] = dp4a(xa[r], prmt(wtx, wty, sel(r, 0)), acc[r])
-                acc[4 + r] = dp4a(xb[r], prmt(wtx, wty, sel(r, 2)), acc[4 + r])
+                acc[r] = dp4a_signed(xa[r], sel(r, 0), acc[r])
+                acc[4 + r] = dp4a_signed(xb[r], sel(r, 2), acc[4 + r])
         else:
             xla = transpose4([prmt(tabs[k][0], tabs[k][1], j[k]) for k in range(4)])
             xha = transpose4([prmt(tabs[k][2], tabs[k][3], j[k]) for k in range(4)])

@@ -21,7 +21,10 @@ ls = torch.zeros((1, 64), device="cuda"); lb = torch.zeros_like(ls); out = torch
 tb.preprocessor(bench.K, 1, 64, x, ls, lb, q)
 def step():
     for i, wt in enumerate(layers):
-        tb.qgemm_lut(wt, 1, q, ls, lb, out[i])
+        if os.environ.get("TRACE_FUSED", "0") == "1":
+            tb.gemv(wt, 1, x, out[i])
+        else:
+            tb.qgemm_lut(wt, 1, q, ls, lb, out[i])
 step(); tb.check(lib.tmac_b200_sync(), "sync")
 tb.check(lib.tmac_b200_graph_begin(), "gb"); step(); g = lib.tmac_b200_graph_end(); tb.check(g, "ge")
 tb.check(lib.tmac_b200_graph_launch(g, 3), "run"); tb.check(lib.tmac_b200_sync(), "sync")
@@ -30,6 +33,9 @@ nc = lib.tmac_b200_debug_trace(buf.ctypes.data, 8 * 4096)
 t = buf[:8 * nc].reshape(8, nc, 8).astype(np.float64)
 t0 = t[:, :, 0].min()
 names = ["entry", "copies issued", "pdl wait done", "lut+data ready", "loop done", "cta reduced", "cluster synced", "stored(leader)"]
+if tb.last_launch()["cluster"] == 0:   # gemv4 (stream-K): slot 6 = partial sums published, 7 = rows finished
+    names = ["entry", "copies issued", "pdl wait done", "lut+data ready", "loop done", "cta synced", "published", "finished"]
+FUSED = os.environ.get("TRACE_FUSED", "0") == "1"
 order = np.argsort(t[:, :, 0].min(axis=1))
 print("ctas per launch", nc, "; times in ns relative to the first CTA entry of the oldest launch in the ring")
 for li in order:
