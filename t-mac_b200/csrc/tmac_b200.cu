@@ -277,8 +277,9 @@ int launch_gemv3(const Resident &R, int row_begin, int row_end, int N, const int
     // Measured on B200 (profiles/): a lone launch per tensor is latency bound and prefers fewer, fatter
     // CTAs with more registers (ILP); grouped / batched launches are ALU-pipe bound and prefer more CTAs.
     const bool lone = (N * std::max(1, nb) == 1);
-    int minb = 3;   // 85-register variant everywhere: shared memory caps residency at 3 CTAs per SM anyway, and the extra ILP measured +6 % on grouped launches
-    (void)lone;
+    // 85-register variant (more ILP) for lone launches and for grouped W1/W2 launches (shared memory caps residency at 3
+    // CTAs per SM anyway; measured +6 %); grouped W3/W4 launches measured better with the 64-register variant.
+    int minb = (lone || L.pb != 4) ? 3 : 4;
     if (lone && p.cs == 8 && p.wpc == 4 && p.bpw == 1) { p.cs = 4; p.wpc = 8; }
     if (!lone && (long)nrsb * N * std::max(1, nb) >= 4L * g.sms) {   // machine already full of whole super-blocks: no K split
         p.cs = 1; p.wpc = std::min(kG3MaxWarps, L.nchunk); p.bpw = (L.nchunk + p.wpc - 1) / p.wpc;
