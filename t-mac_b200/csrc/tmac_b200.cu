@@ -115,6 +115,16 @@ bool is_device_ptr(const void *p) {
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// 0 = ordinary host memory, 1 = page-locked host memory the device can address (dev = its device alias), 2 = device / managed
+int ptr_kind(const void *p, void **dev = nullptr) {
+    if (!p) return 0;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) return 2;
+    if (a.type == cudaMemoryTypeHost && a.devicePointer) { if (dev) *dev = a.devicePointer; return 1; }
+    return 0;
+}
+
 int ensure_init() {
     if (g.inited) return 0;
     int n = 0;
@@ -628,6 +638,8 @@ void tmac_b200_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g.inited) return;
     cudaStreamSynchronize(g.stream());
+    for (auto &kv : g.xchg) if (kv.second) cudaFree(kv.second);
+    g.xchg.clear();
     for (auto &kv : g.res) cudaFree(kv.second.d);
     g.res.clear();
     for (DevBuf *b : {&g.d_b, &g.d_qlut, &g.d_ls, &g.d_lb, &g.d_c, &g.d_part, &g.d_cnt, &g.d_cbits}) { if (b->p) cudaFree(b->p); b->p = nullptr; b->cap = 0; }
@@ -1084,39 +1096,44 @@ int tmac_b200_gemv(int64_t handle, int N, int dtype, const void *B, void *C) {
     const int nag = L.K / L.act_group_size;
     const size_t qb = (size_t)N * L.K * 4, sb = (size_t)N * nag * 4;
     const size_t bb = (size_t)N * L.K * esize(dtype), cb = (size_t)N * L.Mout * esize(dtype);
-    const bool dev_b = is_device_ptr(B), dev_c = is_device_ptr(C);
-    const void *dB = B;
-    if (!dev_b) {
-        stage_wait();
-        if (g.h_in.ensure(bb)) return fail("out of pinned memory");
-        if (h2d(g.d_b, g.h_in, 0, B, bb)) return -1;
-        stage_mark();
-        dB = g.d_b.p;
-    }
-    void *dC = C;
-    if (!dev_c) {
-        // the kernel stores the (small) output straight into pinned host memory (UVA-mapped): one DMA-free write
-        // instead of a device buffer + cudaMemcpyAsync D2H
-        if (g.h_out.ensure(cb)) return fail("out of pinned memory");
-        dC = g.h_out.p;
-    }
+    void *pinB = nullptr, *pinC = nullptr;
+    const int kind_b = ptr_kind(B, &pinB), kind_c = ptr_kind(C, &pinC);
+    const bool dev_b = kind_b == 2, dev_c = kind_c == 2;
     const bool int_path = L.one_scale && L.act_group_size == L.K;
     const bool prefill_shape = g.use_prefill && N >= g.prefill_min_n && L.pb == 2 && L.qch == 8 && L.act_group_size == 64 && !L.one_scale;
     const bool can_fuse = g.use_fused && g.kernel_version != 1 && !int_path && L.act_group_size <= L.ck && g.lut_mode != 1 && !prefill_shape;
-    if (can_fuse) {
-        // one launch: the GEMV builds each chunk's LUT slice itself (bit-identical tables)
-        if (launch_gemv3(R, 0, L.Mout, N, nullptr, nullptr, nullptr, dC, L.Mout, 0, dtype == TMAC_B200_F16, true, nullptr, dB,
-                         dtype == TMAC_B200_F16)) return -1;
-    } else {
+    auto launch_compute = [&](const void *dB, void *dC) -> int {
+        if (can_fuse)   // one launch: the GEMV builds each chunk's LUT slice itself (bit-identical tables)
+            return launch_gemv3(R, 0, L.Mout, N, nullptr, nullptr, nullptr, dC, L.Mout, 0, dtype == TMAC_B200_F16, true, nullptr, dB,
+                                dtype == TMAC_B200_F16);
         if (g.d_qlut.ensure(qb) || g.d_ls.ensure(sb) || g.d_lb.ensure(sb)) return fail("out of device memory");
         if (launch_preprocessor(L.K, N, L.act_group_size, dtype, dB, (float *)g.d_ls.p, (float *)g.d_lb.p, (int8_t *)g.d_qlut.p)) return -1;
-        const bool sym = g.lut_mode != 1;
-        if (launch_gemv(R, 0, L.Mout, N, (const int8_t *)g.d_qlut.p, (const float *)g.d_ls.p, (const float *)g.d_lb.p, dC, L.Mout, 0,
-                        dtype == TMAC_B200_F16, sym, nullptr)) return -1;
+        return launch_gemv(R, 0, L.Mout, N, (const int8_t *)g.d_qlut.p, (const float *)g.d_ls.p, (const float *)g.d_lb.p, dC, L.Mout, 0,
+                           dtype == TMAC_B200_F16, g.lut_mode != 1, nullptr);
+    };
+    // The (small) output is stored by the kernel straight into page-locked host memory the device can address -- the
+    // caller's own buffer when it is page-locked, else our staging buffer -- instead of a device buffer + D2H copy.
+    void *dC = C;
+    if (kind_c == 1) dC = pinC;
+    else if (kind_c == 0) { if (g.h_out.ensure(cb)) return fail("out of pinned memory"); dC = g.h_out.p; }
+
+    const void *dB = B;
+    if (!dev_b) {
+        stage_wait();
+        if (kind_b == 1) {
+            if (g.d_b.ensure(bb)) return fail("out of device memory");
+            CUDA_OK(cudaMemcpyAsync(g.d_b.p, pinB, bb, cudaMemcpyHostToDevice, g.stream()));
+        } else {
+            if (g.h_in.ensure(bb)) return fail("out of pinned memory");
+            if (h2d(g.d_b, g.h_in, 0, B, bb)) return -1;
+            stage_mark();
+        }
+        dB = g.d_b.p;
     }
+    if (launch_compute(dB, dC)) return -1;
     if (!dev_c) {
         CUDA_OK(cudaStreamSynchronize(g.stream()));
-        std::memcpy(C, g.h_out.p, cb);
+        if (kind_c == 0) std::memcpy(C, g.h_out.p, cb);
     }
     return 0;
 }

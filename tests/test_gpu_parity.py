@@ -452,6 +452,31 @@ def test_prefill_tcgen05_tile_matches_oracle(lib, oracle, cfg, N):
         wt.free()
 
 
+@pytest.mark.parametrize("pinned", [False, True], ids=["pageable", "page_locked"])
+def test_host_call_buffers_in_place(lib, oracle, pinned):
+    """tmac_b200_gemv with host buffers (the reference's call shape): page-locked caller buffers are used in place (copy
+    source / kernel store target), ordinary memory goes through the staging buffers; repeated calls with NEW activations
+    in the same buffers see them."""
+    cfg = T.Config(512, 2048, 2, zero_point=True).resolved()
+    w, sc, z, x = T.make_problem(cfg, seed=31, N=1)
+    A, S = T.pack_reference_layout(w, sc, z, cfg)
+    wt = tb.upload_plain(kc(cfg), w, sc, z)
+    try:
+        hin = torch.zeros((1, cfg.K)); hout = torch.zeros((1, cfg.Mout))
+        if pinned:
+            hin, hout = hin.pin_memory(), hout.pin_memory()
+        for rep in range(3):
+            xr = (x * (rep + 1)).astype(np.float32)
+            hin.copy_(torch.from_numpy(xr))
+            hout.fill_(-1.0)
+            tb.gemv(wt, 1, hin, hout)
+            qo, lso, lbo = oracle.preprocessor(xr, cfg.act_group_size)
+            Co = oracle.qgemm(cfg, A, S, qo, lso, lbo)
+            assert np.abs(hout.numpy() - Co).max() <= TIGHT_TOL * np.abs(Co).max(), "rep %d" % rep
+    finally:
+        wt.free()
+
+
 def test_grouped_launch_equals_single_launches(lib, oracle):
     """tmac_b200_qgemm_lut_grouped (q/k/v-style fused launch) is bit-identical to per-tensor launches."""
     cfg = T.Config(512, 2048, 2, zero_point=True).resolved()
