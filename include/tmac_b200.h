@@ -188,6 +188,15 @@ struct tmac_tensor_extra_b200 {  /* mirrors struct tmac_tensor_extra, ggml-tmac.
 };
 TMAC_B200_API int ggml_tmac_b200_transform_tensor(void *data, int ne00, int ne01, int bits,
                                                   struct tmac_tensor_extra_b200 *extra);
+/* The same for every ggml type the reference transforms (ggml-tmac.cpp:72-96, :290-498): I1..I4 (36..39) as above;
+ * Q4_0 (2), TQ1_0 (34), TQ2_0 (35) blocks are decoded like the reference's accessors (:98-236; code w, real value
+ * (w - 2^(bits-1)) * d) and re-encoded.  extra->qweights is then an address key (a reserved, unbacked range of the size
+ * of the reference's permuted copy) to which ggml.c adds its tile offsets; extra->scales holds the scales in the
+ * reference's run-time order.  The kcfg for the shape must have group_size = 32 (Q4_0) / 256 (TQ*), no zero point. */
+TMAC_B200_API int ggml_tmac_b200_transform_tensor_typed(void *data, int ggml_type, int ne00, int ne01,
+                                                        struct tmac_tensor_extra_b200 *extra);
+/* Host-only: the block decode alone (codes [ne01][ne00], scales [ne01][ne00 / block]); returns the block size. */
+TMAC_B200_API int tmac_b200_debug_decode_ggml(int ggml_type, const void *data, int ne00, int ne01, uint8_t *w, float *scales);
 
 #ifdef __cplusplus
 }

@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <sys/mman.h>
 #include <map>
 #include <mutex>
 #include <set>
@@ -71,6 +72,9 @@ struct Resident {
     const unsigned char *host_a = nullptr;  // alias key: reference-layout host range
     size_t host_a_bytes = 0;
     int row0 = 0;                        // first row of the full tensor held here (row shards)
+    void *reserved = nullptr;            // address range reserved (PROT_NONE, no memory) to serve as the host alias key
+    size_t reserved_bytes = 0;
+    float *host_scales = nullptr;        // scales in the reference's run-time order, owned here (tmac_tensor_extra::scales)
 };
 
 struct Context {
@@ -640,7 +644,11 @@ void tmac_b200_shutdown(void) {
     cudaStreamSynchronize(g.stream());
     for (auto &kv : g.xchg) if (kv.second) cudaFree(kv.second);
     g.xchg.clear();
-    for (auto &kv : g.res) cudaFree(kv.second.d);
+    for (auto &kv : g.res) {
+        cudaFree(kv.second.d);
+        if (kv.second.reserved) munmap(kv.second.reserved, kv.second.reserved_bytes);
+        std::free(kv.second.host_scales);
+    }
     g.res.clear();
     for (DevBuf *b : {&g.d_b, &g.d_qlut, &g.d_ls, &g.d_lb, &g.d_c, &g.d_part, &g.d_cnt, &g.d_cbits}) { if (b->p) cudaFree(b->p); b->p = nullptr; b->cap = 0; }
     for (PinBuf *b : {&g.h_in, &g.h_out}) { if (b->p) cudaFreeHost(b->p); b->p = nullptr; b->cap = 0; }
@@ -825,6 +833,8 @@ int tmac_b200_free_weights(int64_t handle) {
     if (it == g.res.end()) return fail("bad handle");
     cudaStreamSynchronize(g.stream());
     cudaFree(it->second.d);
+    if (it->second.reserved) munmap(it->second.reserved, it->second.reserved_bytes);
+    std::free(it->second.host_scales);
     g.res.erase(it);
     return 0;
 }
@@ -1237,9 +1247,9 @@ int ggml_tmac_get_type_bits(int type) {  // ggml-tmac.cpp:503-522; ids from ggml
 }
 
 int ggml_tmac_b200_can_mul_mat(int src0_type, int src1_is_f32, int dst_is_f32, const char *src0_name) {
-    // ggml-tmac.cpp:238-248 minus the backend check (weights live in HBM here).  Only the
-    // pre-permuted I1..I4 types are accepted by this build (Q4_0 / TQ repacking: INTEGRATION.md).
-    const bool supported = src0_type >= 36 && src0_type <= 39;
+    // ggml-tmac.cpp:72-96,238-248 minus the backend check (weights live in HBM here): the pre-permuted I1..I4 types and
+    // the block types the reference re-permutes at load time (Q4_0, TQ1_0, TQ2_0).
+    const bool supported = (src0_type >= 36 && src0_type <= 39) || ggml_block_elems(src0_type) > 0;
     if (!supported || !src1_is_f32 || !dst_is_f32) return 0;
     if (src0_name && (!strcmp(src0_name, "token_embd.weight") || !strcmp(src0_name, "output.weight"))) return 0;
     return 1;
@@ -1277,6 +1287,64 @@ int ggml_tmac_b200_transform_tensor(void *data, int ne00, int ne01, int bits, st
         extra->scales = scales;
     }
     return (int)h;
+}
+
+// ggml-tmac.cpp:290-498 for every type it supports: I1..I4 blobs are aliased in place (above); Q4_0 / TQ1_0 / TQ2_0
+// blocks are decoded element by element like the reference's accessors and encoded into the stream layout.  The
+// reference hands ggml a freshly allocated permuted copy in extra->qweights; here that pointer is only an ADDRESS KEY
+// (ggml.c adds tile offsets to it and passes it back), so a PROT_NONE reservation of the same size stands in for it.
+int ggml_tmac_b200_transform_tensor_typed(void *data, int ggml_type, int ne00, int ne01, struct tmac_tensor_extra_b200 *extra) {
+    const int bits = ggml_tmac_get_type_bits(ggml_type);
+    if (!bits || !data) return fail("transform_tensor: unsupported ggml type " + std::to_string(ggml_type));
+    if (ggml_type >= 36 && ggml_type <= 39) return ggml_tmac_b200_transform_tensor(data, ne00, ne01, bits, extra);
+    tmac_b200_kcfg c;
+    if (tmac_b200_find_kcfg(ne01 * bits, ne00, bits, &c)) return -1;
+    if (c.M != ne01) return fail("transform_tensor: kcfg is for a different M");
+    const int E = ggml_block_elems(ggml_type);
+    if (c.one_scale || c.zero_point || c.group_size != E)
+        return fail("transform_tensor: block type needs a kcfg with group_size = " + std::to_string(E) + ", no zero point, per-group scales");
+    if (validate_cfg(c)) return -1;
+    std::vector<uint8_t> w((size_t)ne01 * ne00);
+    std::vector<float> sc((size_t)ne01 * (ne00 / E));
+    if (!decode_ggml_blocks(ggml_type, data, ne01, ne00, w.data(), sc.data())) return fail("transform_tensor: K is not a multiple of the block size");
+    const size_t abytes = (size_t)ne00 * ne01 * bits / 8;
+    void *key = mmap(nullptr, abytes, PROT_NONE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (key == MAP_FAILED) return fail("transform_tensor: cannot reserve an address range for the tensor");
+    // scales in the reference's run-time order [M/bm][K/gs][bm/bits] (ggml-tmac.cpp:464-489)
+    const int NG = ne00 / E, rows_per_tile = c.bm / bits;
+    float *hs = (float *)std::malloc(sc.size() * sizeof(float));
+    if (!hs) { munmap(key, abytes); return fail("out of host memory"); }
+    for (int r = 0; r < ne01; ++r)
+        for (int gk = 0; gk < NG; ++gk)
+            hs[((size_t)(r / rows_per_tile) * NG + gk) * rows_per_tile + r % rows_per_tile] = sc[(size_t)r * NG + gk];
+    int64_t h;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (ensure_init()) { munmap(key, abytes); std::free(hs); return -1; }
+        PlainWeights P;
+        plain_from_w(w.data(), ne01, ne00, bits, 0, ne01, &P);
+        P.scales = sc;
+        h = register_resident(c, P, key, abytes, 0);
+        if (h < 0) { munmap(key, abytes); std::free(hs); return -1; }
+        Resident &R = g.res[h];
+        R.reserved = key; R.reserved_bytes = abytes; R.host_scales = hs;
+    }
+    if (extra) {
+        extra->lut_scales_size = ne00 / c.act_group_size;
+        extra->scales_size = ne01 * NG;
+        extra->n_tile_num = c.M * c.bits / c.bm;
+        extra->qweights = (uint8_t *)key;
+        extra->scales = hs;
+    }
+    return (int)h;
+}
+
+// Host-only (no GPU): the decode step of the typed transform, for the CPU suite.  w [ne01][ne00] codes, scales
+// [ne01][ne00 / block elems].  Returns the block size or -1.
+int tmac_b200_debug_decode_ggml(int ggml_type, const void *data, int ne00, int ne01, uint8_t *w, float *scales) {
+    if (!data || !w || !scales) return fail("debug_decode_ggml: null argument");
+    if (!decode_ggml_blocks(ggml_type, data, ne01, ne00, w, scales)) return fail("debug_decode_ggml: unsupported type or K");
+    return ggml_block_elems(ggml_type);
 }
 
 }  // extern "C"

@@ -160,6 +160,56 @@ inline void plain_from_w(const uint8_t *w, int Mout, int K, int bits, int row0, 
     (void)Mout;
 }
 
+// ---- ggml block formats -> weight codes + per-block scales ---------------------------------------------
+// The reference re-permutes Q4_0 / TQ1_0 / TQ2_0 tensors at load time by reading them element by element through
+// "accessors" (3rdparty/llama.cpp/ggml/src/ggml-tmac.cpp:98-236, block structs ggml-common.h:145-148, :234-247):
+// get_q(idx) -> code w in [0, 2^bits) with real value (w - 2^(bits-1)) * d, get_scale -> the block's fp16 d.
+//   Q4_0  (type 2,  32 elems, 18 B: d | qs[16]):          w = nibble (low: elems 0-15, high: 16-31)
+//   TQ1_0 (type 34, 256 elems, 54 B: qs[48] | qh[4] | d): base-3 digits, 5 per byte (4 in qh), w = trit + 1
+//   TQ2_0 (type 35, 256 elems, 66 B: qs[64] | d):         2 bits per element, w = q + 1
+enum { kGgmlQ4_0 = 2, kGgmlTQ1_0 = 34, kGgmlTQ2_0 = 35 };
+inline int ggml_block_elems(int type) { return type == kGgmlQ4_0 ? 32 : (type == kGgmlTQ1_0 || type == kGgmlTQ2_0) ? 256 : 0; }
+inline size_t ggml_block_bytes(int type) { return type == kGgmlQ4_0 ? 18 : type == kGgmlTQ1_0 ? 54 : type == kGgmlTQ2_0 ? 66 : 0; }
+inline int ggml_block_bits(int type) { return type == kGgmlQ4_0 ? 4 : (type == kGgmlTQ1_0 || type == kGgmlTQ2_0) ? 2 : 0; }
+
+inline uint8_t ggml_block_q(int type, const uint8_t *blk, int i) {
+    if (type == kGgmlQ4_0) {                       // BlockQ40TypeAccessor::get_q, ggml-tmac.cpp:106-112
+        const uint8_t *qs = blk + 2;
+        return (uint8_t)((qs[i % 16] >> (i / 16 * 4)) & 15);
+    }
+    if (type == kGgmlTQ2_0) {                      // BlockTQ20TypeAccessor::get_q, :215-221
+        const uint8_t *sq = blk + (i / 128) * 32;
+        const int si = i % 128;
+        return (uint8_t)(((sq[si % 32] >> (si / 32 * 2)) & 3) + 1);
+    }
+    // BlockTQ10TypeAccessor::get_q, :158-196: qs[0:32] 5 trits per byte, qs[32:48] 5 per byte, qh[0:4] 4 per byte
+    static const uint8_t pow3[5] = {1, 3, 9, 27, 81};
+    int byte, trit;
+    if (i < 160) { byte = i % 32; trit = i / 32; }
+    else if (i < 240) { byte = 32 + (i - 160) % 16; trit = (i - 160) / 16; }
+    else { byte = 48 + (i - 240) % 4; trit = (i - 240) / 4; }
+    const uint8_t cur = (uint8_t)(blk[byte] * pow3[trit]);
+    return (uint8_t)((((uint16_t)cur * 3) >> 8) + 1);
+}
+inline float ggml_block_scale(int type, const uint8_t *blk) {
+    const uint8_t *d = (type == kGgmlQ4_0) ? blk : (type == kGgmlTQ1_0 ? blk + 52 : blk + 64);
+    return f16_bits_to_f32((uint16_t)(d[0] | (d[1] << 8)));
+}
+// data: [Mout][K / elems] blocks, row major (K % elems == 0).  w: [Mout][K] codes, scales: [Mout][K / elems].
+inline bool decode_ggml_blocks(int type, const void *data, int Mout, int K, uint8_t *w, float *scales) {
+    const int E = ggml_block_elems(type);
+    const size_t B = ggml_block_bytes(type);
+    if (!E || K % E) return false;
+    const uint8_t *p = (const uint8_t *)data;
+    for (int r = 0; r < Mout; ++r)
+        for (int kb = 0; kb < K / E; ++kb) {
+            const uint8_t *blk = p + ((size_t)r * (K / E) + kb) * B;
+            for (int i = 0; i < E; ++i) w[(size_t)r * K + (size_t)kb * E + i] = ggml_block_q(type, blk, i);
+            scales[(size_t)r * (K / E) + kb] = ggml_block_scale(type, blk);
+        }
+    return true;
+}
+
 // Inverse of the reference permutation (python/t_mac/weights.py:57-73): bit-plane row p of the
 // tensor, K-group kg -> byte / nibble in A [M/bm][K/4][bm/2].
 inline uint8_t ref_layout_idx(const uint8_t *A, int KG, int bm, int kf, int p, int kg) {

@@ -42,6 +42,7 @@ EXPORTS = [
     "ggml_tmac_init", "ggml_tmac_free", "ggml_tmac_mul_mat_task_init", "ggml_tmac_mul_mat_task_compute",
     "ggml_tmac_set_n_threads", "ggml_tmac_get_type_bits", "ggml_tmac_b200_can_mul_mat",
     "ggml_tmac_b200_mul_mat_get_wsize", "ggml_tmac_b200_get_nbytes", "ggml_tmac_b200_transform_tensor",
+    "ggml_tmac_b200_transform_tensor_typed", "tmac_b200_debug_decode_ggml",
 ]
 
 _lib = None
@@ -83,6 +84,8 @@ def load() -> C.CDLL:
         "ggml_tmac_b200_can_mul_mat": (i, [i, i, i, C.c_char_p]),
         "ggml_tmac_b200_mul_mat_get_wsize": (sz, [i, i, i, i]), "ggml_tmac_b200_get_nbytes": (sz, [i, i, i]),
         "ggml_tmac_b200_transform_tensor": (i, [vp, i, i, i, C.POINTER(TensorExtra)]),
+        "ggml_tmac_b200_transform_tensor_typed": (i, [vp, i, i, i, C.POINTER(TensorExtra)]),
+        "tmac_b200_debug_decode_ggml": (i, [i, vp, i, i, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -337,6 +337,49 @@ def test_ggml_hook_transform_tensor_i2_blob(lib, oracle):
         lib.tmac_b200_clear_kcfg()
 
 
+@pytest.mark.parametrize("name,bits,block,ags", [("q4_0", 4, 32, 32), ("tq1_0", 2, 256, 64), ("tq2_0", 2, 256, 64)])
+def test_ggml_block_types_through_the_hook(lib, oracle, golden_dir, name, bits, block, ags):
+    """Q4_0 / TQ1_0 / TQ2_0 tensors (golden block bytes from the reference's gguf-py) go through
+    ggml_tmac_b200_transform_tensor_typed, then ggml's two phases with per-tile calls on extra->qweights + offset
+    (ggml.c:12662-12691); result vs the oracle run on the decoded codes / scales in the reference layout."""
+    z = np.load(os.path.join(golden_dir, "ggml_blocks.npz"))
+    q, deq, qt = np.ascontiguousarray(z[name + "_bytes"]), z[name + "_dequant"], int(z[name + "_type"])
+    rows, K = deq.shape
+    cfg = T.Config(rows, K, bits, kfactor=min(16, block // 4), group_size=block, act_group_size=ags).resolved()
+    k = kc(cfg)
+    tb.check(lib.tmac_b200_register_kcfg(C.byref(k)), "register")
+    assert lib.ggml_tmac_b200_can_mul_mat(qt, 1, 1, b"blk.0.attn_q.weight") == 1
+    extra = tb.TensorExtra()
+    h = lib.ggml_tmac_b200_transform_tensor_typed(q.ctypes.data, qt, K, rows, C.byref(extra))
+    tb.check(h, "transform_tensor_typed")
+    try:
+        w = np.zeros((rows, K), np.uint8); sc = np.zeros((rows, K // block), np.float32)
+        assert lib.tmac_b200_debug_decode_ggml(qt, q.ctypes.data, K, rows, w.ctypes.data, sc.ctypes.data) == block
+        A, S = T.pack_reference_layout(w, sc, None, cfg)
+        assert extra.n_tile_num == cfg.n_tile_num and extra.scales_size == S.size
+        got_scales = np.ctypeslib.as_array((C.c_float * S.size).from_address(extra.scales))
+        assert np.array_equal(got_scales, S.reshape(-1)), "extra->scales must be in the reference's run-time order"
+        x = np.random.default_rng(5).standard_normal((1, K)).astype(np.float16).astype(np.float32)
+        nag = K // ags
+        ql = np.zeros((1, K // 4, 16), np.int8); ls = np.zeros((1, nag), np.float32); lb = np.zeros_like(ls)
+        lib.ggml_tmac_mul_mat_task_init(x.ctypes.data, ql.ctypes.data, ls.ctypes.data, lb.ctypes.data, rows, K, 1, bits)
+        out = np.zeros((1, rows), np.float32)
+        n_tile = cfg.n_tile_num; chunk0 = rows // n_tile
+        w_chunk = A.size // n_tile; s_chunk = S.size // n_tile
+        base, sbase = extra.qweights, extra.scales
+        for t in range(n_tile):
+            lib.ggml_tmac_mul_mat_task_compute(base + t * w_chunk, sbase + 4 * t * s_chunk, ql.ctypes.data, ls.ctypes.data, lb.ctypes.data,
+                                               out.ctypes.data + 4 * t * chunk0, chunk0, K, 1, bits)
+        qo, lso, lbo = oracle.preprocessor(x, ags)
+        assert np.array_equal(ql, qo)
+        Co = oracle.qgemm(cfg, A, S, qo, lso, lbo)
+        assert np.abs(out - Co).max() <= TIGHT_TOL * np.abs(Co).max()
+        dense = x @ deq.T                                        # the reference's dequantised weights
+        assert T.nmse(dense, out) <= 5e-4
+    finally:
+        lib.tmac_b200_free_weights(h)
+
+
 def test_fused_gemv_fp16_and_plain_upload(lib, oracle):
     """tmac_b200_gemv (init+compute in one call) with fp16 activations/outputs (the ARM `T`), weights
     uploaded from un-permuted quantised values."""

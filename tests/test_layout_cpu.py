@@ -148,3 +148,28 @@ def test_no_cpu_fallback_without_gpu():
     x = np.zeros((1, 128), np.float32)
     ls = np.zeros(2, np.float32); lb = np.zeros(2, np.float32); q = np.zeros((32, 16), np.int8)
     assert lib.tmac_b200_preprocessor(128, 1, 64, 0, x.ctypes.data, ls.ctypes.data, lb.ctypes.data, q.ctypes.data) == -1
+
+
+GGML_GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "ggml_blocks.npz")
+
+
+@pytest.mark.parametrize("name,bits,block", [("q4_0", 4, 32), ("tq1_0", 2, 256), ("tq2_0", 2, 256)])
+def test_ggml_block_decode_matches_reference_dequant(name, bits, block):
+    """Q4_0 / TQ1_0 / TQ2_0 blocks (golden bytes + dequantised values produced by the reference's own gguf-py,
+    oracle/make_golden_ggml.py) decode to codes w and scales d with (w - 2^(bits-1)) * d == dequant exactly: the
+    semantics of the reference's accessors (ggml-tmac.cpp:98-236) + its dequant convention (tests/test_e2e.py:69-77)."""
+    z = np.load(GGML_GOLDEN)
+    q, deq, qt = z[name + "_bytes"], z[name + "_dequant"], int(z[name + "_type"])
+    rows, K = deq.shape
+    lib = tb.load()
+    w = np.zeros((rows, K), np.uint8); sc = np.zeros((rows, K // block), np.float32)
+    q = np.ascontiguousarray(q)
+    assert lib.tmac_b200_debug_decode_ggml(qt, q.ctypes.data, K, rows, w.ctypes.data, sc.ctypes.data) == block
+    assert lib.ggml_tmac_get_type_bits(qt) == bits
+    assert w.max() < (1 << bits)
+    if bits == 2:
+        assert w.min() >= 1            # ternary: codes 1, 2, 3 <-> -1, 0, +1
+    real = (w.astype(np.float32) - float(1 << (bits - 1))) * np.repeat(sc, block, axis=1)
+    assert np.array_equal(real, deq)
+    # K that is not a multiple of the block size is rejected
+    assert lib.tmac_b200_debug_decode_ggml(qt, q.ctypes.data, K - 32 if block == 256 else K - 16, rows, w.ctypes.data, sc.ctypes.data) == -1
