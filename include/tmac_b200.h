@@ -108,6 +108,15 @@ TMAC_B200_API int64_t tmac_b200_upload_weights(const tmac_b200_kcfg *cfg, const 
  * [M][K/group_size] (zeros already in the (z - 2^(bits-1))*s convention, weights.py:28-30). */
 TMAC_B200_API int64_t tmac_b200_upload_plain(const tmac_b200_kcfg *cfg, const uint8_t *w,
                                              const float *scales, const float *zeros);
+/* GPTQ checkpoint tensors as stored in safetensors (qweight int32 [K*bits/32][M], scales fp16 [K/gs][M], qzeros int32
+ * [K/gs][M*bits/32]) -> resident weights: unpack_gptqv2 + preprocess_weights of the reference's converter
+ * (python/t_mac/model_utils.py:95-129, :262-271; convert_hf_to_gguf.py:300-320) in one call.  cfg: M, K, bits (1, 2 or 4),
+ * group_size, bm, kfactor, act_group_size; zero points are implied.  gptq_v2 = 1 for GPTQModel, 0 for AutoGPTQ (zeros + 1). */
+TMAC_B200_API int64_t tmac_b200_upload_gptq(const tmac_b200_kcfg *cfg, const int32_t *qweight, const uint16_t *scales_f16,
+                                            const int32_t *qzeros, int gptq_v2);
+/* Host-only: the unpack alone (w [M][K], scales / zeros [M][K/group_size]); 0 or -1. */
+TMAC_B200_API int tmac_b200_debug_unpack_gptq(const int32_t *qweight, const uint16_t *scales_f16, const int32_t *qzeros, int K, int M,
+                                              int bits, int group_size, int gptq_v2, uint8_t *w, float *scales, float *zeros);
 /* Host-only layout transform (no GPU needed): writes the stream layout of tmac_b200_upload_weights
  * into dst (dst == NULL: size query); layout_out[12] = {pb, rows/lane, rows/super-block,
  * #super-blocks, K/chunk, quads/chunk, #chunks, scale bytes, zp, one_scale, block bytes, weight bytes}. */

@@ -797,6 +797,30 @@ int64_t tmac_b200_upload_plain(const tmac_b200_kcfg *cfg, const uint8_t *w, cons
     return tmac_b200_upload_plain_rows(cfg, w, scales, zeros, 0, cfg->M);
 }
 
+// GPTQ checkpoint tensors (safetensors: qweight, scales, qzeros) -> resident weights, the C form of
+// unpack_gptqv2 + preprocess_weights + upload (model_utils.py:95-129, :262-271; convert_hf_to_gguf.py:300-320).
+// cfg gives M, K, bits, group_size, bm, kfactor, act_group_size; zero_point is implied.
+int64_t tmac_b200_upload_gptq(const tmac_b200_kcfg *cfg_in, const int32_t *qweight, const uint16_t *scales_f16, const int32_t *qzeros,
+                              int gptq_v2) {
+    if (!cfg_in || !qweight || !scales_f16 || !qzeros) return fail("upload_gptq: null argument");
+    tmac_b200_kcfg cfg = *cfg_in;
+    cfg.zero_point = 1; cfg.one_scale = 0;
+    if (cfg.group_size <= 0 || cfg.K % cfg.group_size) return fail("upload_gptq: bad group_size");
+    const size_t NG = (size_t)cfg.K / cfg.group_size;
+    std::vector<uint8_t> w((size_t)cfg.M * cfg.K);
+    std::vector<float> sc((size_t)cfg.M * NG), zr((size_t)cfg.M * NG);
+    if (!unpack_gptq(qweight, scales_f16, qzeros, cfg.K, cfg.M, cfg.bits, cfg.group_size, gptq_v2 != 0, w.data(), sc.data(), zr.data()))
+        return fail("upload_gptq: unsupported packing (bits must divide 32; K, M multiples of 32/bits)");
+    return tmac_b200_upload_plain(&cfg, w.data(), sc.data(), zr.data());
+}
+// Host-only: the unpack step alone (CPU suite).  w [M][K], scales / zeros [M][K/group_size].
+int tmac_b200_debug_unpack_gptq(const int32_t *qweight, const uint16_t *scales_f16, const int32_t *qzeros, int K, int M, int bits,
+                                int group_size, int gptq_v2, uint8_t *w, float *scales, float *zeros) {
+    if (!qweight || !scales_f16 || !qzeros || !w || !scales || !zeros) return fail("debug_unpack_gptq: null argument");
+    if (!unpack_gptq(qweight, scales_f16, qzeros, K, M, bits, group_size, gptq_v2 != 0, w, scales, zeros)) return fail("debug_unpack_gptq: unsupported packing");
+    return 0;
+}
+
 // Host-only: run the reference-layout -> stream-layout transform without touching the GPU and
 // return the stream bytes (used by the CPU test-suite to pin the layout).  dst may be NULL to
 // query the size.  Returns the byte count or -1.

@@ -210,6 +210,32 @@ inline bool decode_ggml_blocks(int type, const void *data, int Mout, int K, uint
     return true;
 }
 
+// ---- GPTQ safetensors tensors -> codes + scales + biased zeros -------------------------------------------------------
+// Restates unpack_gptqv2 (python/t_mac/model_utils.py:95-129), the converter's entry for GPTQ checkpoints
+// (convert_hf_to_gguf.py:305-306): qweight int32 [K*bits/32][M] packs 32/bits consecutive K positions per word (LSB first),
+// qzeros int32 [K/gs][M*bits/32] packs 32/bits consecutive output rows per word, scales fp16 [K/gs][M].
+// Out: w [M][K] in [0, 2^bits), scales [M][K/gs], zeros [M][K/gs] = (z (+1 for AutoGPTQ v1) - 2^(bits-1)) * scale, the product
+// rounded to fp16 like numpy's float16 multiply (:124-127).  bits must divide 32 (1, 2, 4).
+inline bool unpack_gptq(const int32_t *qweight, const uint16_t *scales_f16, const int32_t *qzeros, int K, int M, int bits,
+                        int group_size, bool gptq_v2, uint8_t *w, float *scales, float *zeros) {
+    if (bits < 1 || 32 % bits || K <= 0 || M <= 0 || group_size <= 0 || K % group_size || K % (32 / bits) || M % (32 / bits)) return false;
+    const int p = 32 / bits, NG = K / group_size;
+    const uint32_t mask = (1u << bits) - 1u;
+    for (int k = 0; k < K; ++k)
+        for (int m = 0; m < M; ++m)
+            w[(size_t)m * K + k] = (uint8_t)(((uint32_t)qweight[(size_t)(k / p) * M + m] >> (bits * (k % p))) & mask);
+    for (int gk = 0; gk < NG; ++gk)
+        for (int m = 0; m < M; ++m) {
+            const float sc = f16_bits_to_f32(scales_f16[(size_t)gk * M + m]);
+            int z = (int)(((uint32_t)qzeros[(size_t)gk * (M / p) + m / p] >> (bits * (m % p))) & mask);
+            if (!gptq_v2) z += 1;
+            const float prod = (float)(z - (1 << (bits - 1))) * sc;       // exact in fp32 (small int x 11-bit mantissa)
+            scales[(size_t)m * NG + gk] = sc;
+            zeros[(size_t)m * NG + gk] = f16_bits_to_f32(f32_to_f16_bits(prod));
+        }
+    return true;
+}
+
 // Inverse of the reference permutation (python/t_mac/weights.py:57-73): bit-plane row p of the
 // tensor, K-group kg -> byte / nibble in A [M/bm][K/4][bm/2].
 inline uint8_t ref_layout_idx(const uint8_t *A, int KG, int bm, int kf, int p, int kg) {

@@ -42,7 +42,7 @@ EXPORTS = [
     "ggml_tmac_init", "ggml_tmac_free", "ggml_tmac_mul_mat_task_init", "ggml_tmac_mul_mat_task_compute",
     "ggml_tmac_set_n_threads", "ggml_tmac_get_type_bits", "ggml_tmac_b200_can_mul_mat",
     "ggml_tmac_b200_mul_mat_get_wsize", "ggml_tmac_b200_get_nbytes", "ggml_tmac_b200_transform_tensor",
-    "ggml_tmac_b200_transform_tensor_typed", "tmac_b200_debug_decode_ggml",
+    "ggml_tmac_b200_transform_tensor_typed", "tmac_b200_debug_decode_ggml", "tmac_b200_upload_gptq", "tmac_b200_debug_unpack_gptq",
 ]
 
 _lib = None
@@ -86,6 +86,8 @@ def load() -> C.CDLL:
         "ggml_tmac_b200_transform_tensor": (i, [vp, i, i, i, C.POINTER(TensorExtra)]),
         "ggml_tmac_b200_transform_tensor_typed": (i, [vp, i, i, i, C.POINTER(TensorExtra)]),
         "tmac_b200_debug_decode_ggml": (i, [i, vp, i, i, vp, vp]),
+        "tmac_b200_upload_gptq": (i64, [C.POINTER(KCfg), vp, vp, vp, i]),
+        "tmac_b200_debug_unpack_gptq": (i, [vp, vp, vp, i, i, i, i, i, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -380,6 +380,31 @@ def test_ggml_block_types_through_the_hook(lib, oracle, golden_dir, name, bits, 
         lib.tmac_b200_free_weights(h)
 
 
+def test_gptq_checkpoint_tensors_to_gemv(lib, oracle, golden_dir):
+    """qweight / scales / qzeros as a GPTQ checkpoint stores them -> tmac_b200_upload_gptq -> GEMV, against the oracle run on
+    the reference's own unpack (golden) packed by the reference layout rule."""
+    z = np.load(os.path.join(golden_dir, "gptq_unpack.npz"))
+    for tag in ("w4_v2", "w2_v1"):
+        bits, K, M, gs, v2 = [int(v) for v in z[tag + "_meta"]]
+        cfg = T.Config(M, K, bits, group_size=gs, act_group_size=min(64, gs), zero_point=True).resolved()
+        qw, qz, sc = (np.ascontiguousarray(z[tag + k]) for k in ("_qweight", "_qzeros", "_scales"))
+        k = kc(cfg)
+        h = lib.tmac_b200_upload_gptq(C.byref(k), qw.ctypes.data, sc.ctypes.data, qz.ctypes.data, v2)
+        tb.check(h, "upload_gptq")
+        try:
+            w, s, zr = z[tag + "_w"], z[tag + "_s"].astype(np.float32), z[tag + "_z"].astype(np.float32)
+            A, S = T.pack_reference_layout(w, s, zr, cfg)
+            x = np.random.default_rng(8).standard_normal((1, K)).astype(np.float16).astype(np.float32)
+            out = np.zeros((1, M), np.float32)
+            tb.check(lib.tmac_b200_gemv(h, 1, tb.F32, x.ctypes.data, out.ctypes.data), "gemv")
+            qo, lso, lbo = oracle.preprocessor(x, cfg.act_group_size)
+            Co = oracle.qgemm(cfg, A, S, qo, lso, lbo)
+            assert np.abs(out - Co).max() <= TIGHT_TOL * np.abs(Co).max(), tag
+            assert T.nmse(T.dense_reference(w, s, zr, x, cfg), out) <= 5e-4
+        finally:
+            lib.tmac_b200_free_weights(h)
+
+
 def test_fused_gemv_fp16_and_plain_upload(lib, oracle):
     """tmac_b200_gemv (init+compute in one call) with fp16 activations/outputs (the ARM `T`), weights
     uploaded from un-permuted quantised values."""

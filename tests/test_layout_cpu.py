@@ -173,3 +173,40 @@ def test_ggml_block_decode_matches_reference_dequant(name, bits, block):
     assert np.array_equal(real, deq)
     # K that is not a multiple of the block size is rejected
     assert lib.tmac_b200_debug_decode_ggml(qt, q.ctypes.data, K - 32 if block == 256 else K - 16, rows, w.ctypes.data, sc.ctypes.data) == -1
+
+
+@pytest.mark.parametrize("tag", ["w4_v2", "w2_v1", "w4_v1"])
+def test_gptq_unpack_matches_reference(tag):
+    """GPTQ safetensors tensors -> (w, scales, biased zeros): bit-identical to the reference's unpack_gptqv2
+    (python/t_mac/model_utils.py:95-129; goldens by oracle/make_golden_gptq.py), including the fp16 rounding of
+    (z - 2^(bits-1)) * scale and AutoGPTQ's zero + 1."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "gptq_unpack.npz"))
+    bits, K, M, gs, v2 = [int(v) for v in z[tag + "_meta"]]
+    qw, qz, sc = (np.ascontiguousarray(z[tag + k]) for k in ("_qweight", "_qzeros", "_scales"))
+    w = np.zeros((M, K), np.uint8); s = np.zeros((M, K // gs), np.float32); zr = np.zeros_like(s)
+    lib = tb.load()
+    assert lib.tmac_b200_debug_unpack_gptq(qw.ctypes.data, sc.ctypes.data, qz.ctypes.data, K, M, bits, gs, v2, w.ctypes.data, s.ctypes.data, zr.ctypes.data) == 0
+    assert np.array_equal(w, z[tag + "_w"])
+    assert np.array_equal(s, z[tag + "_s"].astype(np.float32))
+    assert np.array_equal(zr.view(np.uint32), z[tag + "_z"].astype(np.float32).view(np.uint32))
+    assert lib.tmac_b200_debug_unpack_gptq(qw.ctypes.data, sc.ctypes.data, qz.ctypes.data, K, M, 3, gs, v2, w.ctypes.data, s.ctypes.data, zr.ctypes.data) == -1
+
+
+def test_shipped_kcfg_presets_load():
+    """deploy/tuned/<preset>/kcfg.ini (tools/make_kcfg.py, reference format) load through the reference-format reader and
+    resolve every shape of the preset with the grouping the preset means."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_kcfg", os.path.join(ROOT, "tools", "make_kcfg.py"))
+    mk = importlib.util.module_from_spec(spec); spec.loader.exec_module(mk)
+    lib = tb.load()
+    for preset, (bits, gs, ags, zp, one, shapes) in mk.PRESETS.items():
+        lib.tmac_b200_clear_kcfg()
+        path = os.path.join(ROOT, "deploy", "tuned", preset, "kcfg.ini")
+        assert lib.tmac_b200_load_kcfg_file(path.encode()) == len(shapes), preset
+        for mout, k in shapes:
+            c = tb.KCfg()
+            assert lib.tmac_b200_find_kcfg(mout * bits, k, bits, C.byref(c)) == 0, (preset, mout, k)
+            assert (c.M, c.K, c.bits, c.group_size if not one else gs, c.one_scale, c.zero_point) == (mout, k, bits, gs, int(one), int(zp)), (preset, mout, k)
+            assert c.act_group_size == (k if ags <= 0 else ags)
+            assert (mout * bits) % c.bm == 0
+    lib.tmac_b200_clear_kcfg()
