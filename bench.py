@@ -208,8 +208,12 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback in the product path)")
     torch.cuda.set_device(local)
     dist = None
-    if world > 1:
+    force_sharded = os.environ.get("TMAC_BENCH_FORCE_SHARDED", "0") == "1"      # validate the N > 1 extras on one rank
+    if world > 1 or force_sharded:
         import torch.distributed as dist
+        if world == 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29577")
+            os.environ.setdefault("RANK", "0"); os.environ.setdefault("WORLD_SIZE", "1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = tb.load()
     tb.check(lib.tmac_b200_init(local), "init")
@@ -376,7 +380,29 @@ def main():
 
     extras = {}
     cpu = None
-    if rank == 0 and not args.no_extras:
+    def headline(extras_, cpu_):
+        return {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int8 LUT / int32 dp4a / fp32 scale", "data": "synthetic", "config": workload_config(world),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches["n"], "roofline": roofline,
+                "cpu_baseline": cpu_, "tokens_per_s": extras_}
+
+    if (world > 1 or force_sharded) and not args.no_extras:   # all ranks: the model's linears row-sharded over the ranks
+        # The extras use collectives on every rank; a watchdog bounds them so that a stuck collective can never cost the
+        # headline line: on expiry rank 0 prints the line without the extras and every rank exits.
+        def expire():
+            if rank == 0:
+                print(json.dumps(headline({"error": "sharded tokens/s extras exceeded their time limit"}, None)), flush=True)
+            os._exit(0)
+        dog = threading.Timer(float(os.environ.get("TMAC_BENCH_EXTRAS_LIMIT_S", "420")), expire)
+        dog.daemon = True
+        dog.start()
+        try:
+            extras = tokens_per_second_sharded(tb, lib, torch, dist, stream, rank, world)
+        except Exception as ex:
+            extras = {"error": str(ex)[:200]}
+        dog.cancel()
+    elif rank == 0 and not args.no_extras:
         try:
             extras = tokens_per_second(tb, lib, torch, stream)
         except Exception as ex:  # extras must never kill the headline line
@@ -385,14 +411,133 @@ def main():
             cpu = cpu_arm(12.0)
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "int8 LUT / int32 dp4a / fp32 scale", "data": "synthetic", "config": workload_config(world),
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches["n"], "roofline": roofline,
-                "cpu_baseline": cpu, "tokens_per_s": extras}
-        print(json.dumps(line))
-    if world > 1:
+        print(json.dumps(headline(extras, cpu)), flush=True)
+    if dist is not None:
         dist.destroy_process_group()
+
+
+def tokens_per_second_sharded(tb, lib, torch, dist, stream, rank, world):
+    """Matmul-only decode tokens/s with every quantised linear ROW-SHARDED over the ranks (whole reference
+    tiles per rank, remainders spread; every rank runs its own preprocessor) and one NCCL all-gather per fused group
+    (q/k/v, o, gate/up, down = 4 per layer), the token step captured in one CUDA graph when NCCL capture works, else
+    eager launches (stated).  Strong scaling: the model is fixed, per-rank weights = 1/world.  Runs on ALL ranks."""
+    sys.path.insert(0, os.path.join(ROOT, "t-mac_b200"))
+    from shard import row_partition
+    models = {
+        "llama2_7b_w2_g128_zp": dict(L=32, bits=2, zp=True, os=False, shapes=[("qkv", 4096, 4096, 3), ("o", 4096, 4096, 1), ("gateup", 11008, 4096, 2), ("down", 4096, 11008, 1)]),
+        "bitnet_3b_w2": dict(L=26, bits=2, zp=False, os=True, shapes=[("qkv", 3200, 3200, 3), ("o", 3200, 3200, 1), ("gateup", 8640, 3200, 2), ("down", 3200, 8640, 1)]),
+        "qwen2_7b_w4_g128_zp": dict(L=28, bits=4, zp=True, os=False, shapes=[("q", 3584, 3584, 1), ("kv", 512, 3584, 2), ("o", 3584, 3584, 1), ("gateup", 18944, 3584, 2), ("down", 3584, 18944, 1)]),
+    }
+
+    def all_ok(ok):
+        t = torch.tensor([1 if ok else 0], device="cuda", dtype=torch.int32)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    res = {}
+    for name, m in models.items():
+        handles, plan, local_bytes, err = [], [], 0, None
+        try:
+            for (tag, mout, k, cnt) in m["shapes"]:
+                bits = m["bits"]
+                bm = next(b for b in ((192, 384, 576, 768) if bits == 3 else (256, 128, 512, 1024, 320, 640)) if (mout * bits) % b == 0)
+                tile_rows = bm // bits
+                parts = row_partition(mout, tile_rows, world)
+                row0, rows = parts[rank]
+                mx = max(r for _, r in parts)
+                ags = k if m["os"] else 64
+                with torch.cuda.stream(stream):
+                    xb = torch.randn((1, k), device="cuda")
+                    q = torch.zeros((1, k // 4, 16), dtype=torch.int8, device="cuda")
+                    l1 = torch.zeros((1, k // ags), device="cuda"); l2 = torch.zeros_like(l1)
+                    o = torch.zeros((cnt, mx), device="cuda")
+                    gathered = torch.zeros((world, cnt, mx), device="cuda")
+                hs = []
+                if rows > 0:
+                    w, sc, z = synth(7, mout, k, bits, 128, m["zp"], m["os"])
+                    cfg = tb.make_kcfg(rows, k, bits, bm, 16, 128, ags, m["zp"], m["os"])
+                    ng = k // 128
+                    base = tb.upload_plain(cfg, np.ascontiguousarray(w[row0:row0 + rows]), sc if m["os"] else np.ascontiguousarray(sc[row0:row0 + rows]),
+                                           None if z is None else np.ascontiguousarray(z[row0:row0 + rows]))
+                    hs = [base] + [tb.clone(base) for _ in range(m["L"] * cnt - 1)]
+                    handles += hs
+                    local_bytes += m["L"] * cnt * base.nbytes
+                plan.append((hs, cnt, k, ags, xb, q, l1, l2, o, gathered, rows))
+        except Exception as ex:
+            err = str(ex)[:160]
+        if not all_ok(err is None):
+            res[name] = {"error": err or "another rank failed to build its shard"}
+            for h in handles:
+                h.free()
+            continue
+
+        def token():
+            for layer in range(m["L"]):
+                for (hs, cnt, k, ags, xb, q, l1, l2, o, gathered, rows) in plan:
+                    if rows > 0:
+                        if cnt == 1 and not m["os"]:
+                            tb.gemv(hs[layer], 1, xb, o[0, :rows])
+                        else:
+                            tb.preprocessor(k, 1, ags, xb, l1, l2, q)
+                            if cnt == 1:
+                                tb.qgemm_lut(hs[layer], 1, q, l1, l2, o[0, :rows])
+                            else:
+                                tb.qgemm_lut_grouped(hs[layer * cnt:(layer + 1) * cnt], 1, [q] * cnt, [l1] * cnt, [l2] * cnt,
+                                                     [o[c, :rows] for c in range(cnt)])
+                    dist.all_gather_into_tensor(gathered.view(-1), o.view(-1))      # the group's output vector on every rank
+
+        graph, mode = None, "eager launches (NCCL capture failed)"
+        try:
+            with torch.cuda.stream(stream):
+                token()
+            torch.cuda.synchronize()
+            eager_ok = True
+        except Exception as ex:
+            eager_ok, err = False, str(ex)[:160]
+        if not all_ok(eager_ok):
+            res[name] = {"error": err or "another rank failed"}
+            for h in handles:
+                h.free()
+            continue
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=stream):
+                token()
+            cap_ok = True
+        except Exception:
+            cap_ok = False
+            try:
+                torch.cuda.synchronize()
+            except Exception:
+                pass
+        if all_ok(cap_ok):
+            mode = "one CUDA graph per token (library launches + NCCL all-gathers)"
+            run = graph.replay
+        else:
+            graph = None
+            run = token
+        n = 10
+        with torch.cuda.stream(stream):
+            for _ in range(2):
+                run()
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(n):
+                run()
+            e1.record(stream)
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / n * 1e-3], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
+        tot = torch.tensor([float(local_bytes)], device="cuda"); dist.all_reduce(tot)
+        res[name] = {"tokens_per_s_matmul_only": 1.0 / sec, "ms_per_token": sec * 1e3, "ranks": world, "collectives_per_token": m["L"] * len(plan),
+                     "resident_weight_GB_total": float(tot.item()) / 1e9, "weight_stream_GBps_total": float(tot.item()) / sec / 1e9, "step": mode}
+        del graph
+        for h in handles:
+            h.free()
+    return res
 
 
 def tokens_per_second(tb, lib, torch, stream):
