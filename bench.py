@@ -394,7 +394,7 @@ def main():
             if rank == 0:
                 print(json.dumps(headline({"error": "sharded tokens/s extras exceeded their time limit"}, None)), flush=True)
             os._exit(0)
-        dog = threading.Timer(float(os.environ.get("TMAC_BENCH_EXTRAS_LIMIT_S", "420")), expire)
+        dog = threading.Timer(float(os.environ.get("TMAC_BENCH_EXTRAS_LIMIT_S", "300")), expire)
         dog.daemon = True
         dog.start()
         try:

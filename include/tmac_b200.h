@@ -207,6 +207,28 @@ TMAC_B200_API int ggml_tmac_b200_transform_tensor_typed(void *data, int ggml_typ
 /* Host-only: the block decode alone (codes [ne01][ne00], scales [ne01][ne00 / block]); returns the block size. */
 TMAC_B200_API int tmac_b200_debug_decode_ggml(int ggml_type, const void *data, int ne00, int ne01, uint8_t *w, float *scales);
 
+/* ---- GGUF files: what the reference pipeline produces (convert_hf_to_gguf.py:536-588; tensor blob python/t_mac/
+ * model_utils.py:271) read without llama.cpp: metadata, tensor directory, tensor data mapped read-only. ---------------- */
+struct tmac_b200_gguf_tensor {
+    char name[128];
+    int ggml_type;         /* ggml.h enum: 0 F32, 1 F16, 2 Q4_0, 34 TQ1_0, 35 TQ2_0, 36..39 I1..I4, ... */
+    int n_dims;
+    int64_t ne[4];         /* ne[0] = innermost (K for a weight matrix), ne[1] = rows */
+    uint64_t offset;       /* from the start of the data section */
+    uint64_t nbytes;       /* bytes available up to the next tensor (I-type tensors carry their scales behind the weights) */
+    const void *data;      /* mapped, valid until tmac_b200_gguf_close */
+};
+TMAC_B200_API int64_t tmac_b200_gguf_open(const char *path);                       /* handle > 0 or -1 */
+TMAC_B200_API int tmac_b200_gguf_close(int64_t gguf);
+TMAC_B200_API int tmac_b200_gguf_tensor_count(int64_t gguf);
+TMAC_B200_API int tmac_b200_gguf_tensor_info(int64_t gguf, int index, struct tmac_b200_gguf_tensor *out);
+TMAC_B200_API int tmac_b200_gguf_find_tensor(int64_t gguf, const char *name);     /* index or -1 */
+TMAC_B200_API int tmac_b200_gguf_meta_number(int64_t gguf, const char *key, double *out);
+TMAC_B200_API int tmac_b200_gguf_meta_string(int64_t gguf, const char *key, char *dst, size_t cap);   /* length or -1 */
+/* One quantised linear (2-D, I1..I4 / Q4_0 / TQ1_0 / TQ2_0) -> resident weights through the typed transform; the kcfg of
+ * the shape must be registered.  Returns the weight handle; extra as for ggml_tmac_b200_transform_tensor_typed. */
+TMAC_B200_API int64_t tmac_b200_gguf_load_tensor(int64_t gguf, int index, struct tmac_tensor_extra_b200 *extra);
+
 #ifdef __cplusplus
 }
 #endif

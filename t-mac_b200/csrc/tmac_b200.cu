@@ -25,6 +25,7 @@
 #include "tmac_prefill.cuh"
 #include "tmac_gemv4.cuh"
 #include "tmac_layout.h"
+#include "tmac_gguf.h"
 
 using namespace tmac_b200;
 
@@ -1369,6 +1370,99 @@ int tmac_b200_debug_decode_ggml(int ggml_type, const void *data, int ne00, int n
     if (!data || !w || !scales) return fail("debug_decode_ggml: null argument");
     if (!decode_ggml_blocks(ggml_type, data, ne01, ne00, w, scales)) return fail("debug_decode_ggml: unsupported type or K");
     return ggml_block_elems(ggml_type);
+}
+
+// ---- GGUF files (tmac_gguf.h) ----------------------------------------------------------------------------------------
+static std::map<int64_t, GgufFile *> g_gguf;
+static int64_t g_next_gguf = 1;
+
+int64_t tmac_b200_gguf_open(const char *path) {
+    if (!path) return fail("gguf_open: null path");
+    GgufFile *f = new GgufFile();
+    if (!f->open(path)) { const std::string e = f->error; delete f; return fail("gguf_open: " + e); }
+    std::lock_guard<std::mutex> lk(g_mu);
+    const int64_t h = g_next_gguf++;
+    g_gguf[h] = f;
+    return h;
+}
+int tmac_b200_gguf_close(int64_t gguf) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_gguf.find(gguf);
+    if (it == g_gguf.end()) return fail("gguf_close: bad handle");
+    delete it->second;           // unmaps the file: weights uploaded from it stay resident, their host alias keys go stale
+    g_gguf.erase(it);
+    return 0;
+}
+static GgufFile *gguf_locked(int64_t gguf) {
+    auto it = g_gguf.find(gguf);
+    return it == g_gguf.end() ? nullptr : it->second;
+}
+int tmac_b200_gguf_tensor_count(int64_t gguf) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    GgufFile *f = gguf_locked(gguf);
+    return f ? (int)f->tensors.size() : fail("gguf: bad handle");
+}
+int tmac_b200_gguf_tensor_info(int64_t gguf, int index, struct tmac_b200_gguf_tensor *out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    GgufFile *f = gguf_locked(gguf);
+    if (!f || !out) return fail("gguf: bad handle / null argument");
+    if (index < 0 || index >= (int)f->tensors.size()) return fail("gguf: tensor index out of range");
+    const GgufTensor &T = f->tensors[index];
+    std::memset(out, 0, sizeof *out);
+    std::strncpy(out->name, T.name.c_str(), sizeof out->name - 1);
+    out->ggml_type = T.type; out->n_dims = T.n_dims;
+    for (int d = 0; d < 4; ++d) out->ne[d] = T.ne[d];
+    out->offset = T.offset; out->nbytes = T.nbytes;
+    out->data = f->data(index);
+    return 0;
+}
+int tmac_b200_gguf_find_tensor(int64_t gguf, const char *name) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    GgufFile *f = gguf_locked(gguf);
+    if (!f || !name) return fail("gguf: bad handle / null argument");
+    const int i = f->find(name);
+    return i >= 0 ? i : fail(std::string("gguf: no tensor named '") + name + "'");
+}
+// Metadata: integers / bools / floats (as double) and strings.  Return 0, or -1 when the key is absent or of another kind.
+int tmac_b200_gguf_meta_number(int64_t gguf, const char *key, double *out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    GgufFile *f = gguf_locked(gguf);
+    if (!f || !key || !out) return fail("gguf: bad handle / null argument");
+    auto it = f->meta.find(key);
+    if (it == f->meta.end() || it->second.type == 8 || it->second.type == 9) return fail(std::string("gguf: no numeric key '") + key + "'");
+    *out = it->second.f;
+    return 0;
+}
+int tmac_b200_gguf_meta_string(int64_t gguf, const char *key, char *dst, size_t cap) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    GgufFile *f = gguf_locked(gguf);
+    if (!f || !key || !dst || !cap) return fail("gguf: bad handle / null argument");
+    auto it = f->meta.find(key);
+    if (it == f->meta.end() || it->second.type != 8) return fail(std::string("gguf: no string key '") + key + "'");
+    std::strncpy(dst, it->second.s.c_str(), cap - 1); dst[cap - 1] = 0;
+    return (int)it->second.s.size();
+}
+// Upload one quantised linear of the file (I1..I4, Q4_0, TQ1_0, TQ2_0; 2-D) through the typed transform; the kcfg for its
+// shape must be registered (tmac_b200_load_kcfg_file).  The mapped file region serves as the host alias of I-type tensors.
+int64_t tmac_b200_gguf_load_tensor(int64_t gguf, int index, struct tmac_tensor_extra_b200 *extra) {
+    const uint8_t *data; int type, ne0, ne1; uint64_t nbytes;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        GgufFile *f = gguf_locked(gguf);
+        if (!f) return fail("gguf: bad handle");
+        if (index < 0 || index >= (int)f->tensors.size()) return fail("gguf: tensor index out of range");
+        const GgufTensor &T = f->tensors[index];
+        if (T.n_dims != 2) return fail("gguf_load_tensor: '" + T.name + "' is not a matrix");
+        data = f->data(index); type = T.type; ne0 = (int)T.ne[0]; ne1 = (int)T.ne[1]; nbytes = T.nbytes;
+    }
+    const int bits = ggml_tmac_get_type_bits(type);
+    if (!bits) return fail("gguf_load_tensor: ggml type " + std::to_string(type) + " is not a T-MAC type");
+    uint64_t need;
+    if (ggml_block_elems(type)) need = (uint64_t)ne1 * (ne0 / ggml_block_elems(type)) * ggml_block_bytes(type);
+    else need = ggml_tmac_b200_get_nbytes(ne0, ne1, bits);
+    if (need == 0) return -1;                      // no kcfg for the shape (message set by the lookup)
+    if (nbytes < need) return fail("gguf_load_tensor: tensor data is shorter than its type and shape require");
+    return ggml_tmac_b200_transform_tensor_typed((void *)data, type, ne0, ne1, extra);
 }
 
 }  // extern "C"

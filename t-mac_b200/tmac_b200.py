@@ -32,6 +32,12 @@ class TensorExtra(C.Structure):
                 ("qweights", C.c_void_p), ("scales", C.c_void_p)]
 
 
+class GgufTensor(C.Structure):
+    """struct tmac_b200_gguf_tensor."""
+    _fields_ = [("name", C.c_char * 128), ("ggml_type", C.c_int), ("n_dims", C.c_int), ("ne", C.c_int64 * 4),
+                ("offset", C.c_uint64), ("nbytes", C.c_uint64), ("data", C.c_void_p)]
+
+
 EXPORTS = [
     "tmac_b200_init", "tmac_b200_shutdown", "tmac_b200_last_error", "tmac_b200_version", "tmac_b200_set_stream",
     "tmac_b200_set_float_type", "tmac_b200_set_lut_mode", "tmac_b200_register_kcfg", "tmac_b200_load_kcfg_file",
@@ -43,6 +49,8 @@ EXPORTS = [
     "ggml_tmac_set_n_threads", "ggml_tmac_get_type_bits", "ggml_tmac_b200_can_mul_mat",
     "ggml_tmac_b200_mul_mat_get_wsize", "ggml_tmac_b200_get_nbytes", "ggml_tmac_b200_transform_tensor",
     "ggml_tmac_b200_transform_tensor_typed", "tmac_b200_debug_decode_ggml", "tmac_b200_upload_gptq", "tmac_b200_debug_unpack_gptq",
+    "tmac_b200_gguf_open", "tmac_b200_gguf_close", "tmac_b200_gguf_tensor_count", "tmac_b200_gguf_tensor_info", "tmac_b200_gguf_find_tensor",
+    "tmac_b200_gguf_meta_number", "tmac_b200_gguf_meta_string", "tmac_b200_gguf_load_tensor",
 ]
 
 _lib = None
@@ -88,6 +96,10 @@ def load() -> C.CDLL:
         "tmac_b200_debug_decode_ggml": (i, [i, vp, i, i, vp, vp]),
         "tmac_b200_upload_gptq": (i64, [C.POINTER(KCfg), vp, vp, vp, i]),
         "tmac_b200_debug_unpack_gptq": (i, [vp, vp, vp, i, i, i, i, i, vp, vp, vp]),
+        "tmac_b200_gguf_open": (i64, [C.c_char_p]), "tmac_b200_gguf_close": (i, [i64]), "tmac_b200_gguf_tensor_count": (i, [i64]),
+        "tmac_b200_gguf_tensor_info": (i, [i64, i, C.POINTER(GgufTensor)]), "tmac_b200_gguf_find_tensor": (i, [i64, C.c_char_p]),
+        "tmac_b200_gguf_meta_number": (i, [i64, C.c_char_p, C.POINTER(C.c_double)]), "tmac_b200_gguf_meta_string": (i, [i64, C.c_char_p, C.c_char_p, sz]),
+        "tmac_b200_gguf_load_tensor": (i64, [i64, i, C.POINTER(TensorExtra)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
