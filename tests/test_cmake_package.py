@@ -26,7 +26,7 @@ def test_find_package_tmac_consumer(tmp_path):
     (prefix / "lib" / "cmake" / "TMAC").mkdir(parents=True)
     (prefix / "include").mkdir()
     shutil.copy(LIB, prefix / "lib" / "libtmac_b200.so")
-    shutil.copy(os.path.join(ROOT, "deploy", "tuned", "llama-2-7b-2bit", "kcfg.ini"), prefix / "lib" / "kcfg.ini")
+    shutil.copy(build / "kcfg.ini", prefix / "lib" / "kcfg.ini")          # generated at configure time (tools/make_kcfg.py)
     shutil.copy(build / "TMACConfig.cmake", prefix / "lib" / "cmake" / "TMAC" / "TMACConfig.cmake")
     shutil.copy(os.path.join(ROOT, "include", "tmac_b200.h"), prefix / "include" / "tmac_b200.h")
     shutil.copytree(os.path.join(ROOT, "t-mac_b200", "include", "t-mac"), prefix / "include" / "t-mac")

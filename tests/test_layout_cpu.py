@@ -192,8 +192,8 @@ def test_gptq_unpack_matches_reference(tag):
     assert lib.tmac_b200_debug_unpack_gptq(qw.ctypes.data, sc.ctypes.data, qz.ctypes.data, K, M, 3, gs, v2, w.ctypes.data, s.ctypes.data, zr.ctypes.data) == -1
 
 
-def test_shipped_kcfg_presets_load():
-    """deploy/tuned/<preset>/kcfg.ini (tools/make_kcfg.py, reference format) load through the reference-format reader and
+def test_generated_kcfg_presets_load(tmp_path):
+    """kcfg.ini files written by tools/make_kcfg.py (reference format) load through the reference-format reader and
     resolve every shape of the preset with the grouping the preset means."""
     import importlib.util
     spec = importlib.util.spec_from_file_location("make_kcfg", os.path.join(ROOT, "tools", "make_kcfg.py"))
@@ -201,7 +201,7 @@ def test_shipped_kcfg_presets_load():
     lib = tb.load()
     for preset, (bits, gs, ags, zp, one, shapes) in mk.PRESETS.items():
         lib.tmac_b200_clear_kcfg()
-        path = os.path.join(ROOT, "deploy", "tuned", preset, "kcfg.ini")
+        path = mk.write(preset, str(tmp_path / preset / "kcfg.ini"))
         assert lib.tmac_b200_load_kcfg_file(path.encode()) == len(shapes), preset
         for mout, k in shapes:
             c = tb.KCfg()
