@@ -207,6 +207,11 @@ TMAC_B200_API int ggml_tmac_b200_transform_tensor_typed(void *data, int ggml_typ
 /* Host-only: the block decode alone (codes [ne01][ne00], scales [ne01][ne00 / block]); returns the block size. */
 TMAC_B200_API int tmac_b200_debug_decode_ggml(int ggml_type, const void *data, int ne00, int ne01, uint8_t *w, float *scales);
 
+/* The reference's default tiling for a shape without a tuned kcfg (python/t_mac/ops/qgemm.py:98-115, first candidate of
+ * every knob).  0 or -1. */
+TMAC_B200_API int tmac_b200_default_kcfg(int M, int K, int bits, int group_size, int act_group_size, int zero_point,
+                                         int one_scale, tmac_b200_kcfg *out);
+
 /* ---- GGUF files: what the reference pipeline produces (convert_hf_to_gguf.py:536-588; tensor blob python/t_mac/
  * model_utils.py:271) read without llama.cpp: metadata, tensor directory, tensor data mapped read-only. ---------------- */
 struct tmac_b200_gguf_tensor {

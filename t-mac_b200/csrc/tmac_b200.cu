@@ -1372,6 +1372,36 @@ int tmac_b200_debug_decode_ggml(int ggml_type, const void *data, int ne00, int n
     return ggml_block_elems(ggml_type);
 }
 
+// The reference's default tiling when no tuned kcfg exists (python/t_mac/ops/qgemm.py:98-115: the first candidate of each knob):
+// bm = first of {256,128,512,1024,320,640} ({192,384,576,768} for 3 bits) dividing M*bits with bm % bits == 0; kfactor = first
+// of {8,16} with (4*kfactor) % act_group_size == 0 and group_size % (4*kfactor) == 0 (any of them on the do_scale_final path).
+int tmac_b200_default_kcfg(int M, int K, int bits, int group_size, int act_group_size, int zero_point, int one_scale, tmac_b200_kcfg *out) {
+    if (!out || M <= 0 || K <= 0 || bits < 1 || bits > 4) return fail("default_kcfg: bad argument");
+    static const int bms3[] = {192, 384, 576, 768}, bmsx[] = {256, 128, 512, 1024, 320, 640};
+    const int *bms = bits == 3 ? bms3 : bmsx;
+    const int nb = bits == 3 ? 4 : 6;
+    int bm = 0;
+    for (int i = 0; i < nb && !bm; ++i)
+        if ((M * bits) % bms[i] == 0 && bms[i] % bits == 0) bm = bms[i];
+    if (!bm) return fail("default_kcfg: no tile size divides M*bits = " + std::to_string(M * bits));
+    const int ags = (act_group_size <= 0 || act_group_size > K) ? K : act_group_size;
+    const bool scale_final = one_scale && ags == K;
+    const int wgs = one_scale ? K : group_size;
+    int kf = 0;
+    for (int cand : {8, 16})
+        if (!kf && (scale_final || ((cand * 4) % ags == 0 && wgs > 0 && wgs % (cand * 4) == 0))) kf = cand;
+    if (!kf) {   // act group wider than 64 K positions: the reference has no candidate; the stream layout only needs kfactor | K/4
+        for (int cand : {16, 8})
+            if (!kf && (K / 4) % cand == 0) kf = cand;
+    }
+    if (!kf || (K / 4) % kf) return fail("default_kcfg: no kfactor for this grouping");
+    std::memset(out, 0, sizeof *out);
+    out->M = M; out->K = K; out->bits = bits; out->bm = bm; out->kfactor = kf; out->simd_n_in = 16; out->simd_n_out = 8;
+    out->group_size = one_scale ? (group_size > 0 ? group_size : 128) : group_size; out->act_group_size = ags;
+    out->zero_point = zero_point ? 1 : 0; out->one_scale = one_scale ? 1 : 0;
+    return 0;
+}
+
 // ---- GGUF files (tmac_gguf.h) ----------------------------------------------------------------------------------------
 static std::map<int64_t, GgufFile *> g_gguf;
 static int64_t g_next_gguf = 1;
@@ -1458,8 +1488,14 @@ int64_t tmac_b200_gguf_load_tensor(int64_t gguf, int index, struct tmac_tensor_e
     const int bits = ggml_tmac_get_type_bits(type);
     if (!bits) return fail("gguf_load_tensor: ggml type " + std::to_string(type) + " is not a T-MAC type");
     uint64_t need;
-    if (ggml_block_elems(type)) need = (uint64_t)ne1 * (ne0 / ggml_block_elems(type)) * ggml_block_bytes(type);
-    else need = ggml_tmac_b200_get_nbytes(ne0, ne1, bits);
+    if (ggml_block_elems(type)) {
+        need = (uint64_t)ne1 * (ne0 / ggml_block_elems(type)) * ggml_block_bytes(type);
+        tmac_b200_kcfg c;   // block types fix their grouping themselves: without a tuned kcfg the reference's default tiling will do
+        if (tmac_b200_find_kcfg(ne1 * bits, ne0, bits, &c) != 0) {
+            const int E = ggml_block_elems(type);
+            if (tmac_b200_default_kcfg(ne1, ne0, bits, E, E == 32 ? 32 : 64, 0, 0, &c) != 0 || tmac_b200_register_kcfg(&c) != 0) return -1;
+        }
+    } else need = ggml_tmac_b200_get_nbytes(ne0, ne1, bits);
     if (need == 0) return -1;                      // no kcfg for the shape (message set by the lookup)
     if (nbytes < need) return fail("gguf_load_tensor: tensor data is shorter than its type and shape require");
     return ggml_tmac_b200_transform_tensor_typed((void *)data, type, ne0, ne1, extra);

@@ -210,3 +210,22 @@ def test_generated_kcfg_presets_load(tmp_path):
             assert c.act_group_size == (k if ags <= 0 else ags)
             assert (mout * bits) % c.bm == 0
     lib.tmac_b200_clear_kcfg()
+
+
+def test_default_kcfg_follows_the_reference_rule():
+    """tmac_b200_default_kcfg = first candidate of every knob of QGeMMLUTBitsCodegen._define_config (qgemm.py:98-115)."""
+    lib = tb.load()
+    c = tb.KCfg()
+    cases = [  # (M, K, bits, gs, ags, zp, one) -> (bm, kfactor)
+        ((4096, 4096, 2, 128, 64, 1, 0), (256, 16)), ((11008, 4096, 4, 128, 64, 1, 0), (256, 16)), ((4096, 11008, 2, 128, 64, 0, 0), (256, 16)),
+        ((4096, 4096, 4, 32, 32, 0, 0), (256, 8)), ((3200, 8640, 2, 128, -1, 0, 1), (256, 8)), ((8640, 3200, 2, 128, -1, 0, 1), (128, 8)),
+        ((384, 1024, 3, 128, 64, 1, 0), (192, 16)), ((160, 640, 2, 128, 64, 0, 0), (320, 16)),
+    ]
+    for args, (bm, kf) in cases:
+        assert lib.tmac_b200_default_kcfg(*args, C.byref(c)) == 0, args
+        assert (c.bm, c.kfactor, c.simd_n_in, c.simd_n_out) == (bm, kf, 16, 8), (args, c.bm, c.kfactor)
+        assert c.act_group_size == (args[1] if args[4] <= 0 else args[4])
+        assert lib.tmac_b200_register_kcfg(C.byref(c)) == 0                 # a default kcfg is always a valid one
+        assert T.default_bm(args[0] * args[2], args[2]) == bm
+    assert lib.tmac_b200_default_kcfg(100, 4096, 2, 128, 64, 0, 0, C.byref(c)) == -1   # no tile divides 200 plane rows
+    lib.tmac_b200_clear_kcfg()
