@@ -36,3 +36,8 @@ def test_find_package_tmac_consumer(tmp_path):
     out = subprocess.run([str(cons / "consumer")], env=env, capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "consumer ok" in out.stdout
+    # examples/gguf_gemv: parses the golden file; the upload then fails loudly without a GPU (no CPU fallback) or succeeds on one
+    ex = subprocess.run([str(cons / "gguf_gemv"), os.path.join(ROOT, "tests", "golden", "tiny_tmac.gguf"), str(prefix / "lib" / "kcfg.ini"),
+                         "blk.0.ffn_up.weight"], env=env, capture_output=True, text=True)
+    assert "5 tensors, architecture llama" in ex.stdout and "ggml type 2 (4 bits), 64 x 256" in ex.stdout, ex.stdout + ex.stderr
+    assert ex.returncode == 0 or "no CUDA device" in ex.stderr or "upload failed" in ex.stderr
