@@ -231,7 +231,9 @@ TMAC_B200_API int tmac_b200_gguf_find_tensor(int64_t gguf, const char *name);   
 TMAC_B200_API int tmac_b200_gguf_meta_number(int64_t gguf, const char *key, double *out);
 TMAC_B200_API int tmac_b200_gguf_meta_string(int64_t gguf, const char *key, char *dst, size_t cap);   /* length or -1 */
 /* One quantised linear (2-D, I1..I4 / Q4_0 / TQ1_0 / TQ2_0) -> resident weights through the typed transform; the kcfg of
- * the shape must be registered.  Returns the weight handle; extra as for ggml_tmac_b200_transform_tensor_typed. */
+ * the shape must be registered for I-type tensors (their bytes are permuted by that tiling); block types carry their
+ * grouping themselves, so without a registered kcfg the reference's default tiling (tmac_b200_default_kcfg) is registered
+ * for the shape.  Returns the weight handle; extra as for ggml_tmac_b200_transform_tensor_typed. */
 TMAC_B200_API int64_t tmac_b200_gguf_load_tensor(int64_t gguf, int index, struct tmac_tensor_extra_b200 *extra);
 
 #ifdef __cplusplus
