@@ -207,6 +207,15 @@ TMAC_B200_API int ggml_tmac_b200_transform_tensor_typed(void *data, int ggml_typ
 /* Host-only: the block decode alone (codes [ne01][ne00], scales [ne01][ne00 / block]); returns the block size. */
 TMAC_B200_API int tmac_b200_debug_decode_ggml(int ggml_type, const void *data, int ne00, int ne01, uint8_t *w, float *scales);
 
+/* Host-only converter-side quantisers (3rdparty/llama.cpp/convert_hf_to_gguf.py): fp32 weights [rows][cols] -> codes in
+ * [0, 2^bits) + scales (+ biased zeros) in the convention of tmac_b200_upload_plain.
+ *   bitdistiller: Model._t_mac_quantize_tensor_bitdistiller (:409-452, zero-point branch), bit-identical (fp32, round half even);
+ *                 group_size <= 0 = one group per row; scales / zeros [rows][cols / group_size].
+ *   bitnet:       BitnetModel.weight_quant (:1884-1893) + the ternary rule (:1909-1917): codes 1, 2, 3 and ONE scale. */
+TMAC_B200_API int tmac_b200_quantize_bitdistiller(const float *w, int rows, int cols, int bits, int group_size, uint8_t *codes,
+                                                  float *scales, float *zeros);
+TMAC_B200_API int tmac_b200_quantize_bitnet(const float *w, int rows, int cols, uint8_t *codes, float *scale);
+
 /* The reference's default tiling for a shape without a tuned kcfg (python/t_mac/ops/qgemm.py:98-115, first candidate of
  * every knob).  0 or -1. */
 TMAC_B200_API int tmac_b200_default_kcfg(int M, int K, int bits, int group_size, int act_group_size, int zero_point,

@@ -822,6 +822,19 @@ int tmac_b200_debug_unpack_gptq(const int32_t *qweight, const uint16_t *scales_f
     return 0;
 }
 
+// Host-only converter-side quantisers (tmac_layout.h): fp weights -> codes + scales (+ zeros) in the T-MAC convention, ready for
+// tmac_b200_upload_plain.  0 or -1.
+int tmac_b200_quantize_bitdistiller(const float *w, int rows, int cols, int bits, int group_size, uint8_t *codes, float *scales, float *zeros) {
+    if (!w || !codes || !scales || !zeros) return fail("quantize_bitdistiller: null argument");
+    if (!quantize_bitdistiller(w, rows, cols, bits, group_size, codes, scales, zeros)) return fail("quantize_bitdistiller: bad shape / bits / group size");
+    return 0;
+}
+int tmac_b200_quantize_bitnet(const float *w, int rows, int cols, uint8_t *codes, float *scale) {
+    if (!w || !codes || !scale || rows <= 0 || cols <= 0) return fail("quantize_bitnet: bad argument");
+    quantize_bitnet(w, (size_t)rows * cols, codes, scale);
+    return 0;
+}
+
 // Host-only: run the reference-layout -> stream-layout transform without touching the GPU and
 // return the stream bytes (used by the CPU test-suite to pin the layout).  dst may be NULL to
 // query the size.  Returns the byte count or -1.

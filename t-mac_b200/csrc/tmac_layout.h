@@ -30,6 +30,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -234,6 +235,58 @@ inline bool unpack_gptq(const int32_t *qweight, const uint16_t *scales_f16, cons
             zeros[(size_t)m * NG + gk] = f16_bits_to_f32(f32_to_f16_bits(prod));
         }
     return true;
+}
+
+// ---- converter-side quantisers (3rdparty/llama.cpp/convert_hf_to_gguf.py) ---------------------------------------------------
+// BitDistiller-style asymmetric group quantiser, zero_point branch of Model._t_mac_quantize_tensor_bitdistiller (:409-452):
+// per group of `group_size` columns (<= 0: the whole row) scale = max(max - min, 1e-5) / (2^bits - 1),
+// zero = clamp(-round(min / scale), 0, 2^bits - 1), code = clamp(round(w / scale) + zero, 0, 2^bits - 1) (round half to even, all in
+// fp32), returned zeros = (zero - 2^(bits-1)) * scale -- the T-MAC convention W = (code - 2^(bits-1)) * scale - zeros.
+inline bool quantize_bitdistiller(const float *w, int rows, int cols, int bits, int group_size, uint8_t *codes, float *scales, float *zeros) {
+    const int gs = group_size > 0 ? group_size : cols;
+    if (rows <= 0 || cols <= 0 || bits < 1 || bits > 8 || cols % gs) return false;
+    const int ng = cols / gs;
+    const float max_int = (float)((1 << bits) - 1);
+    for (int r = 0; r < rows; ++r)
+        for (int g = 0; g < ng; ++g) {
+            const float *x = w + (size_t)r * cols + (size_t)g * gs;
+            float mx = x[0], mn = x[0];
+            for (int i = 1; i < gs; ++i) { mx = x[i] > mx ? x[i] : mx; mn = x[i] < mn ? x[i] : mn; }
+            float d = mx - mn;
+            if (d < 1e-5f) d = 1e-5f;
+            const float sc = d / max_int;
+            float zero = -std::nearbyintf(mn / sc);
+            zero = zero < 0.f ? 0.f : (zero > max_int ? max_int : zero);
+            for (int i = 0; i < gs; ++i) {
+                float q = std::nearbyintf(x[i] / sc) + zero;
+                q = q < 0.f ? 0.f : (q > max_int ? max_int : q);
+                codes[(size_t)r * cols + (size_t)g * gs + i] = (uint8_t)q;
+            }
+            scales[(size_t)r * ng + g] = sc;
+            zeros[(size_t)r * ng + g] = (zero - (float)(1 << (bits - 1))) * sc;
+        }
+    return true;
+}
+// BitNet b1.58: BitnetModel.weight_quant (:1884-1893: s = max(mean|w|, 1e-5), t = clamp(round(w / s), -1, 1), stored as t / (1/s))
+// followed by the T-MAC ternary rule (:1909-1917): scale = max|t / (1/s)|, code = round(value / scale + 2) in {1, 2, 3}; one scale
+// per tensor.  The mean is accumulated in double (torch sums in fp32 with its own blocking), so the scale may differ from the
+// reference by one ulp; the codes only could at an exact rounding tie.
+inline void quantize_bitnet(const float *w, size_t n, uint8_t *codes, float *scale) {
+    double acc = 0.0;
+    for (size_t i = 0; i < n; ++i) acc += std::fabs((double)w[i]);
+    float s = n ? (float)(acc / (double)n) : 0.f;
+    if (s < 1e-5f) s = 1e-5f;
+    const float iscale = 1.0f / s;
+    float mxabs = 0.f;
+    for (size_t i = 0; i < n; ++i) {
+        float t = std::nearbyintf(w[i] * iscale);
+        t = t < -1.f ? -1.f : (t > 1.f ? 1.f : t);
+        const float v = t / iscale;
+        codes[i] = (uint8_t)((int)t + 2);
+        const float a = std::fabs(v);
+        mxabs = a > mxabs ? a : mxabs;
+    }
+    *scale = mxabs;
 }
 
 // Inverse of the reference permutation (python/t_mac/weights.py:57-73): bit-plane row p of the

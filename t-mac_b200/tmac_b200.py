@@ -49,7 +49,7 @@ EXPORTS = [
     "ggml_tmac_set_n_threads", "ggml_tmac_get_type_bits", "ggml_tmac_b200_can_mul_mat",
     "ggml_tmac_b200_mul_mat_get_wsize", "ggml_tmac_b200_get_nbytes", "ggml_tmac_b200_transform_tensor",
     "ggml_tmac_b200_transform_tensor_typed", "tmac_b200_debug_decode_ggml", "tmac_b200_upload_gptq", "tmac_b200_debug_unpack_gptq",
-    "tmac_b200_default_kcfg", "tmac_b200_gguf_open", "tmac_b200_gguf_close", "tmac_b200_gguf_tensor_count", "tmac_b200_gguf_tensor_info", "tmac_b200_gguf_find_tensor",
+    "tmac_b200_default_kcfg", "tmac_b200_quantize_bitdistiller", "tmac_b200_quantize_bitnet", "tmac_b200_gguf_open", "tmac_b200_gguf_close", "tmac_b200_gguf_tensor_count", "tmac_b200_gguf_tensor_info", "tmac_b200_gguf_find_tensor",
     "tmac_b200_gguf_meta_number", "tmac_b200_gguf_meta_string", "tmac_b200_gguf_load_tensor",
 ]
 
@@ -97,6 +97,7 @@ def load() -> C.CDLL:
         "tmac_b200_upload_gptq": (i64, [C.POINTER(KCfg), vp, vp, vp, i]),
         "tmac_b200_debug_unpack_gptq": (i, [vp, vp, vp, i, i, i, i, i, vp, vp, vp]),
         "tmac_b200_default_kcfg": (i, [i, i, i, i, i, i, i, C.POINTER(KCfg)]),
+        "tmac_b200_quantize_bitdistiller": (i, [vp, i, i, i, i, vp, vp, vp]), "tmac_b200_quantize_bitnet": (i, [vp, i, i, vp, vp]),
         "tmac_b200_gguf_open": (i64, [C.c_char_p]), "tmac_b200_gguf_close": (i, [i64]), "tmac_b200_gguf_tensor_count": (i, [i64]),
         "tmac_b200_gguf_tensor_info": (i, [i64, i, C.POINTER(GgufTensor)]), "tmac_b200_gguf_find_tensor": (i, [i64, C.c_char_p]),
         "tmac_b200_gguf_meta_number": (i, [i64, C.c_char_p, C.POINTER(C.c_double)]), "tmac_b200_gguf_meta_string": (i, [i64, C.c_char_p, C.c_char_p, sz]),

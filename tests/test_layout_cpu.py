@@ -229,3 +229,33 @@ def test_default_kcfg_follows_the_reference_rule():
         assert T.default_bm(args[0] * args[2], args[2]) == bm
     assert lib.tmac_b200_default_kcfg(100, 4096, 2, 128, 64, 0, 0, C.byref(c)) == -1   # no tile divides 200 plane rows
     lib.tmac_b200_clear_kcfg()
+
+
+def test_converter_quantisers_match_reference():
+    """BitDistiller group quantiser: bit-identical to the reference method; BitNet ternarisation: identical codes, scale within
+    one ulp (goldens made by calling the reference's convert_hf_to_gguf.py methods, oracle/make_golden_quantizers.py)."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "quantizers.npz"))
+    lib = tb.load()
+    for tag in ("bd_w2_g128", "bd_w4_g64", "bd_w3_rowwise"):
+        bits, gs, rows, cols = [int(v) for v in z[tag + "_meta"]]
+        W = np.ascontiguousarray(z[tag + "_in"])
+        ng = cols // (gs if gs > 0 else cols)
+        codes = np.zeros((rows, cols), np.uint8); sc = np.zeros((rows, ng), np.float32); zr = np.zeros_like(sc)
+        assert lib.tmac_b200_quantize_bitdistiller(W.ctypes.data, rows, cols, bits, gs, codes.ctypes.data, sc.ctypes.data, zr.ctypes.data) == 0
+        assert np.array_equal(codes, z[tag + "_w"]), tag
+        assert np.array_equal(sc.view(np.uint32), z[tag + "_scales"].view(np.uint32)), tag
+        assert np.array_equal(zr.view(np.uint32), z[tag + "_zeros"].view(np.uint32)), tag
+        # dequantised with the T-MAC convention the weights come back within half a step (row 3 holds the degenerate constant
+        # group of the fixture, which the reference algorithm itself cannot represent)
+        real = (codes.astype(np.float32) - (1 << (bits - 1))) * np.repeat(sc, cols // ng, axis=1) - np.repeat(zr, cols // ng, axis=1)
+        keep = np.arange(rows) != 3
+        assert np.abs(real - W)[keep].max() <= 0.5001 * sc[keep].max() + 1e-7
+    for tag in ("bitnet_a", "bitnet_b"):
+        W = np.ascontiguousarray(z[tag + "_in"])
+        codes = np.zeros(W.shape, np.uint8); s = np.zeros(1, np.float32)
+        assert lib.tmac_b200_quantize_bitnet(W.ctypes.data, W.shape[0], W.shape[1], codes.ctypes.data, s.ctypes.data) == 0
+        assert np.array_equal(codes, z[tag + "_codes"]), tag
+        ref = np.float32(z[tag + "_scale"])
+        assert abs(int(s.view(np.uint32)[0]) - int(ref.view(np.uint32))) <= 1, (s[0], ref)
+        assert set(np.unique(codes)) <= {1, 2, 3}
+    assert lib.tmac_b200_quantize_bitdistiller(W.ctypes.data, 4, 100, 2, 64, codes.ctypes.data, s.ctypes.data, s.ctypes.data) == -1
