@@ -1168,7 +1168,9 @@ int tmac_b200_gemv(int64_t handle, int N, int dtype, const void *B, void *C) {
     const void *dB = B;
     if (!dev_b) {
         stage_wait();
-        if (kind_b == 1) {
+        if (kind_b == 1 && !dev_c) {
+            // page-locked caller buffer as the copy source itself -- only when this call synchronises before returning (host
+            // output); with a device output the call returns early and the caller may overwrite B at once: stage it instead
             if (g.d_b.ensure(bb)) return fail("out of device memory");
             CUDA_OK(cudaMemcpyAsync(g.d_b.p, pinB, bb, cudaMemcpyHostToDevice, g.stream()));
         } else {
