@@ -112,6 +112,8 @@ struct Context {
 
 Context g;
 std::mutex g_mu;
+std::map<int64_t, GgufFile *> g_gguf;    // open GGUF files (tmac_b200_gguf_*)
+int64_t g_next_gguf = 1;
 
 bool is_device_ptr(const void *p) {
     if (!p) return false;
@@ -645,6 +647,10 @@ void tmac_b200_shutdown(void) {
     cudaStreamSynchronize(g.stream());
     for (auto &kv : g.xchg) if (kv.second) cudaFree(kv.second);
     g.xchg.clear();
+    for (auto &e : g.ptr_tables) if (e.second) cudaFree(e.second);
+    g.ptr_tables.clear();
+    for (auto &kv : g_gguf) delete kv.second;
+    g_gguf.clear();
     for (auto &kv : g.res) {
         cudaFree(kv.second.d);
         if (kv.second.reserved) munmap(kv.second.reserved, kv.second.reserved_bytes);
@@ -1418,8 +1424,6 @@ int tmac_b200_default_kcfg(int M, int K, int bits, int group_size, int act_group
 }
 
 // ---- GGUF files (tmac_gguf.h) ----------------------------------------------------------------------------------------
-static std::map<int64_t, GgufFile *> g_gguf;
-static int64_t g_next_gguf = 1;
 
 int64_t tmac_b200_gguf_open(const char *path) {
     if (!path) return fail("gguf_open: null path");
