@@ -23,6 +23,7 @@
 
 #include "tmac_kernels.cuh"
 #include "tmac_prefill.cuh"
+#include "tmac_prefill16.cuh"
 #include "tmac_gemv4.cuh"
 #include "tmac_layout.h"
 #include "tmac_gguf.h"
@@ -93,6 +94,7 @@ struct Context {
     int use_fused = 1;
     int use_g4 = 0, g4_grid = 0;         // lone launches: stream-K kernel (0 off, 1 auto, 2 whenever the shape allows); grid override
     std::map<cudaStream_t, void *> xchg; // gemv4 exchange slots, one buffer per stream that ever launched it
+    int use_prefill16 = 0;               // DRAFT fp16-operand prefill tile (tmac_prefill16.cuh), opt-in until validated on hardware
     int use_prefill = 1, prefill_min_n = 32;   // N >= prefill_min_n: tcgen05 int8 tile (W2 g128 act64)                   // tmac_b200_gemv builds the LUT inside the GEMV when the grouping allows
     int64_t next_hint = 0;               // one-shot: tensor whose blocks the next launch prefetches into L2
     std::map<int64_t, Resident> res;
@@ -156,6 +158,7 @@ int ensure_init() {
     if (const char *e = getenv("TMAC_B200_MINB")) g.minb_override = atoi(e);
     if (const char *e = getenv("TMAC_B200_FUSED")) g.use_fused = atoi(e);
     if (const char *e = getenv("TMAC_B200_PREFILL")) g.use_prefill = atoi(e);
+    if (const char *e = getenv("TMAC_B200_PREFILL16")) g.use_prefill16 = atoi(e);
     if (const char *e = getenv("TMAC_B200_PREFILL_MIN_N")) g.prefill_min_n = atoi(e);
     if (const char *e = getenv("TMAC_B200_WPC")) g.wpc_override = atoi(e);
     if (const char *e = getenv("TMAC_B200_NBUF")) g.nbuf_override = atoi(e);
@@ -434,6 +437,25 @@ int launch_prefill(const Resident &R, int N, const int8_t *qlut, const float *ls
     if (!g.use_prefill || N < g.prefill_min_n || !sym) return 1;
     if (L.pb != 2 || L.qch != 8 || L.act_group_size != 64 || L.one_scale || L.ck != 128) return 1;
     const size_t rawsz = (L.blk + 127) & ~(size_t)127;
+    if (g.use_prefill16 && N >= 64) {   // DRAFT: scales folded into fp16 operands, fp32 accumulation over K (tmac_prefill16.cuh)
+        const int nmain = L.K / 64, nextra = (L.nchunk + 31) / 32, ntile16 = (N + kP16NT - 1) / kP16NT;
+        const size_t smem16 = (size_t)kP16Stages * (kP16ABytes + kP16BBytes) + 2 * rawsz + 256 * 16 + (2 * kP16Stages + 1) * 8 + 1024;
+        if (smem16 <= 227 * 1024) {
+            if (g.d_tiles.ensure((size_t)ntile16 * (nmain + nextra) * kP16BBytes)) return fail("out of device memory (LUT tiles)");
+            lut_tile16_kernel<<<dim3(nmain + nextra, ntile16), 256, 0, g.stream()>>>(qlut, ls, lb, (unsigned char *)g.d_tiles.p, N, L.K, nmain, nextra);
+            CUDA_OK(cudaGetLastError());
+            Prefill16Params q{};
+            q.W = R.d; q.C = C; q.N = N; q.K = L.K; q.Mout = L.Mout; q.ldc = ldc; q.out_f16 = out_f16;
+            q.nchunk = L.nchunk; q.zp = L.zp; q.sd = L.sd; q.blk_bytes = (int)L.blk; q.nmain = nmain; q.nextra = nextra;
+            q.rsb_stride = L.rsb_stride; q.tiles = (const unsigned char *)g.d_tiles.p;
+            CUDA_OK(cudaFuncSetAttribute((const void *)prefill16_w2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+            prefill16_w2_kernel<<<dim3(L.nrsb, ntile16), kP16Threads, smem16, g.stream()>>>(q);
+            CUDA_OK(cudaGetLastError());
+            g.last_launch[0] = 16; g.last_launch[1] = kP16Threads / 32; g.last_launch[2] = L.nchunk; g.last_launch[3] = 1; g.last_launch[4] = L.nrsb;
+            g.last_launch[5] = L.pb; g.last_launch[6] = 1; g.last_launch[7] = -N;
+            return 0;
+        }
+    }
     const size_t smem = (size_t)kPfStages * (kPfStageBytes + kPfRec) + 2 * rawsz + 256 * 8 + (2 * kPfStages + 4) * 8 + 1024;
     if (smem > 225 * 1024) return 1;
     const int nag = L.K / 64, ntile = (N + kPfNT - 1) / kPfNT;
@@ -986,6 +1008,7 @@ int tmac_b200_debug_set(const char *key, int value) {
     else if (k == "g4_grid") g.g4_grid = value;
     else if (k == "fused") g.use_fused = value;
     else if (k == "prefill") g.use_prefill = value;
+    else if (k == "prefill16") g.use_prefill16 = value;
     else if (k == "prefill_min_n") g.prefill_min_n = value;
     else if (k == "pdl") g.use_pdl = value;
     else if (k == "pdl_late") g.pdl_late = value;
