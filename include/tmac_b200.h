@@ -157,6 +157,28 @@ TMAC_B200_API int tmac_b200_qgemm_lut_grouped(const int64_t *handles, int count,
 /* Fused convenience (llama_cpp_init + llama_cpp_compute of the whole tensor in one call,
  * workspaces owned by the library): C [N][M] = qgemm_lut(preprocessor(B)). */
 TMAC_B200_API int tmac_b200_gemv(int64_t handle, int N, int dtype, const void *B, void *C);
+/* ---- decode sequences: a chain of (dependent) GEMVs in ONE persistent launch ------------------------------------------
+ * The reference executes a token step as ggml's graph loop: one mul_mat node after the other on a persistent thread pool
+ * (3rdparty/llama.cpp/ggml/src/ggml.c:12562-12706 per node; llama_cpp_init + llama_cpp_compute per node,
+ * include/t-mac/tmac_gemm_wrapper.h:173-228).  A sequence is that loop for the quantised linears on the GPU: one CTA per
+ * SM stays resident, the weight stream of op i+1, i+2 runs under the arithmetic of op i (weights do not depend on
+ * activations), and the data dependency op -> op is carried by {value, epoch} words in HBM instead of a kernel boundary.
+ *   seq_add_gemv: C = gemv(handle, input).  input = x (external device fp32 vector [K], 16-byte aligned) when x != NULL,
+ *                 else elements [in_offset, in_offset + K) of the output of the earlier op `in_op` (in_offset even).
+ *                 C (device, [M] of dtype, optional) receives a plain copy of the output.  Returns the op index.
+ *   All tensors of a sequence share bits / group_size / act_group_size (one kernel instantiation); fp path
+ *   (act_group_size <= 128).  Results equal tmac_b200_gemv up to fp32 re-association (different K split). */
+TMAC_B200_API int64_t tmac_b200_seq_create(void);
+TMAC_B200_API int tmac_b200_seq_add_gemv(int64_t seq, int64_t handle, const void *x, int in_op, int in_offset, void *C, int dtype);
+TMAC_B200_API int tmac_b200_seq_build(int64_t seq);     /* allocates the device tables; no more ops afterwards */
+TMAC_B200_API int tmac_b200_seq_launch(int64_t seq);    /* asynchronous, on the current stream; capturable in a CUDA graph */
+TMAC_B200_API int tmac_b200_seq_status(int64_t seq);    /* synchronises; 0 = ok, -1 = a bounded wait inside the kernel expired */
+/* info[8] = {grid, ring slots, slot bytes, shared-memory bytes, ops, planes/word, quads/chunk, quads/activation group} */
+TMAC_B200_API int tmac_b200_seq_info(int64_t seq, int *out8);
+/* Debug (tmac_b200_debug_set("trace", 1) before seq_build): globaltimer stamps [ops][grid][8] of the last launch:
+ * 0 op entered, 1 LUT slices built, 2 lookups done (warp 0), 3 CTA reduced, 4 rows published.  Returns grid. */
+TMAC_B200_API int tmac_b200_seq_trace(int64_t seq, long long *dst, size_t cap_bytes);
+TMAC_B200_API int tmac_b200_seq_free(int64_t seq);
 /* Debug / parity gate G2: integer bit-plane sums CBits int32 [N][M*bits] in the reference
  * plane layout ([M/8][bits][8] per tensor), act-group sums folded over K. */
 TMAC_B200_API int tmac_b200_cbits(int64_t handle, int N, const void *QLUT, int32_t *CBits);

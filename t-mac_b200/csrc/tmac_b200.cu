@@ -25,6 +25,7 @@
 #include "tmac_prefill.cuh"
 #include "tmac_prefill16.cuh"
 #include "tmac_gemv4.cuh"
+#include "tmac_seq.cuh"
 #include "tmac_layout.h"
 #include "tmac_gguf.h"
 
@@ -92,6 +93,7 @@ struct Context {
     int cs_override = 0, wpc_override = 0, pdl_late = -1, minb_override = 0, nbuf_override = 0;
     int last_launch[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int use_fused = 1;
+    int seq_grid = 0;                    // decode sequences: grid override (tests: CTA-boundary placements); 0 = one CTA per SM
     int use_g4 = 0, g4_grid = 0;         // lone launches: stream-K kernel (0 off, 1 auto, 2 whenever the shape allows); grid override
     std::map<cudaStream_t, void *> xchg; // gemv4 exchange slots, one buffer per stream that ever launched it
     int use_prefill16 = 0;               // DRAFT fp16-operand prefill tile (tmac_prefill16.cuh), opt-in until validated on hardware
@@ -116,6 +118,24 @@ Context g;
 std::mutex g_mu;
 std::map<int64_t, GgufFile *> g_gguf;    // open GGUF files (tmac_b200_gguf_*)
 int64_t g_next_gguf = 1;
+
+// decode sequences (tmac_b200_seq_*)
+struct SeqOpHost { int64_t handle; const void *x_ext; int in_op, in_off; void *C; int out_f16; };
+struct Sequence {
+    std::vector<SeqOpHost> ops;
+    bool built = false;
+    int grid = 0, pb = 0, qch = 0, agq = 0, bits = 0;
+    seq_fn fn = nullptr;
+    size_t smem = 0;
+    SeqParams params{};
+    void *d_ops = nullptr, *d_y = nullptr, *d_xchg = nullptr, *d_epochs = nullptr, *d_err = nullptr, *d_trace = nullptr;
+    void release() {
+        for (void *q : {d_ops, d_y, d_xchg, d_epochs, d_err, d_trace}) if (q) cudaFree(q);
+        d_ops = d_y = d_xchg = d_epochs = d_err = d_trace = nullptr; built = false;
+    }
+};
+std::map<int64_t, Sequence> g_seqs;
+int64_t g_next_seq = 1;
 
 bool is_device_ptr(const void *p) {
     if (!p) return false;
@@ -667,6 +687,8 @@ void tmac_b200_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g.inited) return;
     cudaStreamSynchronize(g.stream());
+    for (auto &kv : g_seqs) kv.second.release();
+    g_seqs.clear();
     for (auto &kv : g.xchg) if (kv.second) cudaFree(kv.second);
     g.xchg.clear();
     for (auto &e : g.ptr_tables) if (e.second) cudaFree(e.second);
@@ -1005,6 +1027,8 @@ int tmac_b200_debug_set(const char *key, int value) {
     if (ensure_init()) return -1;
     const std::string k = key ? key : "";
     if (k == "g4") g.use_g4 = value;
+    else if (k == "seq_grid") g.seq_grid = value;
+    else if (k == "trace") g.trace = value;
     else if (k == "g4_grid") g.g4_grid = value;
     else if (k == "fused") g.use_fused = value;
     else if (k == "prefill") g.use_prefill = value;
@@ -1214,6 +1238,192 @@ int tmac_b200_gemv(int64_t handle, int N, int dtype, const void *B, void *C) {
         CUDA_OK(cudaStreamSynchronize(g.stream()));
         if (kind_c == 0) std::memcpy(C, g.h_out.p, cb);
     }
+    return 0;
+}
+
+// ---- decode sequences: a chain of dependent GEMVs in ONE persistent launch (tmac_seq.cuh) ---------------------------
+// The reference runs a token step as ggml's graph loop over mul_mat nodes on a persistent thread pool
+// (3rdparty/llama.cpp/ggml/src/ggml.c:12562-12706 per node); a sequence is that loop for the quantised linears.
+
+int64_t tmac_b200_seq_create(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    const int64_t h = g_next_seq++;
+    g_seqs[h];
+    return h;
+}
+
+int tmac_b200_seq_add_gemv(int64_t seq, int64_t handle, const void *x, int in_op, int in_offset, void *C, int dtype) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_seqs.find(seq);
+    if (it == g_seqs.end()) return fail("seq_add_gemv: bad sequence");
+    Sequence &S = it->second;
+    if (S.built) return fail("seq_add_gemv: sequence already built");
+    auto rt = g.res.find(handle);
+    if (rt == g.res.end()) return fail("seq_add_gemv: bad weight handle");
+    const StreamLayout &L = rt->second.L;
+    if (x) {
+        if (!is_device_ptr(x)) return fail("seq_add_gemv: the external input must be a device pointer");
+        if ((uintptr_t)x % 16) return fail("seq_add_gemv: the external input must be 16-byte aligned");
+    } else {
+        if (in_op < 0 || in_op >= (int)S.ops.size()) return fail("seq_add_gemv: in_op must name an earlier op of the sequence");
+        const StreamLayout &P = g.res.find(S.ops[in_op].handle)->second.L;
+        if (in_offset < 0 || in_offset % 2 || in_offset + L.K > P.Mout) return fail("seq_add_gemv: [in_offset, in_offset + K) must lie inside the producer's output (even offset)");
+    }
+    if (C && !is_device_ptr(C)) return fail("seq_add_gemv: C must be a device pointer (or NULL)");
+    S.ops.push_back({handle, x, x ? -1 : in_op, in_offset, C, dtype == TMAC_B200_F16});
+    return (int)S.ops.size() - 1;
+}
+
+int tmac_b200_seq_build(int64_t seq) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_seqs.find(seq);
+    if (it == g_seqs.end()) return fail("seq_build: bad sequence");
+    Sequence &S = it->second;
+    if (S.built) return 0;
+    if (S.ops.empty()) return fail("seq_build: empty sequence");
+    const int G = g.seq_grid > 0 ? std::min(g.seq_grid, g.sms) : g.sms;
+    const int n = (int)S.ops.size();
+    std::vector<SeqOp> ops(n);
+    std::vector<size_t> yoff(n);
+    size_t ytot = 0, red_b = 0, tab_b = 0, lsb_b = 0, slot_b = 0;
+    int rsbmax = 0;
+    for (int i = 0; i < n; ++i) {
+        auto rt = g.res.find(S.ops[i].handle);
+        if (rt == g.res.end()) return fail("seq_build: a weight handle was freed");
+        const StreamLayout &L = rt->second.L;
+        const bool int_path = L.one_scale && L.act_group_size == L.K;
+        if (int_path || L.act_group_size > L.ck) return fail("seq_build: activation group must lie inside a chunk (fp path)");
+        const int agq = std::min(L.act_group_size, L.ck) / 16;
+        if (i == 0) { S.pb = L.pb; S.qch = L.qch; S.agq = agq; S.bits = L.bits; }
+        else if (S.pb != L.pb || S.qch != L.qch || S.agq != agq || S.bits != L.bits) return fail("seq_build: all tensors of a sequence must share bits / grouping");
+        const long total = (long)L.nrsb * L.nchunk;
+        const long ge = std::min<long>(G, total);
+        const int per = (int)((total + ge - 1) / ge);
+        const int nseg = (per - 1 + L.nchunk - 1) / L.nchunk + 1;
+        const int ntab = std::min(per, L.nchunk);
+        const int nag = L.qch / agq;
+        red_b = std::max(red_b, (size_t)nseg * kSeqWarps * L.rsb * 4);
+        tab_b = std::max(tab_b, (size_t)ntab * L.qch * 4 * 8);
+        lsb_b = std::max(lsb_b, (size_t)ntab * 2 * nag * 4);
+        slot_b = std::max(slot_b, (L.blk + 127) & ~(size_t)127);
+        rsbmax = std::max(rsbmax, L.rsb);
+        yoff[i] = ytot;
+        ytot += ((size_t)L.nrsb * L.rsb * sizeof(uint2) + 255) & ~(size_t)255;
+    }
+    const size_t budget = 227 * 1024;
+    const size_t fixed = ((red_b + 15) & ~(size_t)15) + ((tab_b + 15) & ~(size_t)15) + ((lsb_b + 15) & ~(size_t)15) + 64 * 8 + (kSeqWarps + 1) * 4 + 64;
+    if (fixed + 4 * slot_b > budget) return fail("seq_build: shared-memory budget exceeded");
+    const int nslots = (int)std::min<size_t>(64, (budget - fixed) / slot_b);
+    S.fn = pick_seq(S.pb, S.qch, S.agq);
+    if (!S.fn) return fail("seq_build: chunking not instantiated");
+    S.grid = G;
+    const size_t xper = (size_t)G * rsbmax * sizeof(uint2);
+    if (cudaMalloc(&S.d_ops, n * sizeof(SeqOp)) != cudaSuccess || cudaMalloc(&S.d_y, ytot) != cudaSuccess ||
+        cudaMalloc(&S.d_xchg, xper * n) != cudaSuccess || cudaMalloc(&S.d_epochs, G * sizeof(unsigned)) != cudaSuccess ||
+        cudaMalloc(&S.d_err, sizeof(int)) != cudaSuccess) { cudaGetLastError(); S.release(); return fail("seq_build: out of device memory"); }
+    if (g.trace) {
+        if (cudaMalloc(&S.d_trace, (size_t)n * G * 8 * sizeof(long long)) != cudaSuccess) { cudaGetLastError(); S.release(); return fail("seq_build: out of device memory (trace)"); }
+        cudaMemset(S.d_trace, 0, (size_t)n * G * 8 * sizeof(long long));
+    }
+    CUDA_OK(cudaMemset(S.d_y, 0, ytot));
+    CUDA_OK(cudaMemset(S.d_xchg, 0, xper * n));
+    CUDA_OK(cudaMemset(S.d_epochs, 0, G * sizeof(unsigned)));
+    CUDA_OK(cudaMemset(S.d_err, 0, sizeof(int)));
+    for (int i = 0; i < n; ++i) {
+        const Resident &R = g.res.find(S.ops[i].handle)->second;
+        const StreamLayout &L = R.L;
+        SeqOp &o = ops[i];
+        o.W = R.d;
+        o.x_ext = (const float *)S.ops[i].x_ext;
+        o.x_ll = S.ops[i].x_ext ? nullptr : (const uint2 *)((char *)S.d_y + yoff[S.ops[i].in_op]) + S.ops[i].in_off;
+        o.C = S.ops[i].C;
+        o.y = (uint2 *)((char *)S.d_y + yoff[i]);
+        o.xchg = (uint2 *)((char *)S.d_xchg + xper * i);
+        o.rsb_stride = L.rsb_stride;
+        o.K = L.K; o.Mout = L.Mout; o.nrsb = L.nrsb; o.nchunk = L.nchunk;
+        o.blk_bytes = (int)L.blk; o.total = L.nrsb * L.nchunk;
+        o.zp = L.zp; o.one_scale = L.one_scale; o.sd = L.sd; o.out_f16 = S.ops[i].out_f16;
+        o.scale0 = L.scale0; o.geff = std::min(G, o.total);
+    }
+    CUDA_OK(cudaMemcpy(S.d_ops, ops.data(), n * sizeof(SeqOp), cudaMemcpyHostToDevice));
+    SeqParams &P = S.params;
+    P.ops = (const SeqOp *)S.d_ops; P.nops = n; P.nslots = nslots; P.slot_bytes = (int)slot_b;
+    size_t off = (size_t)nslots * slot_b;
+    P.red_off = (int)off; off += (red_b + 15) & ~(size_t)15;
+    P.tab_off = (int)off; off += (tab_b + 15) & ~(size_t)15;
+    P.lsb_off = (int)off; off += (lsb_b + 15) & ~(size_t)15;
+    P.bar_off = (int)off; off += (size_t)nslots * 8;
+    P.prog_off = (int)off; off += (kSeqWarps + 1) * 4;   // + the producer's `issued` counter
+    P.epochs = (unsigned *)S.d_epochs; P.err = (int *)S.d_err; P.trace = (long long *)S.d_trace;
+    S.smem = off;
+    CUDA_OK(cudaFuncSetAttribute((const void *)S.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.smem));
+    S.built = true;
+    return 0;
+}
+
+int tmac_b200_seq_launch(int64_t seq) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_seqs.find(seq);
+    if (it == g_seqs.end()) return fail("seq_launch: bad sequence");
+    Sequence &S = it->second;
+    if (!S.built) return fail("seq_launch: call tmac_b200_seq_build first");
+    uint32_t wtx, wty;
+    plane_weight_regs(S.bits, true, &wtx, &wty);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(S.grid, 1, 1);
+    cfg.blockDim = dim3(kSeqThreads, 1, 1);
+    cfg.dynamicSmemBytes = S.smem;
+    cfg.stream = g.stream();
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;      // every CTA must be resident: CTAs wait for each other's rows
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CUDA_OK(cudaLaunchKernelEx(&cfg, S.fn, S.params, wtx, wty));
+    return 0;
+}
+
+/* Synchronises the stream and returns the sequence's error flag (0 = every wait completed). */
+int tmac_b200_seq_status(int64_t seq) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_seqs.find(seq);
+    if (it == g_seqs.end() || !it->second.built) return fail("seq_status: bad sequence");
+    CUDA_OK(cudaStreamSynchronize(g.stream()));
+    int e = 0;
+    CUDA_OK(cudaMemcpy(&e, it->second.d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (e) return fail("sequence kernel: a bounded wait expired (code " + std::to_string(e) + ")");
+    return 0;
+}
+
+/* info[8] = {grid, ring slots, slot bytes, shared memory bytes, ops, planes/word, quads/chunk, quads/act group} */
+int tmac_b200_seq_info(int64_t seq, int *out8) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_seqs.find(seq);
+    if (it == g_seqs.end() || !it->second.built || !out8) return fail("seq_info: bad sequence");
+    const Sequence &S = it->second;
+    const int v[8] = {S.grid, S.params.nslots, S.params.slot_bytes, (int)S.smem, (int)S.ops.size(), S.pb, S.qch, S.agq};
+    std::memcpy(out8, v, sizeof v);
+    return 0;
+}
+
+/* Debug (knob "trace" set before seq_build): globaltimer stamps [ops][grid][8] of the last launch; returns grid. */
+int tmac_b200_seq_trace(int64_t seq, long long *dst, size_t cap_bytes) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_seqs.find(seq);
+    if (it == g_seqs.end() || !it->second.built || !it->second.d_trace) return fail("seq_trace: tracing was not enabled when the sequence was built");
+    CUDA_OK(cudaStreamSynchronize(g.stream()));
+    const size_t bytes = std::min(cap_bytes, it->second.ops.size() * (size_t)it->second.grid * 8 * sizeof(long long));
+    CUDA_OK(cudaMemcpy(dst, it->second.d_trace, bytes, cudaMemcpyDeviceToHost));
+    return it->second.grid;
+}
+
+int tmac_b200_seq_free(int64_t seq) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_seqs.find(seq);
+    if (it == g_seqs.end()) return fail("seq_free: bad sequence");
+    if (g.inited) cudaStreamSynchronize(g.stream());
+    it->second.release();
+    g_seqs.erase(it);
     return 0;
 }
 

@@ -51,6 +51,8 @@ EXPORTS = [
     "ggml_tmac_b200_transform_tensor_typed", "tmac_b200_debug_decode_ggml", "tmac_b200_upload_gptq", "tmac_b200_debug_unpack_gptq",
     "tmac_b200_default_kcfg", "tmac_b200_quantize_bitdistiller", "tmac_b200_quantize_bitnet", "tmac_b200_gguf_open", "tmac_b200_gguf_close", "tmac_b200_gguf_tensor_count", "tmac_b200_gguf_tensor_info", "tmac_b200_gguf_find_tensor",
     "tmac_b200_gguf_meta_number", "tmac_b200_gguf_meta_string", "tmac_b200_gguf_load_tensor",
+    "tmac_b200_seq_create", "tmac_b200_seq_add_gemv", "tmac_b200_seq_build", "tmac_b200_seq_launch", "tmac_b200_seq_status",
+    "tmac_b200_seq_info", "tmac_b200_seq_trace", "tmac_b200_seq_free",
 ]
 
 _lib = None
@@ -102,6 +104,9 @@ def load() -> C.CDLL:
         "tmac_b200_gguf_tensor_info": (i, [i64, i, C.POINTER(GgufTensor)]), "tmac_b200_gguf_find_tensor": (i, [i64, C.c_char_p]),
         "tmac_b200_gguf_meta_number": (i, [i64, C.c_char_p, C.POINTER(C.c_double)]), "tmac_b200_gguf_meta_string": (i, [i64, C.c_char_p, C.c_char_p, sz]),
         "tmac_b200_gguf_load_tensor": (i64, [i64, i, C.POINTER(TensorExtra)]),
+        "tmac_b200_seq_create": (i64, []), "tmac_b200_seq_add_gemv": (i, [i64, i64, vp, i, i, vp, i]),
+        "tmac_b200_seq_build": (i, [i64]), "tmac_b200_seq_launch": (i, [i64]), "tmac_b200_seq_status": (i, [i64]),
+        "tmac_b200_seq_info": (i, [i64, C.POINTER(C.c_int)]), "tmac_b200_seq_trace": (i, [i64, vp, sz]), "tmac_b200_seq_free": (i, [i64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -213,6 +218,49 @@ def gemv(wt: Weights, N, B, Cout, dtype=F32):
 
 def cbits(wt: Weights, N, qlut, out):
     check(load().tmac_b200_cbits(wt.handle, N, ptr(qlut), ptr(out)), "tmac_b200_cbits")
+
+
+class Sequence:
+    """A chain of (dependent) GEMVs executed by one persistent launch (tmac_b200_seq_*, include/tmac_b200.h)."""
+
+    def __init__(self):
+        self.h = load().tmac_b200_seq_create()
+        check(self.h, "tmac_b200_seq_create")
+        self.nops = 0
+
+    def add(self, wt: "Weights", x=None, in_op: int = -1, in_offset: int = 0, out=None, dtype=F32) -> int:
+        """x: external device fp32 vector, or None -> elements [in_offset, in_offset + K) of op `in_op`'s output."""
+        rc = load().tmac_b200_seq_add_gemv(self.h, wt.handle, ptr(x), in_op, in_offset, ptr(out), dtype)
+        check(rc, "tmac_b200_seq_add_gemv")
+        self.nops += 1
+        return rc
+
+    def build(self):
+        check(load().tmac_b200_seq_build(self.h), "tmac_b200_seq_build")
+        return self
+
+    def launch(self):
+        check(load().tmac_b200_seq_launch(self.h), "tmac_b200_seq_launch")
+
+    def status(self):
+        check(load().tmac_b200_seq_status(self.h), "tmac_b200_seq_status")
+
+    def info(self) -> dict:
+        v = (C.c_int * 8)()
+        check(load().tmac_b200_seq_info(self.h, v), "tmac_b200_seq_info")
+        return dict(zip(["grid", "ring_slots", "slot_bytes", "smem_bytes", "ops", "planes_per_word", "quads_per_chunk", "quads_per_act_group"], list(v)))
+
+    def trace(self):
+        import numpy as np
+        inf = self.info()
+        buf = np.zeros((inf["ops"], inf["grid"], 8), np.int64)
+        check(load().tmac_b200_seq_trace(self.h, buf.ctypes.data, buf.nbytes), "tmac_b200_seq_trace")
+        return buf
+
+    def free(self):
+        if self.h > 0:
+            load().tmac_b200_seq_free(self.h)
+            self.h = -1
 
 
 class TMACGeMMWrapper:
