@@ -119,6 +119,9 @@ std::mutex g_mu;
 std::map<int64_t, GgufFile *> g_gguf;    // open GGUF files (tmac_b200_gguf_*)
 int64_t g_next_gguf = 1;
 
+std::map<int64_t, cudaGraphExec_t> g_graphs;   // tmac_b200_graph_*
+int64_t g_next_graph = 1;
+
 // decode sequences (tmac_b200_seq_*)
 struct SeqOpHost { int64_t handle; const void *x_ext; int in_op, in_off; void *C; int out_f16; };
 struct Sequence {
@@ -155,7 +158,11 @@ int ptr_kind(const void *p, void **dev = nullptr) {
 }
 
 int ensure_init() {
-    if (g.inited) return 0;
+    if (g.inited) {   // the CUDA current device is per host thread (ggml worker threads enter here too)
+        static thread_local int t_dev = -1;
+        if (t_dev != g.device) { if (cudaSetDevice(g.device) != cudaSuccess) { cudaGetLastError(); return fail("cudaSetDevice failed"); } t_dev = g.device; }
+        return 0;
+    }
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return fail("no CUDA device: libtmac_b200 has no CPU fallback"); }
     int dev = 0;
@@ -602,6 +609,7 @@ int validate_cfg(const tmac_b200_kcfg &c) {
     if (c.bm <= 0 || (c.M * c.bits) % c.bm || c.bm % 32 || c.bm % c.bits) return fail("kcfg: bm must divide M*bits and be a multiple of 32 and of bits");
     if (c.kfactor <= 0 || (c.K / 4) % c.kfactor) return fail("kcfg: kfactor must divide K/4");
     if (c.simd_n_in != 16 || c.simd_n_out != 8) return fail("kcfg: only simd_n_in=16, simd_n_out=8 (the reference's only instantiation)");
+    if (!c.one_scale && (c.group_size <= 0 || c.K % c.group_size || c.group_size % 32)) return fail("kcfg: group_size must be a positive multiple of 32 that divides K");
     return 0;
 }
 
@@ -689,6 +697,8 @@ void tmac_b200_shutdown(void) {
     cudaStreamSynchronize(g.stream());
     for (auto &kv : g_seqs) kv.second.release();
     g_seqs.clear();
+    for (auto &kv : g_graphs) cudaGraphExecDestroy(kv.second);
+    g_graphs.clear();
     for (auto &kv : g.xchg) if (kv.second) cudaFree(kv.second);
     g.xchg.clear();
     for (auto &e : g.ptr_tables) if (e.second) cudaFree(e.second);
@@ -701,12 +711,13 @@ void tmac_b200_shutdown(void) {
         std::free(kv.second.host_scales);
     }
     g.res.clear();
-    for (DevBuf *b : {&g.d_b, &g.d_qlut, &g.d_ls, &g.d_lb, &g.d_c, &g.d_part, &g.d_cnt, &g.d_cbits}) { if (b->p) cudaFree(b->p); b->p = nullptr; b->cap = 0; }
+    for (DevBuf *b : {&g.d_b, &g.d_qlut, &g.d_ls, &g.d_lb, &g.d_c, &g.d_part, &g.d_cnt, &g.d_cbits, &g.d_trace, &g.d_tiles}) { if (b->p) cudaFree(b->p); b->p = nullptr; b->cap = 0; }
     for (PinBuf *b : {&g.h_in, &g.h_out}) { if (b->p) cudaFreeHost(b->p); b->p = nullptr; b->cap = 0; }
     if (g.stage_ev) cudaEventDestroy(g.stage_ev);
     g.stage_ev = nullptr; g.stage_pending = false;
     if (g.own) cudaStreamDestroy(g.own);
     g.own = nullptr; g.cnt_zeroed = 0; g.sym_qluts.clear();
+    g.user = nullptr; g.use_user = false; g.trace_ctas = 0; g.trace_seq = 0; g.next_hint = 0;
     g.inited = false;
 }
 
@@ -781,6 +792,7 @@ int tmac_b200_load_kcfg_file(const char *path) {
     for (auto &s : secs) {
         int t, m, k, n, b;
         if (sscanf(s.name.c_str(), "qgemm_lut_t%d_int8_m%d_k%d_n%d_b%d", &t, &m, &k, &n, &b) != 5) continue;
+        if (b < 1 || b > 4) continue;                    // not a section this library can serve (and m / b below)
         auto get = [&](const char *key, long dflt) { auto it = s.kv.find(key); return it == s.kv.end() ? dflt : it->second; };
         tmac_b200_kcfg c{};
         c.M = m / b; c.K = k; c.bits = b;
@@ -829,7 +841,8 @@ int64_t tmac_b200_upload_plain_rows(const tmac_b200_kcfg *cfg_in, const uint8_t 
     if (cfg.simd_n_in == 0) cfg.simd_n_in = 16;
     if (cfg.simd_n_out == 0) cfg.simd_n_out = 8;
     if (cfg.act_group_size <= 0 || cfg.act_group_size > cfg.K) cfg.act_group_size = cfg.K;
-    if (cfg.bits < 1 || cfg.bits > 4 || cfg.M <= 0 || cfg.K % 32) return fail("upload_plain: bad shape");
+    if (cfg.bits < 1 || cfg.bits > 4 || cfg.M <= 0 || cfg.K <= 0 || cfg.K % 32) return fail("upload_plain: bad shape");
+    if (!cfg.one_scale && (cfg.group_size <= 0 || cfg.K % cfg.group_size || cfg.group_size % 32)) return fail("upload_plain: group_size must be a positive multiple of 32 that divides K");
     if (row0 < 0 || rows <= 0 || row0 + rows > cfg.M) return fail("upload_plain: bad row range");
     if (cfg.zero_point && !zeros && !cfg.one_scale) return fail("upload_plain: zero_point set but zeros == NULL");
     PlainWeights P;
@@ -941,6 +954,7 @@ int64_t tmac_b200_clone_weights(int64_t handle) {
     if (it == g.res.end()) return fail("clone: bad handle");
     Resident R = it->second;
     R.host_a = nullptr; R.host_a_bytes = 0;
+    R.reserved = nullptr; R.reserved_bytes = 0; R.host_scales = nullptr;   // owned by the original only (no double munmap / free)
     if (cudaMalloc((void **)&R.d, R.L.total) != cudaSuccess) { cudaGetLastError(); return fail("out of device memory for clone"); }
     if (cudaMemcpy(R.d, it->second.d, R.L.total, cudaMemcpyDeviceToDevice) != cudaSuccess) { cudaFree(R.d); return fail("clone copy failed"); }
     const int64_t h = g.next_handle++;
@@ -950,8 +964,6 @@ int64_t tmac_b200_clone_weights(int64_t handle) {
 
 // ---- CUDA-graph helpers: capture a sequence of library calls (device pointers only; run the
 // sequence once eagerly first so that every workspace is allocated) and replay it. -------------
-static std::map<int64_t, cudaGraphExec_t> g_graphs;
-static int64_t g_next_graph = 1;
 
 int tmac_b200_graph_begin(void) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -1175,6 +1187,11 @@ int tmac_b200_qgemm_lut_grouped(const int64_t *handles, int count, int N, int dt
     if (!dtab) {
         if (cudaMalloc(&dtab, tab.size() * sizeof(void *)) != cudaSuccess) { cudaGetLastError(); return fail("out of device memory (pointer table)"); }
         CUDA_OK(cudaMemcpy(dtab, tab.data(), tab.size() * sizeof(void *), cudaMemcpyHostToDevice));
+        if (g.ptr_tables.size() >= 256) {          // bounded: evict the oldest table (its launches are complete or enqueued before this sync)
+            cudaStreamSynchronize(g.stream());
+            cudaFree(g.ptr_tables.front().second);
+            g.ptr_tables.erase(g.ptr_tables.begin());
+        }
         g.ptr_tables.emplace_back(tab, dtab);
     }
     const void **dt = (const void **)dtab;
@@ -1671,7 +1688,12 @@ int tmac_b200_gguf_close(int64_t gguf) {
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_gguf.find(gguf);
     if (it == g_gguf.end()) return fail("gguf_close: bad handle");
-    delete it->second;           // unmaps the file: weights uploaded from it stay resident, their host alias keys go stale
+    // the file is unmapped: weights uploaded from it stay resident, but their host alias keys (ranges inside the mapping)
+    // must not survive -- a later mapping can land on the same addresses and would resolve to the old tensor
+    const unsigned char *lo = it->second->base, *hi = lo + it->second->size;
+    for (auto &kv : g.res)
+        if (kv.second.host_a && kv.second.host_a >= lo && kv.second.host_a < hi) { kv.second.host_a = nullptr; kv.second.host_a_bytes = 0; }
+    delete it->second;
     g_gguf.erase(it);
     return 0;
 }

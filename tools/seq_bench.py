@@ -1,0 +1,83 @@
+"""Time the decode sequence kernel on the bench workload (32 distinct 11008x4096 W2 g128 zp tensors):
+independent inputs vs a true dependency chain (x_{i+1} = first K outputs of op i); optional per-op timeline.
+
+    python tools/seq_bench.py [--trace] [--layers 32] [--reps 20]
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "t-mac_b200")); sys.path.insert(0, ROOT)
+import torch                      # noqa: E402
+import tmac_b200 as tb            # noqa: E402
+import bench                      # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--trace", action="store_true")
+ap.add_argument("--layers", type=int, default=32)
+ap.add_argument("--reps", type=int, default=20)
+ap.add_argument("--bits", type=int, default=2)
+ap.add_argument("--mout", type=int, default=bench.MOUT)
+ap.add_argument("--k", type=int, default=bench.K)
+args = ap.parse_args()
+
+lib = tb.load(); tb.check(lib.tmac_b200_init(0), "init")
+st = torch.cuda.Stream(); torch.cuda.set_stream(st); tb.check(lib.tmac_b200_set_stream(st.cuda_stream), "set_stream")
+if args.trace:
+    tb.debug_set("trace", 1)
+L = args.layers
+w, sc, z = bench.synth(100, args.mout, args.k, args.bits, 128, True, False)
+bm = 256 if (args.mout * args.bits) % 256 == 0 else 128
+cfg = tb.make_kcfg(args.mout, args.k, args.bits, bm, 16, 128, 64, True, False)
+base = tb.upload_plain(cfg, w, sc, z)
+layers = [base] + [tb.clone(base) for _ in range(L - 1)]
+x = torch.randn((L, args.k), device="cuda").half().float()
+out = torch.zeros((L, args.mout), device="cuda")
+abytes = bench.algorithmic_bytes(args.mout, args.k, args.bits, 128, True)
+
+
+def timed(seq, reps):
+    for _ in range(3):
+        seq.launch()
+    seq.status()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(reps):
+        seq.launch()
+    e1.record(st); torch.cuda.synchronize()
+    seq.status()
+    return e0.elapsed_time(e1) / reps * 1e3
+
+
+for name, chained in (("independent inputs", False), ("dependent chain", True)):
+    if chained and args.k > args.mout:
+        continue
+    seq = tb.Sequence()
+    for i, wt in enumerate(layers):
+        if chained and i > 0:
+            seq.add(wt, in_op=i - 1, in_offset=0, out=out[i])
+        else:
+            seq.add(wt, x=x[i], out=out[i])
+    seq.build()
+    us = timed(seq, args.reps)
+    print("%-20s: %.1f us per launch of %d GEMVs = %.2f us per GEMV = %.0f GB/s (%.3f of 6588)  %s" %
+          (name, us, L, us / L, abytes * L / us / 1e3, abytes * L / us / 1e3 / 6588, seq.info()), flush=True)
+    if args.trace:
+        seq.launch(); seq.status()
+        t = seq.trace().astype(np.float64)          # [ops][grid][8] ns
+        t0 = t[0, :, 0].min()
+        ent, lut, mth, red, pub = (t[:, :, k] - t0 for k in range(5))
+        print("  per op (us, mean over CTAs / max): wait+LUT %.2f/%.2f  lookups %.2f/%.2f  reduce barrier %.2f/%.2f  publish %.2f/%.2f" % (
+            (lut - ent).mean() / 1e3, (lut - ent).max() / 1e3, (mth - lut).mean() / 1e3, (mth - lut).max() / 1e3,
+            (red - mth).mean() / 1e3, (red - mth).max() / 1e3, (pub - red).mean() / 1e3, (pub - red).max() / 1e3))
+        per_op = np.diff(pub.max(axis=1)) / 1e3
+        print("  op period (last CTA published -> next op's last): median %.2f us, min %.2f, max %.2f" % (np.median(per_op), per_op.min(), per_op.max()))
+        mid = min(L - 1, 10)
+        order = np.argsort(ent[mid])
+        print("  op %d timeline (us after launch) for 6 CTAs spread over the grid:" % mid)
+        for c in order[:: max(1, len(order) // 6)][:6]:
+            print("    cta %3d: enter %.2f  lut %.2f  lookups %.2f  reduced %.2f  published %.2f" % (c, ent[mid, c] / 1e3, lut[mid, c] / 1e3, mth[mid, c] / 1e3, red[mid, c] / 1e3, pub[mid, c] / 1e3))
+    seq.free()
