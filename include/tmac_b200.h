@@ -175,8 +175,9 @@ TMAC_B200_API int tmac_b200_seq_launch(int64_t seq);    /* asynchronous, on the 
 TMAC_B200_API int tmac_b200_seq_status(int64_t seq);    /* synchronises; 0 = ok, -1 = a bounded wait inside the kernel expired */
 /* info[8] = {grid, ring slots, slot bytes, shared-memory bytes, ops, planes/word, quads/chunk, quads/activation group} */
 TMAC_B200_API int tmac_b200_seq_info(int64_t seq, int *out8);
-/* Debug (tmac_b200_debug_set("trace", 1) before seq_build): globaltimer stamps [ops][grid][8] of the last launch:
- * 0 op entered, 1 LUT slices built, 2 lookups done (warp 0), 3 CTA reduced, 4 rows published.  Returns grid. */
+/* Debug (tmac_b200_debug_set("trace", 1) before seq_build): globaltimer stamps [ops][grid][16] of the last launch:
+ * 0 op entered, 1 own LUT work done, 2 first block resident, 3/5/4 lookups done (first / middle / last warp), 6 CTA sums read,
+ * 7 rows published, 8/9 producer thread enters / has requested the op.  Returns grid. */
 TMAC_B200_API int tmac_b200_seq_trace(int64_t seq, long long *dst, size_t cap_bytes);
 TMAC_B200_API int tmac_b200_seq_free(int64_t seq);
 /* Debug / parity gate G2: integer bit-plane sums CBits int32 [N][M*bits] in the reference
@@ -196,6 +197,7 @@ TMAC_B200_API int preprocessor_int8(int m, int k, int n, int b, void *B, void *L
 /* ---- ggml hook (3rdparty/llama.cpp/ggml/include/ggml-tmac.h:25-38).  The four entry points
  *      that take raw buffers keep their exact signatures; the four that take `ggml_tensor *`
  *      are offered ggml-free (shape arguments) -- INTEGRATION.md shows the 6-line shim. */
+#ifndef TMAC_B200_NO_GGML_DECLS   /* a translation unit that includes the reference's ggml-tmac.h takes these six from there */
 TMAC_B200_API void ggml_tmac_init(void);
 TMAC_B200_API void ggml_tmac_free(void);
 TMAC_B200_API void ggml_tmac_mul_mat_task_init(void *src1, void *qlut, void *lut_scales,
@@ -205,6 +207,7 @@ TMAC_B200_API void ggml_tmac_mul_mat_task_compute(void *src0, void *scales, void
                                                   int n, int k, int m, int bits);
 TMAC_B200_API void ggml_tmac_set_n_threads(int n_threads);
 TMAC_B200_API int ggml_tmac_get_type_bits(int ggml_type);           /* ggml-tmac.cpp:503-526 */
+#endif
 /* ggml-free forms of can_mul_mat / get_wsize / get_nbytes / transform_tensor */
 TMAC_B200_API int ggml_tmac_b200_can_mul_mat(int src0_type, int src1_is_f32, int dst_is_f32,
                                              const char *src0_name);

@@ -131,10 +131,10 @@ struct Sequence {
     seq_fn fn = nullptr;
     size_t smem = 0;
     SeqParams params{};
-    void *d_ops = nullptr, *d_y = nullptr, *d_xchg = nullptr, *d_epochs = nullptr, *d_err = nullptr, *d_trace = nullptr;
+    void *d_ops = nullptr, *d_ctas = nullptr, *d_lut = nullptr, *d_y = nullptr, *d_xchg = nullptr, *d_epochs = nullptr, *d_err = nullptr, *d_trace = nullptr;
     void release() {
-        for (void *q : {d_ops, d_y, d_xchg, d_epochs, d_err, d_trace}) if (q) cudaFree(q);
-        d_ops = d_y = d_xchg = d_epochs = d_err = d_trace = nullptr; built = false;
+        for (void *q : {d_ops, d_ctas, d_lut, d_y, d_xchg, d_epochs, d_err, d_trace}) if (q) cudaFree(q);
+        d_ops = d_ctas = d_lut = d_y = d_xchg = d_epochs = d_err = d_trace = nullptr; built = false;
     }
 };
 std::map<int64_t, Sequence> g_seqs;
@@ -1303,8 +1303,10 @@ int tmac_b200_seq_build(int64_t seq) {
     const int n = (int)S.ops.size();
     std::vector<SeqOp> ops(n);
     std::vector<size_t> yoff(n);
-    size_t ytot = 0, red_b = 0, tab_b = 0, lsb_b = 0, slot_b = 0;
+    size_t ytot = 0, red_b = 0, tab_b = 0, lsb_b = 0, slot_b = 0, yfin_b = 0, ltot = 0;
     int rsbmax = 0;
+    std::vector<size_t> loff(n, (size_t)-1);       // LUT hand-over records of op i (only if an aligned consumer exists)
+    const bool handover = getenv("TMAC_B200_SEQ_HANDOVER") ? atoi(getenv("TMAC_B200_SEQ_HANDOVER")) != 0 : true;
     for (int i = 0; i < n; ++i) {
         auto rt = g.res.find(S.ops[i].handle);
         if (rt == g.res.end()) return fail("seq_build: a weight handle was freed");
@@ -1321,6 +1323,16 @@ int tmac_b200_seq_build(int64_t seq) {
         const int ntab = std::min(per, L.nchunk);
         const int nag = L.qch / agq;
         red_b = std::max(red_b, (size_t)nseg * kSeqWarps * L.rsb * 4);
+        yfin_b = std::max(yfin_b, (size_t)nseg * L.rsb * 4);
+        if (!S.ops[i].x_ext && handover) {   // consumer of an earlier op: can it take ready-made LUT records?
+            const int src = S.ops[i].in_op;
+            const StreamLayout &PL = g.res.find(S.ops[src].handle)->second.L;
+            if (S.ops[i].in_off % L.act_group_size == 0 && PL.rsb % L.act_group_size == 0 && loff[src] == (size_t)-1) {
+                loff[src] = ltot;
+                const size_t rows = (size_t)PL.nrsb * PL.rsb;
+                ltot += ((rows / 4 + rows / L.act_group_size) * sizeof(uint4) + 255) & ~(size_t)255;
+            }
+        }
         tab_b = std::max(tab_b, (size_t)ntab * L.qch * 4 * 8);
         lsb_b = std::max(lsb_b, (size_t)ntab * 2 * nag * 4);
         slot_b = std::max(slot_b, (L.blk + 127) & ~(size_t)127);
@@ -1329,21 +1341,22 @@ int tmac_b200_seq_build(int64_t seq) {
         ytot += ((size_t)L.nrsb * L.rsb * sizeof(uint2) + 255) & ~(size_t)255;
     }
     const size_t budget = 227 * 1024;
-    const size_t fixed = ((red_b + 15) & ~(size_t)15) + ((tab_b + 15) & ~(size_t)15) + ((lsb_b + 15) & ~(size_t)15) + 64 * 8 + (kSeqWarps + 1) * 4 + 64;
+    const size_t fixed = ((red_b + 15) & ~(size_t)15) + ((tab_b + 15) & ~(size_t)15) + ((lsb_b + 15) & ~(size_t)15) + ((yfin_b + 15) & ~(size_t)15) + 64 * 8 + (kSeqWarps + 1) * 4 + 64 + 2 * kSeqDescWords * 4;
     if (fixed + 4 * slot_b > budget) return fail("seq_build: shared-memory budget exceeded");
     const int nslots = (int)std::min<size_t>(64, (budget - fixed) / slot_b);
     S.fn = pick_seq(S.pb, S.qch, S.agq);
     if (!S.fn) return fail("seq_build: chunking not instantiated");
     S.grid = G;
     const size_t xper = (size_t)G * rsbmax * sizeof(uint2);
-    if (cudaMalloc(&S.d_ops, n * sizeof(SeqOp)) != cudaSuccess || cudaMalloc(&S.d_y, ytot) != cudaSuccess ||
-        cudaMalloc(&S.d_xchg, xper * n) != cudaSuccess || cudaMalloc(&S.d_epochs, G * sizeof(unsigned)) != cudaSuccess ||
+    if (cudaMalloc(&S.d_ops, n * sizeof(SeqOp)) != cudaSuccess || cudaMalloc(&S.d_ctas, (size_t)n * G * sizeof(SeqCta)) != cudaSuccess || cudaMalloc(&S.d_y, ytot) != cudaSuccess ||
+        cudaMalloc(&S.d_xchg, xper * n) != cudaSuccess || cudaMalloc(&S.d_lut, std::max<size_t>(ltot, 256)) != cudaSuccess || cudaMalloc(&S.d_epochs, G * sizeof(unsigned)) != cudaSuccess ||
         cudaMalloc(&S.d_err, sizeof(int)) != cudaSuccess) { cudaGetLastError(); S.release(); return fail("seq_build: out of device memory"); }
     if (g.trace) {
-        if (cudaMalloc(&S.d_trace, (size_t)n * G * 8 * sizeof(long long)) != cudaSuccess) { cudaGetLastError(); S.release(); return fail("seq_build: out of device memory (trace)"); }
-        cudaMemset(S.d_trace, 0, (size_t)n * G * 8 * sizeof(long long));
+        if (cudaMalloc(&S.d_trace, (size_t)n * G * (16 + 8 * kSeqWarps) * sizeof(long long)) != cudaSuccess) { cudaGetLastError(); S.release(); return fail("seq_build: out of device memory (trace)"); }
+        cudaMemset(S.d_trace, 0, (size_t)n * G * (16 + 8 * kSeqWarps) * sizeof(long long));
     }
     CUDA_OK(cudaMemset(S.d_y, 0, ytot));
+    CUDA_OK(cudaMemset(S.d_lut, 0, std::max<size_t>(ltot, 256)));
     CUDA_OK(cudaMemset(S.d_xchg, 0, xper * n));
     CUDA_OK(cudaMemset(S.d_epochs, 0, G * sizeof(unsigned)));
     CUDA_OK(cudaMemset(S.d_err, 0, sizeof(int)));
@@ -1362,16 +1375,59 @@ int tmac_b200_seq_build(int64_t seq) {
         o.blk_bytes = (int)L.blk; o.total = L.nrsb * L.nchunk;
         o.zp = L.zp; o.one_scale = L.one_scale; o.sd = L.sd; o.out_f16 = S.ops[i].out_f16;
         o.scale0 = L.scale0; o.geff = std::min(G, o.total);
+        o.lut_out = o.ag_out = nullptr; o.lut_in = o.ag_in = nullptr;
+        if (loff[i] != (size_t)-1) {
+            o.lut_out = (uint4 *)((char *)S.d_lut + loff[i]);
+            o.ag_out = o.lut_out + (size_t)L.nrsb * L.rsb / 4;
+        }
+        if (!S.ops[i].x_ext && handover) {
+            const int src = S.ops[i].in_op;
+            const StreamLayout &PL = g.res.find(S.ops[src].handle)->second.L;
+            if (loff[src] != (size_t)-1 && S.ops[i].in_off % L.act_group_size == 0 && PL.rsb % L.act_group_size == 0) {
+                const uint4 *base = (const uint4 *)((char *)S.d_lut + loff[src]);
+                o.lut_in = base + S.ops[i].in_off / 4;
+                o.ag_in = base + (size_t)PL.nrsb * PL.rsb / 4 + S.ops[i].in_off / L.act_group_size;
+            }
+        }
     }
     CUDA_OK(cudaMemcpy(S.d_ops, ops.data(), n * sizeof(SeqOp), cudaMemcpyHostToDevice));
+    {   // per (op, CTA) shares: blocks [T*c/GE, T*(c+1)/GE) in (row super-block, chunk) order
+        std::vector<SeqCta> ct((size_t)n * G);
+        const int pmax = std::max(1, nslots / 2);
+        for (int i = 0; i < n; ++i) {
+            const long T = ops[i].total, GE = ops[i].geff, nc = ops[i].nchunk;
+            auto first_block = [&](long c) { return T * c / GE; };
+            for (int c = 0; c < G; ++c) {
+                SeqCta &q = ct[(size_t)i * G + c];
+                std::memset(&q, 0, sizeof q);
+                q.fc = c;
+                if (c >= GE) continue;
+                const long b0 = first_block(c), b1 = first_block(c + 1);
+                q.b0 = (int)b0; q.nb = (int)(b1 - b0);
+                q.sb_first = (int)(b0 / nc); q.c0 = (int)(b0 % nc);
+                q.nseg = (int)((b1 - 1) / nc - b0 / nc + 1);
+                q.nck = (int)std::min<long>(q.nb, nc);
+                q.npass = (q.nb + pmax - 1) / pmax;
+                q.P = (q.nb + q.npass - 1) / q.npass;
+                q.last_open = (b1 % nc) != 0;                     // my last super-block continues in CTA c + 1
+                int fc = c;                                       // CTA that owns the first block of my first super-block
+                while (fc > 0 && first_block(fc) > (long)q.sb_first * nc) --fc;
+                q.fc = fc;
+            }
+        }
+        CUDA_OK(cudaMemcpy(S.d_ctas, ct.data(), ct.size() * sizeof(SeqCta), cudaMemcpyHostToDevice));
+    }
     SeqParams &P = S.params;
-    P.ops = (const SeqOp *)S.d_ops; P.nops = n; P.nslots = nslots; P.slot_bytes = (int)slot_b;
+    P.ops = (const SeqOp *)S.d_ops; P.ctas = (const SeqCta *)S.d_ctas; P.nops = n; P.nslots = nslots; P.slot_bytes = (int)slot_b;
     size_t off = (size_t)nslots * slot_b;
     P.red_off = (int)off; off += (red_b + 15) & ~(size_t)15;
     P.tab_off = (int)off; off += (tab_b + 15) & ~(size_t)15;
     P.lsb_off = (int)off; off += (lsb_b + 15) & ~(size_t)15;
     P.bar_off = (int)off; off += (size_t)nslots * 8;
     P.prog_off = (int)off; off += (kSeqWarps + 1) * 4;   // + the producer's `issued` counter
+    off = (off + 15) & ~(size_t)15;
+    P.yfin_off = (int)off; off += (yfin_b + 15) & ~(size_t)15;
+    P.desc_off = (int)off; off += 2 * kSeqDescWords * 4;
     P.epochs = (unsigned *)S.d_epochs; P.err = (int *)S.d_err; P.trace = (long long *)S.d_trace;
     S.smem = off;
     CUDA_OK(cudaFuncSetAttribute((const void *)S.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.smem));
@@ -1429,7 +1485,7 @@ int tmac_b200_seq_trace(int64_t seq, long long *dst, size_t cap_bytes) {
     auto it = g_seqs.find(seq);
     if (it == g_seqs.end() || !it->second.built || !it->second.d_trace) return fail("seq_trace: tracing was not enabled when the sequence was built");
     CUDA_OK(cudaStreamSynchronize(g.stream()));
-    const size_t bytes = std::min(cap_bytes, it->second.ops.size() * (size_t)it->second.grid * 8 * sizeof(long long));
+    const size_t bytes = std::min(cap_bytes, it->second.ops.size() * (size_t)it->second.grid * (16 + 8 * kSeqWarps) * sizeof(long long));
     CUDA_OK(cudaMemcpy(dst, it->second.d_trace, bytes, cudaMemcpyDeviceToHost));
     return it->second.grid;
 }

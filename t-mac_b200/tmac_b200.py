@@ -253,9 +253,11 @@ class Sequence:
     def trace(self):
         import numpy as np
         inf = self.info()
-        buf = np.zeros((inf["ops"], inf["grid"], 8), np.int64)
+        n, g = inf["ops"], inf["grid"]
+        buf = np.zeros(n * g * (16 + 8 * 20), np.int64)
         check(load().tmac_b200_seq_trace(self.h, buf.ctypes.data, buf.nbytes), "tmac_b200_seq_trace")
-        return buf
+        self.warp_trace = buf[n * g * 16:].reshape(n, g, 20, 8)      # per warp: enter, LUT done, first block resident, lookups done, rows done
+        return buf[:n * g * 16].reshape(n, g, 16)
 
     def free(self):
         if self.h > 0:

@@ -67,17 +67,30 @@ for name, chained in (("independent inputs", False), ("dependent chain", True)):
           (name, us, L, us / L, abytes * L / us / 1e3, abytes * L / us / 1e3 / 6588, seq.info()), flush=True)
     if args.trace:
         seq.launch(); seq.status()
-        t = seq.trace().astype(np.float64)          # [ops][grid][8] ns
+        t = seq.trace().astype(np.float64) / 1e3    # [ops][grid][16] us
         t0 = t[0, :, 0].min()
-        ent, lut, mth, red, pub = (t[:, :, k] - t0 for k in range(5))
-        print("  per op (us, mean over CTAs / max): wait+LUT %.2f/%.2f  lookups %.2f/%.2f  reduce barrier %.2f/%.2f  publish %.2f/%.2f" % (
-            (lut - ent).mean() / 1e3, (lut - ent).max() / 1e3, (mth - lut).mean() / 1e3, (mth - lut).max() / 1e3,
-            (red - mth).mean() / 1e3, (red - mth).max() / 1e3, (pub - red).mean() / 1e3, (pub - red).max() / 1e3))
-        per_op = np.diff(pub.max(axis=1)) / 1e3
-        print("  op period (last CTA published -> next op's last): median %.2f us, min %.2f, max %.2f" % (np.median(per_op), per_op.min(), per_op.max()))
+        ent, lut, res, m0, mL, mM, sums, pub, pr0, pr1 = (t[:, :, k] - t0 for k in range(10))
+        mlast = np.maximum(np.maximum(m0, mL), mM)
+        print("  cycles waiting for weights per op: warp 0 median %.0f max %.0f | last warp median %.0f max %.0f" % (np.median(t[:, :, 10]) * 1e3, t[:, :, 10].max() * 1e3, np.median(t[:, :, 11]) * 1e3, t[:, :, 11].max() * 1e3))
+
+        def fmt(a):
+            return "%.2f/%.2f/%.2f" % (np.median(a), np.percentile(a, 90), a.max())
+        print("  per (op, CTA) us, median/p90/max:  enter->own LUT done %s | ->first block resident (bar A + weights) %s | lookups warp0 %s, last of 3 sampled warps %s | bar B + sums %s | publish/finish %s" % (
+            fmt(lut - ent), fmt(res - lut), fmt(m0 - res), fmt(mlast - res), fmt(sums - mlast), fmt(pub - sums)))
+        print("  producer lead (consumers enter op - producer finished requesting it): median %.2f min %.2f us" % (np.median((ent - pr1)[1:]), (ent - pr1)[1:].min()))
+        per_op = np.diff(pub.max(axis=1))
+        print("  op period: median %.2f us (min %.2f, max %.2f); spread of 'enter' across CTAs: median %.2f us; of 'lookups done': %.2f us" % (
+            np.median(per_op), per_op.min(), per_op.max(), np.median(ent.max(axis=1) - ent.min(axis=1)), np.median(mlast.max(axis=1) - mlast.min(axis=1))))
         mid = min(L - 1, 10)
+        wt_ = seq.warp_trace.astype(np.float64) / 1e3 - t0
+        for c in (np.argsort(ent[mid])[len(ent[mid]) // 2], np.argsort(pub[mid])[-1]):
+            print("  op %d cta %d per warp (enter / LUT done / first block / lookups done / rows done), us:" % (mid, c))
+            for w in range(20):
+                cb = seq.warp_trace[mid, c, :, 5].min()
+                print("    w%02d %s   clock64 rel. to first arrival: arrive bar A %6d, released %6d, before weight wait %6d" % (w, "  ".join("%7.2f" % v for v in wt_[mid, c, w, :5]), seq.warp_trace[mid, c, w, 5] - cb, seq.warp_trace[mid, c, w, 6] - cb, seq.warp_trace[mid, c, w, 7] - cb))
         order = np.argsort(ent[mid])
-        print("  op %d timeline (us after launch) for 6 CTAs spread over the grid:" % mid)
+        print("  op %d timeline (us after launch), 6 CTAs:" % mid)
         for c in order[:: max(1, len(order) // 6)][:6]:
-            print("    cta %3d: enter %.2f  lut %.2f  lookups %.2f  reduced %.2f  published %.2f" % (c, ent[mid, c] / 1e3, lut[mid, c] / 1e3, mth[mid, c] / 1e3, red[mid, c] / 1e3, pub[mid, c] / 1e3))
+            print("    cta %3d: enter %.2f  lut %.2f  resident %.2f  lookups(w0/mid/last) %.2f/%.2f/%.2f  sums %.2f  published %.2f" % (
+                c, ent[mid, c], lut[mid, c], res[mid, c], m0[mid, c], mM[mid, c], mL[mid, c], sums[mid, c], pub[mid, c]))
     seq.free()
