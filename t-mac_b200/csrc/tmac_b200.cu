@@ -24,7 +24,6 @@
 #include "tmac_kernels.cuh"
 #include "tmac_prefill.cuh"
 #include "tmac_prefill16.cuh"
-#include "tmac_gemv4.cuh"
 #include "tmac_seq.cuh"
 #include "tmac_layout.h"
 #include "tmac_gguf.h"
@@ -87,15 +86,12 @@ struct Context {
     bool use_user = false;
     int float_type = TMAC_B200_F32;
     int lut_mode = 0;                    // 0 auto, 1 general, 2 symmetric
-    int ks_override = 0;
-    int kernel_version = 3;              // 3 = gemv3_kernel (clusters + DSMEM + PDL), 1 = gemv_kernel (split-K scratch)
     int use_pdl = 1;
     int cs_override = 0, wpc_override = 0, pdl_late = -1, minb_override = 0, nbuf_override = 0;
     int last_launch[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int use_fused = 1;
+    int seq_smem_kb = 200;               // decode sequences: shared-memory budget; the rest of the 228 KB stays L1 (descriptor / polling loads, spills)
     int seq_grid = 0;                    // decode sequences: grid override (tests: CTA-boundary placements); 0 = one CTA per SM
-    int use_g4 = 0, g4_grid = 0;         // lone launches: stream-K kernel (0 off, 1 auto, 2 whenever the shape allows); grid override
-    std::map<cudaStream_t, void *> xchg; // gemv4 exchange slots, one buffer per stream that ever launched it
     int use_prefill16 = 0;               // DRAFT fp16-operand prefill tile (tmac_prefill16.cuh), opt-in until validated on hardware
     int use_prefill = 1, prefill_min_n = 32;   // N >= prefill_min_n: tcgen05 int8 tile (W2 g128 act64)                   // tmac_b200_gemv builds the LUT inside the GEMV when the grouping allows
     int64_t next_hint = 0;               // one-shot: tensor whose blocks the next launch prefetches into L2
@@ -105,12 +101,11 @@ struct Context {
     std::set<const void *> sym_qluts;    // device QLUT buffers last written by our preprocessor
     std::vector<std::pair<std::vector<const void *>, void *>> ptr_tables;   // grouped-launch pointer tables
     // workspaces
-    DevBuf d_b, d_qlut, d_ls, d_lb, d_c, d_part, d_cnt, d_cbits, d_trace, d_tiles;
+    DevBuf d_b, d_qlut, d_ls, d_lb, d_c, d_cbits, d_trace, d_tiles;
     int trace = 0, trace_ctas = 0, trace_seq = 0;
     PinBuf h_in, h_out;
     cudaEvent_t stage_ev = nullptr;      // last H2D that read h_in
     bool stage_pending = false;
-    size_t cnt_zeroed = 0;
     cudaStream_t stream() const { return use_user ? user : own; }
 };
 
@@ -175,9 +170,7 @@ int ensure_init() {
     if (prop.major < 10) return fail("libtmac_b200 is built for sm_100a only (found sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + ")");
     g.sms = prop.multiProcessorCount;
     CUDA_OK(cudaStreamCreate(&g.own));   // blocking stream: ordered after the legacy default stream (safe default for torch/ggml callers)
-    if (const char *e = getenv("TMAC_B200_KS")) g.ks_override = atoi(e);
     if (const char *e = getenv("TMAC_B200_LUT_MODE")) g.lut_mode = atoi(e);
-    if (const char *e = getenv("TMAC_B200_KERNEL")) g.kernel_version = atoi(e);
     if (const char *e = getenv("TMAC_B200_PDL")) g.use_pdl = atoi(e);
     if (const char *e = getenv("TMAC_B200_TRACE")) g.trace = atoi(e);
     if (const char *e = getenv("TMAC_B200_CS")) g.cs_override = atoi(e);
@@ -189,30 +182,11 @@ int ensure_init() {
     if (const char *e = getenv("TMAC_B200_PREFILL_MIN_N")) g.prefill_min_n = atoi(e);
     if (const char *e = getenv("TMAC_B200_WPC")) g.wpc_override = atoi(e);
     if (const char *e = getenv("TMAC_B200_NBUF")) g.nbuf_override = atoi(e);
-    if (const char *e = getenv("TMAC_B200_G4")) g.use_g4 = atoi(e);
-    if (const char *e = getenv("TMAC_B200_G4_GRID")) g.g4_grid = atoi(e);
     g.inited = true;
     return 0;
 }
 
 // ---- kernel dispatch ---------------------------------------------------------------------
-typedef void (*gemv_fn)(const GemvParams, const uint32_t, const uint32_t);
-
-template <int PB, bool SYM> gemv_fn pick_qch(int qch) {
-    switch (qch) {
-        case 2: return gemv_kernel<PB, SYM, 2>;
-        case 4: return gemv_kernel<PB, SYM, 4>;
-        case 8: return gemv_kernel<PB, SYM, 8>;
-    }
-    return nullptr;
-}
-gemv_fn pick_gemv(int pb, bool sym, int qch) {
-    if (pb == 4) return sym ? pick_qch<4, true>(qch) : pick_qch<4, false>(qch);
-    if (pb == 2) return sym ? pick_qch<2, true>(qch) : pick_qch<2, false>(qch);
-    if (pb == 1) return sym ? pick_qch<1, true>(qch) : pick_qch<1, false>(qch);
-    return nullptr;
-}
-
 typedef void (*gemv3_fn)(const Gemv3Params, const uint32_t, const uint32_t);
 template <int PB, bool SYM, int MINB> gemv3_fn pick3_qa(int qch, int agq) {
     switch (qch * 16 + agq) {
@@ -288,17 +262,10 @@ void choose_decomposition(int nrsb, int nchunk, int N, int *cs_out, int *wpc_out
 struct BatchPtrs { int n = 0; const unsigned char *const *W = nullptr; const int8_t *const *q = nullptr; const float *const *ls = nullptr,
                    *const *lb = nullptr; void *const *C = nullptr; };
 
-int launch_gemv4(const Resident &R, int row_begin, int row_end, const int8_t *qlut, const float *ls, const float *lb, void *C,
-                 int c_row0, int out_f16, bool sym, const void *fused_act, int act_f16);
-
 int launch_gemv3(const Resident &R, int row_begin, int row_end, int N, const int8_t *qlut, const float *ls, const float *lb, void *C,
                  int ldc, int c_row0, int out_f16, bool sym, const BatchPtrs *batch = nullptr, const void *fused_act = nullptr,
                  int act_f16 = 0) {
     const StreamLayout &L = R.L;
-    if (N == 1 && !batch) {   // one tensor, one activation row: the stream-K kernel when the shape is worth it
-        const int rc = launch_gemv4(R, row_begin, row_end, qlut, ls, lb, C, c_row0, out_f16, sym, fused_act, act_f16);
-        if (rc <= 0) return rc;
-    }
     if (row_begin < 0 || row_end > L.Mout || row_begin >= row_end) return fail("qgemm_lut: bad row range");
     const int rsb0 = row_begin / L.rsb, rsb1 = (row_end + L.rsb - 1) / L.rsb, nrsb = rsb1 - rsb0;
     const bool int_path = L.one_scale && L.act_group_size == L.K;
@@ -373,90 +340,6 @@ int launch_gemv3(const Resident &R, int row_begin, int row_end, int N, const int
     return 0;
 }
 
-// Lone launch (N = 1, one tensor): stream-K grid, one CTA per SM per launch (gemv4_kernel, tmac_gemv4.cuh).
-// Returns 1 when the shape is left to gemv3 (small tensors, chunkings that are not instantiated, shares that do not
-// fit two CTAs per SM), 0 on launch, -1 on error.
-constexpr size_t kG4SmemBudget = 112 * 1024;   // two CTAs per SM: 2 * (budget + 1 KB reserved) <= 227 KB
-int launch_gemv4(const Resident &R, int row_begin, int row_end, const int8_t *qlut, const float *ls, const float *lb, void *C,
-                 int c_row0, int out_f16, bool sym, const void *fused_act, int act_f16) {
-    const StreamLayout &L = R.L;
-    if (!g.use_g4 || g.kernel_version != 3) return 1;
-    if (row_begin < 0 || row_end > L.Mout || row_begin >= row_end) return fail("qgemm_lut: bad row range");
-    const int rsb0 = row_begin / L.rsb, rsb1 = (row_end + L.rsb - 1) / L.rsb, nrsb = rsb1 - rsb0;
-    const long total = (long)nrsb * L.nchunk;
-    if (g.use_g4 == 1 && (total < 4L * g.sms || L.nchunk < 4)) return 1;
-    const bool int_path = L.one_scale && L.act_group_size == L.K;
-    const int agq = int_path ? 0 : std::min(L.act_group_size, L.ck) / 16;
-    if (fused_act) sym = true;
-    gemv4_fn fn = pick_gemv4(L.pb, sym, L.qch, agq, fused_act != nullptr);
-    if (!fn) return 1;
-    const int tab = L.qch * 4 * (sym ? 8 : 16);
-    int G = 0, per = 0, nseg = 0, ntab = 0; size_t stage = 0, smem = 0;
-    const long cands[3] = {g.g4_grid > 0 ? std::min<long>(g.g4_grid, 2L * g.sms) : 0L, (long)g.sms, 2L * g.sms};
-    for (long cl : cands) {
-        if (cl <= 0) continue;
-        const int cand = (int)std::min(cl, total);
-        const int per_c = (int)((total + cand - 1) / cand);
-        const int nseg_c = (per_c - 1 + L.nchunk - 1) / L.nchunk + 1;
-        const size_t stage_c = ((size_t)per_c * L.blk + 127) & ~(size_t)127;
-        const int ntab_c = std::min(per_c, L.nchunk);
-        const size_t smem_c = stage_c + (size_t)nseg_c * kG4Warps * L.rsb * 4 + (size_t)ntab_c * (tab + 5 * 4) + kG4Warps * 8;
-        if (smem_c <= kG4SmemBudget) { G = cand; per = per_c; nseg = nseg_c; stage = stage_c; smem = smem_c; ntab = ntab_c; break; }
-    }
-    if (!G) return 1;
-    void *&xchg = g.xchg[g.stream()];
-    if (!xchg) {   // first use on this stream (not capturable: run once before capturing a graph)
-        const size_t bytes = (size_t)2 * g.sms * kG4MaxRsb * sizeof(uint2);
-        if (cudaMalloc(&xchg, bytes) != cudaSuccess) { cudaGetLastError(); xchg = nullptr; return fail("out of device memory (exchange slots)"); }
-        CUDA_OK(cudaMemset(xchg, 0, bytes));
-    }
-    Gemv4Params p{};
-    p.W = R.d + (size_t)rsb0 * L.rsb_stride;
-    p.Wnext = nullptr;
-    if (g.next_hint) {
-        auto it = g.res.find(g.next_hint);
-        if (it != g.res.end() && it->second.L.total == L.total && it->second.L.blk == L.blk) p.Wnext = it->second.d + (size_t)rsb0 * L.rsb_stride;
-        g.next_hint = 0;
-    }
-    p.qlut = qlut; p.lut_scales = ls; p.lut_biases = lb; p.C = C; p.act = fused_act; p.act_f16 = act_f16;
-    p.K = L.K; p.row_begin = row_begin; p.row_end = row_end; p.c_row0 = c_row0;
-    p.nrsb = nrsb; p.rsb0 = rsb0; p.nchunk = L.nchunk; p.ags = L.act_group_size;
-    p.zp = L.zp; p.one_scale = L.one_scale; p.sd = L.sd; p.out_f16 = out_f16; p.blk_bytes = (int)L.blk;
-    p.total = (int)total; p.per_max = per; p.nseg_max = nseg; p.stage_bytes = (int)stage; p.ntab = ntab;
-    p.rsb_stride = L.rsb_stride; p.scale0 = L.scale0; p.xchg = (uint2 *)xchg;
-    g.last_launch[0] = 0; g.last_launch[1] = kG4Warps; g.last_launch[2] = per; g.last_launch[3] = 2;
-    g.last_launch[4] = G; g.last_launch[5] = L.pb; g.last_launch[6] = sym ? 1 : 0; g.last_launch[7] = 1;
-    if (g.trace) {   // ring of 8 launches
-        const size_t pl = (size_t)G * 8;
-        if (g.d_trace.ensure(std::max((size_t)8192, pl * 8 * sizeof(long long)))) return fail("out of device memory (trace)");
-        p.trace = (long long *)g.d_trace.p + pl * (size_t)(g.trace_seq++ % 8);
-        g.trace_ctas = G;
-    }
-    if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    uint32_t wtx, wty;
-    plane_weight_regs(L.bits, sym, &wtx, &wty);
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(G, 1, 1);
-    cfg.blockDim = dim3(kG4Warps * 32, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = g.stream();
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = g.use_pdl ? 1 : 0;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    CUDA_OK(cudaLaunchKernelEx(&cfg, fn, p, wtx, wty));
-    return 0;
-}
-
-int choose_ks(const StreamLayout &L, int nrsb, int N) {
-    if (g.ks_override > 0) return std::max(1, std::min(g.ks_override, L.nchunk));
-    const int target = 2 * g.sms;
-    int ks = (target + nrsb * N - 1) / (nrsb * N);
-    const int max_ks = std::max(1, L.nchunk / 8);      // >= one chunk per warp per split
-    ks = std::max(1, std::min(ks, std::min(max_ks, 16)));
-    return ks;
-}
-
 // Prefill tile on tcgen05 (tmac_prefill.cuh).  Returns 1 if the shape is not covered (caller falls back to the GEMV
 // kernel per activation row), 0 on launch, -1 on error.
 int launch_prefill(const Resident &R, int N, const int8_t *qlut, const float *ls, const float *lb, void *C, int ldc, int out_f16, bool sym) {
@@ -508,59 +391,16 @@ int launch_prefill(const Resident &R, int N, const int8_t *qlut, const float *ls
     return 0;
 }
 
-// v1 launch (one CTA per (super-block, K split); kept for A/B comparison: TMAC_B200_KERNEL=1).
-// Launch qgemm_lut over rows [row_begin,row_end) (relative to the resident tensor).
-// All pointers are device pointers; C is [N][ldc] with C[n][row - c_row0].
+// Launch qgemm_lut over rows [row_begin,row_end) (relative to the resident tensor): the tcgen05 tile for whole-tensor batches,
+// else gemv3_kernel.  All pointers are device pointers; C is [N][ldc] with C[n][row - c_row0].
 int launch_gemv(const Resident &R, int row_begin, int row_end, int N, const int8_t *qlut, const float *ls,
                 const float *lb, void *C, int ldc, int c_row0, int out_f16, bool sym, int32_t *cbits_unused) {
     (void)cbits_unused;
-    if (g.kernel_version != 1 && row_begin == 0 && row_end == R.L.Mout && c_row0 == 0 && ldc == R.L.Mout) {
+    if (row_begin == 0 && row_end == R.L.Mout && c_row0 == 0 && ldc == R.L.Mout) {
         const int rc = launch_prefill(R, N, qlut, ls, lb, C, ldc, out_f16, sym);
         if (rc <= 0) return rc;
     }
-    if (g.kernel_version != 1) return launch_gemv3(R, row_begin, row_end, N, qlut, ls, lb, C, ldc, c_row0, out_f16, sym);
-    const StreamLayout &L = R.L;
-    if (row_begin < 0 || row_end > L.Mout || row_begin >= row_end) return fail("qgemm_lut: bad row range");
-    const int rsb0 = row_begin / L.rsb, rsb1 = (row_end + L.rsb - 1) / L.rsb, nrsb = rsb1 - rsb0;
-    const bool int_path = L.one_scale && L.act_group_size == L.K;
-    GemvParams p{};
-    p.W = R.d + (size_t)rsb0 * L.rsb_stride;
-    p.qlut = qlut; p.lut_scales = ls; p.lut_biases = lb; p.C = C;
-    p.K = L.K; p.N = N; p.ldc = ldc;
-    p.row_begin = row_begin; p.row_end = row_end; p.c_row0 = c_row0;
-    p.bits = L.bits; p.nrsb = nrsb; p.rsb0 = rsb0;
-    p.nchunk = L.nchunk; p.ags = L.act_group_size; p.ck = L.ck;
-    p.zp = L.zp; p.one_scale = L.one_scale; p.int_path = int_path ? 1 : 0; p.sd = L.sd; p.out_f16 = out_f16;
-    p.rsb_stride = L.rsb_stride; p.blk_stride = L.blk; p.scale0 = L.scale0;
-    p.ks = choose_ks(L, nrsb, N);
-    if (p.ks > 1) {
-        const size_t part_bytes = (size_t)N * p.ks * nrsb * L.rsb * sizeof(float);
-        const size_t cnt_bytes = (size_t)N * nrsb * sizeof(int);
-        if (g.d_part.ensure(part_bytes)) return fail("out of device memory (split-K scratch)");
-        if (cnt_bytes > g.d_cnt.cap || g.cnt_zeroed < cnt_bytes) {
-            if (g.d_cnt.ensure(cnt_bytes)) return fail("out of device memory (counters)");
-            CUDA_OK(cudaMemsetAsync(g.d_cnt.p, 0, g.d_cnt.cap, g.stream()));
-            g.cnt_zeroed = g.d_cnt.cap;
-        }
-        p.partial = (float *)g.d_part.p;
-        p.counters = (int *)g.d_cnt.p;
-    }
-    gemv_fn fn = pick_gemv(L.pb, sym, L.qch);
-    if (!fn) return fail("qgemm_lut: unsupported chunking (qch=" + std::to_string(L.qch) + ")");
-    // shared memory: tables + lut scales + chunk biases + cross-warp reduction
-    const int cmax = (L.nchunk + p.ks - 1) / p.ks + 1;
-    const size_t smem = (size_t)cmax * L.qch * 4 * (sym ? 8 : 16) + (size_t)(cmax * L.ck / std::min(L.ck, L.act_group_size) + 2) * 4 +
-                        (size_t)cmax * 4 + (size_t)kGemvWarps * L.rsb * 4 + 64;
-    if (smem > 48 * 1024) {
-        if (smem > 227 * 1024) return fail("qgemm_lut: K too large for the shared-memory LUT (" + std::to_string(smem) + " B)");
-        CUDA_OK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
-    uint32_t wtx, wty;
-    plane_weight_regs(L.bits, sym, &wtx, &wty);
-    dim3 grid(nrsb, p.ks, N);
-    fn<<<grid, kGemvThreads, smem, g.stream()>>>(p, wtx, wty);
-    CUDA_OK(cudaGetLastError());
-    return 0;
+    return launch_gemv3(R, row_begin, row_end, N, qlut, ls, lb, C, ldc, c_row0, out_f16, sym);
 }
 
 int launch_preprocessor(int K, int N, int ags, int dtype, const void *B, float *ls, float *lb, int8_t *qlut) {
@@ -699,8 +539,6 @@ void tmac_b200_shutdown(void) {
     g_seqs.clear();
     for (auto &kv : g_graphs) cudaGraphExecDestroy(kv.second);
     g_graphs.clear();
-    for (auto &kv : g.xchg) if (kv.second) cudaFree(kv.second);
-    g.xchg.clear();
     for (auto &e : g.ptr_tables) if (e.second) cudaFree(e.second);
     g.ptr_tables.clear();
     for (auto &kv : g_gguf) delete kv.second;
@@ -711,12 +549,12 @@ void tmac_b200_shutdown(void) {
         std::free(kv.second.host_scales);
     }
     g.res.clear();
-    for (DevBuf *b : {&g.d_b, &g.d_qlut, &g.d_ls, &g.d_lb, &g.d_c, &g.d_part, &g.d_cnt, &g.d_cbits, &g.d_trace, &g.d_tiles}) { if (b->p) cudaFree(b->p); b->p = nullptr; b->cap = 0; }
+    for (DevBuf *b : {&g.d_b, &g.d_qlut, &g.d_ls, &g.d_lb, &g.d_c, &g.d_cbits, &g.d_trace, &g.d_tiles}) { if (b->p) cudaFree(b->p); b->p = nullptr; b->cap = 0; }
     for (PinBuf *b : {&g.h_in, &g.h_out}) { if (b->p) cudaFreeHost(b->p); b->p = nullptr; b->cap = 0; }
     if (g.stage_ev) cudaEventDestroy(g.stage_ev);
     g.stage_ev = nullptr; g.stage_pending = false;
     if (g.own) cudaStreamDestroy(g.own);
-    g.own = nullptr; g.cnt_zeroed = 0; g.sym_qluts.clear();
+    g.own = nullptr; g.sym_qluts.clear();
     g.user = nullptr; g.use_user = false; g.trace_ctas = 0; g.trace_seq = 0; g.next_hint = 0;
     g.inited = false;
 }
@@ -1038,10 +876,9 @@ int tmac_b200_debug_set(const char *key, int value) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (ensure_init()) return -1;
     const std::string k = key ? key : "";
-    if (k == "g4") g.use_g4 = value;
-    else if (k == "seq_grid") g.seq_grid = value;
+    if (k == "seq_grid") g.seq_grid = value;
+    else if (k == "seq_smem_kb") g.seq_smem_kb = value;
     else if (k == "trace") g.trace = value;
-    else if (k == "g4_grid") g.g4_grid = value;
     else if (k == "fused") g.use_fused = value;
     else if (k == "prefill") g.use_prefill = value;
     else if (k == "prefill16") g.use_prefill16 = value;
@@ -1052,7 +889,6 @@ int tmac_b200_debug_set(const char *key, int value) {
     else if (k == "wpc") g.wpc_override = value;
     else if (k == "minb") g.minb_override = value;
     else if (k == "nbuf") g.nbuf_override = value;
-    else if (k == "kernel") g.kernel_version = value;
     else return fail("tmac_b200_debug_set: unknown key '" + k + "'");
     return 0;
 }
@@ -1219,7 +1055,7 @@ int tmac_b200_gemv(int64_t handle, int N, int dtype, const void *B, void *C) {
     const bool dev_b = kind_b == 2, dev_c = kind_c == 2;
     const bool int_path = L.one_scale && L.act_group_size == L.K;
     const bool prefill_shape = g.use_prefill && N >= g.prefill_min_n && L.pb == 2 && L.qch == 8 && L.act_group_size == 64 && !L.one_scale;
-    const bool can_fuse = g.use_fused && g.kernel_version != 1 && !int_path && L.act_group_size <= L.ck && g.lut_mode != 1 && !prefill_shape;
+    const bool can_fuse = g.use_fused && !int_path && L.act_group_size <= L.ck && g.lut_mode != 1 && !prefill_shape;
     auto launch_compute = [&](const void *dB, void *dC) -> int {
         if (can_fuse)   // one launch: the GEMV builds each chunk's LUT slice itself (bit-identical tables)
             return launch_gemv3(R, 0, L.Mout, N, nullptr, nullptr, nullptr, dC, L.Mout, 0, dtype == TMAC_B200_F16, true, nullptr, dB,
@@ -1340,7 +1176,7 @@ int tmac_b200_seq_build(int64_t seq) {
         yoff[i] = ytot;
         ytot += ((size_t)L.nrsb * L.rsb * sizeof(uint2) + 255) & ~(size_t)255;
     }
-    const size_t budget = 227 * 1024;
+    const size_t budget = (size_t)std::max(64, std::min(227, g.seq_smem_kb)) * 1024;
     const size_t fixed = ((red_b + 15) & ~(size_t)15) + ((tab_b + 15) & ~(size_t)15) + ((lsb_b + 15) & ~(size_t)15) + ((yfin_b + 15) & ~(size_t)15) + 64 * 8 + (kSeqWarps + 1) * 4 + 64 + 2 * kSeqDescWords * 4;
     if (fixed + 4 * slot_b > budget) return fail("seq_build: shared-memory budget exceeded");
     const int nslots = (int)std::min<size_t>(64, (budget - fixed) / slot_b);
@@ -1352,8 +1188,8 @@ int tmac_b200_seq_build(int64_t seq) {
         cudaMalloc(&S.d_xchg, xper * n) != cudaSuccess || cudaMalloc(&S.d_lut, std::max<size_t>(ltot, 256)) != cudaSuccess || cudaMalloc(&S.d_epochs, G * sizeof(unsigned)) != cudaSuccess ||
         cudaMalloc(&S.d_err, sizeof(int)) != cudaSuccess) { cudaGetLastError(); S.release(); return fail("seq_build: out of device memory"); }
     if (g.trace) {
-        if (cudaMalloc(&S.d_trace, (size_t)n * G * (16 + 8 * kSeqWarps) * sizeof(long long)) != cudaSuccess) { cudaGetLastError(); S.release(); return fail("seq_build: out of device memory (trace)"); }
-        cudaMemset(S.d_trace, 0, (size_t)n * G * (16 + 8 * kSeqWarps) * sizeof(long long));
+        if (cudaMalloc(&S.d_trace, (size_t)n * G * (16 + 16 * kSeqWarps) * sizeof(long long)) != cudaSuccess) { cudaGetLastError(); S.release(); return fail("seq_build: out of device memory (trace)"); }
+        cudaMemset(S.d_trace, 0, (size_t)n * G * (16 + 16 * kSeqWarps) * sizeof(long long));
     }
     CUDA_OK(cudaMemset(S.d_y, 0, ytot));
     CUDA_OK(cudaMemset(S.d_lut, 0, std::max<size_t>(ltot, 256)));
@@ -1485,7 +1321,7 @@ int tmac_b200_seq_trace(int64_t seq, long long *dst, size_t cap_bytes) {
     auto it = g_seqs.find(seq);
     if (it == g_seqs.end() || !it->second.built || !it->second.d_trace) return fail("seq_trace: tracing was not enabled when the sequence was built");
     CUDA_OK(cudaStreamSynchronize(g.stream()));
-    const size_t bytes = std::min(cap_bytes, it->second.ops.size() * (size_t)it->second.grid * (16 + 8 * kSeqWarps) * sizeof(long long));
+    const size_t bytes = std::min(cap_bytes, it->second.ops.size() * (size_t)it->second.grid * (16 + 16 * kSeqWarps) * sizeof(long long));
     CUDA_OK(cudaMemcpy(dst, it->second.d_trace, bytes, cudaMemcpyDeviceToHost));
     return it->second.grid;
 }

@@ -3,7 +3,7 @@
 //   preprocessor_kernel : activation row -> per-act-group LUT scale, LUT bias, int8 LUT
 //                         (python/t_mac/intrins/lut_ctor.cc:38-260; loop nest
 //                          deploy/tuned/kernels.cc:1002-1040).  Bit-exact with the x86 reference.
-//   gemv_kernel         : table-lookup GEMV over the stream layout (tmac_layout.h)
+//   gemv3_kernel        : table-lookup GEMV over the stream layout (tmac_layout.h)
 //                         (python/t_mac/intrins/tbl.cc:323-630 + generated recombine
 //                          deploy/tuned/aarch64-llama-2-7b-2bit/kernels.cc:1059-1075).
 //
@@ -21,25 +21,6 @@
 #include <stdint.h>
 
 namespace tmac_b200 {
-
-struct GemvParams {
-    const unsigned char *W;        // stream layout (already offset to the first row super-block)
-    const int8_t *qlut;            // [N][K/4][16]
-    const float *lut_scales;       // [N][K/ags]
-    const float *lut_biases;       // [N][K/ags]
-    void *C;                       // [N][ldc] f32 or f16
-    float *partial;                // split-K scratch [N][ks][nrsb*rsb] (float or int32 bits)
-    int *counters;                 // [N][nrsb] arrival counters (zero on entry, reset on exit)
-    int32_t *cbits;                // optional debug output [N][M*bits] (int path only), else null
-    int K, N, ldc;
-    int row_begin, row_end;        // rows (relative to the resident tensor's first row) that are stored
-    int c_row0;                    // C[n][row - c_row0]
-    int bits, nrsb, rsb0;          // rsb0: first super-block index (for row numbering)
-    int nchunk, ags, ck;
-    int zp, one_scale, int_path, sd, out_f16, ks;
-    size_t rsb_stride, blk_stride;
-    float scale0;
-};
 
 // (a & b) | c in ONE LOP3 (the compiler splits it in two when b and c are immediates)
 __device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c) {
@@ -226,167 +207,6 @@ __host__ __device__ inline void plane_weight_regs(int bits, bool sym, uint32_t *
 
 __device__ __forceinline__ float load_scale(const unsigned char *p, int sd, int i) {
     return sd == 2 ? __half2float(reinterpret_cast<const __half *>(p)[i]) : reinterpret_cast<const float *>(p)[i];
-}
-
-// ------------------------------------------------------------------------------------------
-// gemv_kernel.  grid = (nrsb, ks, N), block = 256 (8 warps).
-//   CTA (rsb, ks, n): rows of one super-block, K chunks [c0,c1).  warp w takes chunks
-//   c0+w, c0+w+8, ...; every lane owns RW rows, so there is no cross-lane reduction; warps are
-//   reduced through shared memory in fixed order; K splits through a global scratch + arrival
-//   counter, the last CTA summing the splits in fixed order (deterministic).
-// ------------------------------------------------------------------------------------------
-constexpr int kGemvThreads = 256;
-constexpr int kGemvWarps = kGemvThreads / 32;
-
-template <int PB, bool SYM, int QCH>
-__global__ void __launch_bounds__(kGemvThreads) gemv_kernel(const GemvParams p, const uint32_t wtx, const uint32_t wty) {
-    constexpr int RW = 8 / PB;
-    constexpr int RSB = 32 * RW;
-    constexpr int TW = SYM ? 2 : 4;               // 32-bit words per group table
-    extern __shared__ __align__(128) unsigned char smem[];
-
-    const int rsb = blockIdx.x, ks = blockIdx.y, n = blockIdx.z;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int c0 = (int)((long long)p.nchunk * ks / p.ks);
-    const int c1 = (int)((long long)p.nchunk * (ks + 1) / p.ks);
-    const int ngroups = (c1 - c0) * QCH * 4;
-    const int agq = p.ags / 16;                    // quads per activation group
-    const int ag0 = (c0 * p.ck) / p.ags;
-    const int ag1 = (c1 * p.ck + p.ags - 1) / p.ags;
-
-    uint32_t *tab = reinterpret_cast<uint32_t *>(smem);                       // [ngroups][TW]
-    float *ls_s = reinterpret_cast<float *>(smem + (size_t)ngroups * TW * 4);  // [ag1-ag0]
-    float *lbc_s = ls_s + (ag1 - ag0);                                         // [c1-c0] bias sum per chunk
-    float *red = lbc_s + (c1 - c0);                                            // [8][RSB]
-
-    // ---- prologue: stage the activation tables of this K range -----------------------------
-    {
-        const uint4 *q4 = reinterpret_cast<const uint4 *>(p.qlut + (size_t)n * p.K * 4) + (size_t)c0 * QCH * 4;
-        for (int g = tid; g < ngroups; g += kGemvThreads) {
-            const uint4 L = __ldg(q4 + g);
-            if (SYM) reinterpret_cast<uint2 *>(tab)[g] = make_uint2(L.x, L.y);
-            else     reinterpret_cast<uint4 *>(tab)[g] = make_uint4(L.x, L.y, __byte_perm(L.w, 0, 0x0123), __byte_perm(L.z, 0, 0x0123));
-        }
-        const int nag = p.K / p.ags;
-        const float *lsg = p.lut_scales + (size_t)n * nag, *lbg = p.lut_biases + (size_t)n * nag;
-        for (int a = tid; a < ag1 - ag0; a += kGemvThreads) ls_s[a] = lsg[ag0 + a];
-        if (!p.int_path)
-            for (int c = tid; c < c1 - c0; c += kGemvThreads) {
-                const int a0 = ((c0 + c) * p.ck) / p.ags, a1 = ((c0 + c + 1) * p.ck) / p.ags;
-                float s = 0.f;
-                for (int a = a0; a < a1; ++a) s += lbg[a];
-                lbc_s[c] = s;
-            }
-    }
-    __syncthreads();
-
-    float cacc[RW];
-    int iacc[RW];
-#pragma unroll
-    for (int i = 0; i < RW; ++i) { cacc[i] = 0.f; iacc[i] = 0; }
-
-    const unsigned char *rsb_base = p.W + (size_t)rsb * p.rsb_stride;
-    for (int c = c0 + warp; c < c1; c += kGemvWarps) {
-        const unsigned char *blk = rsb_base + (size_t)c * p.blk_stride;
-        const uint4 *wp = reinterpret_cast<const uint4 *>(blk) + lane;
-        uint4 wv[QCH];
-#pragma unroll
-        for (int q = 0; q < QCH; ++q) wv[q] = ldg_stream(wp + q * 32);
-        float sc[RW], zr[RW];
-        if (!p.one_scale) {
-            const unsigned char *sp = blk + (size_t)QCH * 512;
-#pragma unroll
-            for (int i = 0; i < RW; ++i) {
-                sc[i] = load_scale(sp, p.sd, lane * RW + i);
-                zr[i] = p.zp ? load_scale(sp + (size_t)RSB * p.sd, p.sd, lane * RW + i) : 0.f;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < RW; ++i) { sc[i] = p.scale0; zr[i] = 0.f; }
-        }
-        const uint32_t *tb = tab + (size_t)(c - c0) * QCH * 4 * TW;
-        float facc[RW];
-#pragma unroll
-        for (int i = 0; i < RW; ++i) facc[i] = 0.f;
-#pragma unroll
-        for (int q = 0; q < QCH; ++q) {
-            uint32_t t[4 * TW];
-#pragma unroll
-            for (int j = 0; j < TW; ++j) {
-                const uint4 tv = reinterpret_cast<const uint4 *>(tb + q * 4 * TW)[j];
-                t[4 * j] = tv.x; t[4 * j + 1] = tv.y; t[4 * j + 2] = tv.z; t[4 * j + 3] = tv.w;
-            }
-            Quad<PB, SYM>::run(wv[q], t, iacc, wtx, wty);
-            if (!p.int_path && ((q + 1) % agq == 0 || q == QCH - 1)) {
-                const float lsv = ls_s[(c * QCH + q) / agq - ag0];
-#pragma unroll
-                for (int i = 0; i < RW; ++i) { facc[i] = fmaf(lsv, (float)iacc[i], facc[i]); iacc[i] = 0; }
-            }
-        }
-        if (!p.int_path) {
-            const float lb = lbc_s[c - c0];
-#pragma unroll
-            for (int i = 0; i < RW; ++i) {
-                float v = fmaf(0.5f * sc[i], facc[i] + lb, cacc[i]);
-                if (p.zp) v = fmaf(zr[i], lb, v);
-                cacc[i] = v;
-            }
-        }
-    }
-
-    // ---- cross-warp reduction (fixed order) --------------------------------------------------
-#pragma unroll
-    for (int i = 0; i < RW; ++i)
-        red[warp * RSB + lane * RW + i] = p.int_path ? __int_as_float(iacc[i]) : cacc[i];
-    __syncthreads();
-
-    const int row_local = tid;                          // RSB <= 256 = blockDim
-    const int row = (p.rsb0 + rsb) * RSB + row_local;   // row relative to the resident tensor
-    float fsum = 0.f;
-    int isum = 0;
-    if (row_local < RSB) {
-#pragma unroll
-        for (int w = 0; w < kGemvWarps; ++w) {
-            const float v = red[w * RSB + row_local];
-            if (p.int_path) isum += __float_as_int(v); else fsum += v;
-        }
-    }
-    const int padded = p.nrsb * RSB;
-    if (p.ks > 1) {
-        float *part = p.partial + ((size_t)n * p.ks + ks) * padded + (size_t)rsb * RSB;
-        if (row_local < RSB) part[row_local] = p.int_path ? __int_as_float(isum) : fsum;
-        __threadfence();
-        __shared__ int s_last;
-        __syncthreads();
-        if (tid == 0) {
-            const int t = atomicAdd(p.counters + (size_t)n * p.nrsb + rsb, 1);
-            s_last = (t == p.ks - 1);
-            if (s_last) p.counters[(size_t)n * p.nrsb + rsb] = 0;   // self-reset for the next launch
-        }
-        __syncthreads();
-        if (!s_last) return;
-        __threadfence();
-        fsum = 0.f; isum = 0;
-        if (row_local < RSB)
-            for (int k2 = 0; k2 < p.ks; ++k2) {
-                const float v = __ldcg(p.partial + ((size_t)n * p.ks + k2) * padded + (size_t)rsb * RSB + row_local);
-                if (p.int_path) isum += __float_as_int(v); else fsum += v;
-            }
-    }
-    if (row_local >= RSB || row < p.row_begin || row >= p.row_end) return;
-    float out;
-    if (p.int_path) {
-        // C = ((sum_b alpha_b*CBits_b) * LUT_Scales[0] + LUT_Biases[0]*alpha_0) * Scales[0]
-        // (python/t_mac/ops/qgemm.py:160,171-174); isum = sum_b 2*alpha_b*CBits_b exactly.
-        const float cb = __fmul_rn((float)isum, 0.5f);
-        const float t1 = __fmul_rn(cb, ls_s[0]);
-        const float t2 = __fmul_rn(p.lut_biases[(size_t)n * (p.K / p.ags)], 0.5f);
-        out = __fmul_rn(__fadd_rn(t1, t2), p.scale0);
-    } else
-        out = fsum;
-    const size_t o = (size_t)n * p.ldc + (size_t)(row - p.c_row0);
-    if (p.out_f16) reinterpret_cast<__half *>(p.C)[o] = __float2half_rn(out);
-    else reinterpret_cast<float *>(p.C)[o] = out;
 }
 
 // ==========================================================================================

@@ -29,7 +29,7 @@
 
 namespace tmac_b200 {
 
-constexpr int kSeqWarps = 20;                         // consumer warps per CTA
+constexpr int kSeqWarps = 19;                         // consumer warps per CTA
 constexpr int kSeqThreads = (kSeqWarps + 1) * 32;     // + 1 producer warp
 constexpr int kSeqMaxRsb = 256;                       // rows per super-block, PB = 1
 constexpr int kSeqDescWords = 64;                     // SeqOp (words 0..) + SeqCta (words 40..55) staged in shared memory
@@ -76,7 +76,7 @@ struct SeqParams {
     int red_off, tab_off, lsb_off, bar_off, prog_off, yfin_off, desc_off;   // shared-memory offsets (bytes)
     unsigned int *epochs;                 // [grid] launch counter of every CTA (incremented by that CTA at exit)
     int *err;                             // != 0: a wait expired
-    long long *trace;                     // optional [nops][grid][16] globaltimer stamps, followed by [nops][grid][NW][8] per-warp stamps
+    long long *trace;                     // optional [nops][grid][16] globaltimer stamps, followed by [nops][grid][NW][16] per-warp clock64 stamps
 };
 
 __device__ __forceinline__ long long seq_timer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
@@ -280,8 +280,8 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_kernel(const SeqParams p, 
         const int npass = qc.npass, P = qc.P, fc = qc.fc, last_open = qc.last_open;
         if (lane == 0) st_volatile_s32(prog + warp, seq_base);
         long long *tr = p.trace ? p.trace + ((size_t)op * G + cta) * 16 : nullptr;
-        long long *tw = (p.trace && lane == 0) ? p.trace + (size_t)p.nops * G * 16 + (((size_t)op * G + cta) * NW + warp) * 8 : nullptr;
-        if (tw) tw[0] = seq_timer();
+        long long *tw = (p.trace && lane == 0) ? p.trace + (size_t)p.nops * G * 16 + (((size_t)op * G + cta) * NW + warp) * 16 : nullptr;
+        if (tw) { tw[0] = clock64(); tw[12] = seq_timer(); }
         if (tr && tid == 0) { tr[0] = seq_timer(); tr[10] = 0; }
         if (tr && warp == NW - 1 && lane == 0) tr[11] = 0;
 
@@ -333,11 +333,10 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_kernel(const SeqParams p, 
             }
         }
         if (tr && tid == 0) tr[1] = seq_timer();      // (stamps right after a bar.sync would show its issue, not its release)
-        if (tw) tw[1] = seq_timer();
-        const long long ck0 = tw ? clock64() : 0;
+        if (tw) tw[1] = clock64();
         seq_bar(1);
         long long ck1 = 0;
-        if (tw) { const int dummy = ld_volatile_s32(prog + NW); ck1 = clock64() + (dummy == -12345); tw[5] = ck0; tw[6] = ck1; }
+        if (tw) { const int dummy = ld_volatile_s32(prog + NW); ck1 = clock64() + (dummy == -12345); tw[2] = ck1; }
 
         // ---- (B) lookups over my units (unit = one activation group of one block) ----
         for (int s = 0; s < nseg; ++s) {                       // rows of super-blocks I do not touch must read as zero
@@ -378,14 +377,14 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_kernel(const SeqParams p, 
                 const float *ls = lsb + (size_t)ci * (2 * NAG);
                 {
                     const long long tw0 = tr ? clock64() : 0;
-                    if (tw && ck1) tw[7] = tw0;
+                    if (tw && ck1) tw[3] = tw0;
                     int spins = 0;
                     while (ld_volatile_s32(issued) <= seq_base + j && ++spins < kSeqSpinLimit) __nanosleep(100);
                     if (spins >= kSeqSpinLimit || !seq_mbar_wait(full + slot, (uint32_t)par)) atomicExch(p.err, 4);
                     if (tr && lane == 0 && (warp == 0 || warp == NW - 1)) tr[warp == 0 ? 10 : 11] += clock64() - tw0;   // cycles waiting for weights
                 }
                 if (tr && tid == 0 && u == 0) tr[2] = seq_timer();      // first block of the share is resident
-                if (tw && ck1) { tw[2] = seq_timer(); ck1 = 0; }           // my first block is resident
+                if (tw && ck1) { tw[4] = clock64(); ck1 = 0; }           // my first block is resident
                 const unsigned char *stage = ring + (size_t)slot * p.slot_bytes;
                 const uint4 *wp = reinterpret_cast<const uint4 *>(stage) + lane;
                 float facc[RW];
@@ -447,7 +446,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_kernel(const SeqParams p, 
             }
         }
         if (tr && lane == 0 && (warp == 0 || warp == NW / 2 || warp == NW - 1)) tr[warp == 0 ? 3 : (warp == NW - 1 ? 4 : 5)] = seq_timer();
-        if (tw) tw[3] = seq_timer();
+        if (tw) tw[5] = clock64();
         if (tid < 56) desc[((op + 1) & 1) * kSeqDescWords + tid] = next_word;
         seq_bar(2);
 
@@ -460,6 +459,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_kernel(const SeqParams p, 
 #pragma unroll 4
             for (int w = 0; w < NW; ++w) mine += red[((size_t)s * NW + w) * RSB + t];
             if (tr && item == 0) tr[6] = seq_timer() + (mine == 1.2345e-30f);    // after the barrier released and the sums are in
+            if (tw && item < NW * 32) tw[6] = clock64() + (mine == 1.2345e-30f);
             if (!ends_here) {                                   // continues in the next CTA (always my last super-block)
                 seq_publish(xchg + (size_t)cta * RSB + t, __float_as_uint(mine), epoch);
                 continue;
@@ -470,6 +470,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_kernel(const SeqParams p, 
                     fsum += __uint_as_float(seq_wait<2>(xchg + (size_t)k2 * RSB + t, true, epoch, p.err, 2).x);
             }
             fsum += mine;
+            if (tw && item < NW * 32) tw[7] = clock64() + (fsum == 1.2345e-30f);
             const int row = sb * RSB + t;
             if (row < Mout) {
                 if (Cout) {
@@ -479,6 +480,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_kernel(const SeqParams p, 
                 seq_publish(yv + row, __float_as_uint(fsum), epoch);
             }
             if (lut_out) yfin[item] = row < Mout ? fsum : 0.f;
+            if (tw && item < NW * 32) tw[8] = clock64();
         }
         if (lut_out) {
             // the consumer's preprocessor for the rows finished here (row super-blocks that end in this CTA): thread = K-group of
@@ -495,9 +497,11 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_kernel(const SeqParams p, 
                     if (t < GPSW) {
                         const bool valid = t < GPS;
                         const float4 f = valid ? reinterpret_cast<const float4 *>(yfin)[s * GPS + t] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (tw) tw[9] = clock64() + (f.x == 1.2345e-30f);
                         uint32_t lo, hi;
                         float scale, bias;
                         lut_group<WL>(f.x, f.y, f.z, f.w, lane, lo, hi, scale, bias);
+                        if (tw) tw[10] = clock64() + (lo == 0x12345678u);
                         if (valid) {
                             const size_t g = (size_t)(sb_first + s) * GPS + t;
                             seq_publish16(lut_out + g, lo, hi, epoch);
@@ -523,7 +527,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_kernel(const SeqParams p, 
             }
         }
         if (tr && tid == 0) tr[7] = seq_timer();
-        if (tw) tw[4] = seq_timer();
+        if (tw) tw[11] = clock64();
         seq_base += nb;
         slot_base += nb;
         while (slot_base >= p.nslots) { slot_base -= p.nslots; par_base ^= 1; }

@@ -220,6 +220,9 @@ def cbits(wt: Weights, N, qlut, out):
     check(load().tmac_b200_cbits(wt.handle, N, ptr(qlut), ptr(out)), "tmac_b200_cbits")
 
 
+SEQ_WARPS = 19      # kSeqWarps (consumer warps per CTA of the sequence kernel)
+
+
 class Sequence:
     """A chain of (dependent) GEMVs executed by one persistent launch (tmac_b200_seq_*, include/tmac_b200.h)."""
 
@@ -254,9 +257,9 @@ class Sequence:
         import numpy as np
         inf = self.info()
         n, g = inf["ops"], inf["grid"]
-        buf = np.zeros(n * g * (16 + 8 * 20), np.int64)
+        buf = np.zeros(n * g * (16 + 16 * SEQ_WARPS), np.int64)
         check(load().tmac_b200_seq_trace(self.h, buf.ctypes.data, buf.nbytes), "tmac_b200_seq_trace")
-        self.warp_trace = buf[n * g * 16:].reshape(n, g, 20, 8)      # per warp: enter, LUT done, first block resident, lookups done, rows done
+        self.warp_trace = buf[n * g * 16:].reshape(n, g, SEQ_WARPS, 16)      # per consumer warp: clock64 stamps (tmac_seq.cuh)
         return buf[:n * g * 16].reshape(n, g, 16)
 
     def free(self):

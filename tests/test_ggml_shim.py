@@ -57,3 +57,17 @@ def test_shim_compiles_against_reference_headers_and_resolves_all_hooks(tmp_path
     assert out[0] == "10" and out[1] == "2"
     # wsize / nbytes: the reference's formulas (ggml-tmac.cpp:258-263: qlut K*N*4 + 2 * lut scales/biases; :277-288: M*K*bits/8 + scales)
     assert int(out[2]) == 4096 * 4 + 2 * 64 * 4 and int(out[3]) == 11008 * 4096 * 2 // 8 + 11008 * 32 * 2 * 4
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_INC), reason="reference tree not mounted (GPU box)")
+def test_vendored_ggml_builds_with_GGML_TMAC_against_this_package(tmp_path):
+    """the reference's vendored ggml configured with -DGGML_TMAC=ON -DGGML_TMAC_TVM_THREADPOOL=ON (the branch of
+    ggml.c that calls the hook once per mat-vec from thread 0, ref:ggml.c:12610-12630) finds package TMAC = this library,
+    compiles our ggml-tmac.cpp in place of the reference's and links libtmac_b200.so (tools/ggml_tmac_build.sh)."""
+    env = dict(os.environ, W=str(tmp_path / "w"))
+    r = subprocess.run(["bash", os.path.join(ROOT, "tools", "ggml_tmac_build.sh")], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "TMAC found" in r.stdout and "ggml_tmac_* symbols defined in libggml: 4" in r.stdout
+    for s in ("ggml_tmac_init", "ggml_tmac_mul_mat_task_init", "ggml_tmac_mul_mat_task_compute", "ggml_tmac_get_type_bits"):
+        assert s in r.stdout, s                  # imported by libggml.so, exported by libtmac_b200.so
+    assert "libtmac_b200.so" in r.stdout

@@ -213,97 +213,6 @@ def test_tile_calls_like_ggml(lib, oracle):
         wt.free()
 
 
-@pytest.fixture
-def force_g4(lib):
-    """Run the lone-launch stream-K kernel (gemv4) on every shape it is instantiated for, whatever the size."""
-    tb.debug_set("g4", 2)
-    yield
-    tb.debug_set("g4", 0); tb.debug_set("g4_grid", 0)
-
-
-G4_CASES = [
-    (T.Config(1024, 4096, 2, zero_point=True), "w2zp"),
-    (T.Config(512, 4096, 4), "w4"),
-    (T.Config(384, 1024, 3, zero_point=True), "w3zp"),
-    (T.Config(512, 2048, 1), "w1"),
-    (T.Config(640, 3200, 2, one_scale=True), "bitnet_int32"),
-    (T.Config(192, 512, 2, bm=128, zero_point=True), "ragged"),
-    (T.Config(320, 1024, 2, bm=320, group_size=64, act_group_size=64, zero_point=True), "g64"),
-    (T.Config(768, 11008, 2, zero_point=True), "k11008"),
-]
-
-
-@pytest.mark.parametrize("grid", [0, 2, 3, 7, 37, 296], ids=lambda g: "grid%d" % g)
-@pytest.mark.parametrize("cfg,name", G4_CASES, ids=[c[1] for c in G4_CASES])
-def test_stream_k_lone_launch_matches_oracle(lib, oracle, force_g4, cfg, name, grid):
-    """gemv4_kernel: every CTA-boundary placement (super-blocks cut in 2, 3, many pieces; a CTA that only publishes;
-    a single CTA) against the oracle -- two-call path (G1-G3 incl. the bit-exact int32 path) and the fused single launch
-    (bit-identical to the two-call path, same summation order)."""
-    cfg = cfg.resolved()
-    tb.debug_set("g4_grid", grid)
-    w, sc, z, x = T.make_problem(cfg, seed=21)
-    A, S = T.pack_reference_layout(w, sc, z, cfg)
-    wt = tb.upload_reference_layout(kc(cfg), A, S)
-    try:
-        nag = cfg.K // cfg.act_group_size
-        dx = torch.from_numpy(x).cuda()
-        dq = torch.zeros((1, cfg.K // 4, 16), dtype=torch.int8, device="cuda")
-        dls = torch.zeros((1, nag), device="cuda"); dlb = torch.zeros_like(dls)
-        two = torch.full((1, cfg.Mout), 7.0, device="cuda"); fused = torch.full((1, cfg.Mout), -7.0, device="cuda")
-        tb.preprocessor(cfg.K, 1, cfg.act_group_size, dx, dls, dlb, dq)
-        for rep in range(3):        # repeated launches reuse the exchange slots
-            tb.qgemm_lut(wt, 1, dq, dls, dlb, two)
-        ll = tb.last_launch()
-        assert ll["cluster"] == 0, "expected the stream-K kernel, got %r" % ll
-        tb.gemv(wt, 1, dx, fused)
-        torch.cuda.synchronize()
-        qo, lso, lbo = oracle.preprocessor(x, cfg.act_group_size)
-        Co = oracle.qgemm(cfg, A, S, qo, lso, lbo)
-        Cout = two.cpu().numpy()
-        if cfg.one_scale and cfg.act_group_size == cfg.K:
-            assert np.array_equal(Cout.view(np.uint32), Co.view(np.uint32)), "int32 path must be bit exact"
-        else:
-            assert np.abs(Cout - Co).max() <= TIGHT_TOL * np.abs(Co).max()
-            assert torch.equal(fused, two), "fused launch must equal the two-call path bit for bit"
-    finally:
-        wt.free()
-
-
-def test_stream_k_general_lut_and_tile_calls(lib, oracle, force_g4):
-    """gemv4 with a non-symmetric LUT (16-entry path) and with ggml-style row-range calls."""
-    tb.debug_set("g4_grid", 5)
-    cfg = T.Config(1024, 2048, 2, bm=128, zero_point=True).resolved()
-    w, sc, z, x = T.make_problem(cfg, seed=23)
-    A, S = T.pack_reference_layout(w, sc, z, cfg)
-    k = kc(cfg)
-    tb.check(lib.tmac_b200_register_kcfg(C.byref(k)), "register")
-    wt = tb.upload_reference_layout(k, A, S)
-    try:
-        rng = np.random.default_rng(4)
-        nag = cfg.K // cfg.act_group_size
-        q = rng.integers(-127, 128, size=(1, cfg.K // 4, 16)).astype(np.int8)
-        ls = np.abs(rng.standard_normal((1, nag))).astype(np.float32); lb = rng.standard_normal((1, nag)).astype(np.float32)
-        Co = oracle.qgemm(cfg, A, S, q, ls, lb)
-        dC = torch.zeros((1, cfg.Mout), device="cuda")
-        tb.check(lib.tmac_b200_set_lut_mode(1), "set_lut_mode")     # caller-made device table: general 16-entry path
-        tb.qgemm_lut(wt, 1, torch.from_numpy(q).cuda(), torch.from_numpy(ls).cuda(), torch.from_numpy(lb).cuda(), dC)
-        tb.check(lib.tmac_b200_set_lut_mode(0), "set_lut_mode")
-        ll = tb.last_launch()
-        assert ll["cluster"] == 0 and ll["sym_lut"] == 0
-        assert np.abs(dC.cpu().numpy() - Co).max() <= TIGHT_TOL * np.abs(Co).max()
-        out = np.zeros((1, cfg.Mout), np.float32)
-        n_tile = cfg.n_tile_num; chunk0 = cfg.Mout // n_tile
-        w_chunk = A.size // n_tile; s_chunk = S.size // n_tile
-        for t in range(n_tile):
-            lib.ggml_tmac_mul_mat_task_compute(A.ctypes.data + t * w_chunk, S.ctypes.data + 4 * t * s_chunk, q.ctypes.data, ls.ctypes.data,
-                                               lb.ctypes.data, out.ctypes.data + 4 * t * chunk0, chunk0, cfg.K, 1, cfg.bits)
-        assert tb.last_launch()["cluster"] == 0
-        assert np.abs(out - Co).max() <= TIGHT_TOL * np.abs(Co).max()
-    finally:
-        tb.check(lib.tmac_b200_set_lut_mode(0), "set_lut_mode")
-        wt.free()
-
-
 def test_ggml_hook_transform_tensor_i2_blob(lib, oracle):
     """The load-time path of the llama.cpp fork: an I2 tensor blob `permuted weights || fp32 scales`
     (python/t_mac/model_utils.py:271, ggml-tmac.cpp:336-345) goes through ggml_tmac_b200_transform_tensor, then the

@@ -22,12 +22,15 @@ ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--bits", type=int, default=2)
 ap.add_argument("--mout", type=int, default=bench.MOUT)
 ap.add_argument("--k", type=int, default=bench.K)
+ap.add_argument("--smem", type=int, default=0)
 args = ap.parse_args()
 
 lib = tb.load(); tb.check(lib.tmac_b200_init(0), "init")
 st = torch.cuda.Stream(); torch.cuda.set_stream(st); tb.check(lib.tmac_b200_set_stream(st.cuda_stream), "set_stream")
 if args.trace:
     tb.debug_set("trace", 1)
+if args.smem:
+    tb.debug_set("seq_smem_kb", args.smem)
 L = args.layers
 w, sc, z = bench.synth(100, args.mout, args.k, args.bits, 128, True, False)
 bm = 256 if (args.mout * args.bits) % 256 == 0 else 128
@@ -82,12 +85,15 @@ for name, chained in (("independent inputs", False), ("dependent chain", True)):
         print("  op period: median %.2f us (min %.2f, max %.2f); spread of 'enter' across CTAs: median %.2f us; of 'lookups done': %.2f us" % (
             np.median(per_op), per_op.min(), per_op.max(), np.median(ent.max(axis=1) - ent.min(axis=1)), np.median(mlast.max(axis=1) - mlast.min(axis=1))))
         mid = min(L - 1, 10)
-        wt_ = seq.warp_trace.astype(np.float64) / 1e3 - t0
+        wt_ = seq.warp_trace.astype(np.float64)
+        names = ["enter", "LUT own", "barA rel", "pre-wait", "blk res", "lookups", "sums", "xchg", "y pub", "barLUT", "LUT built", "end"]
         for c in (np.argsort(ent[mid])[len(ent[mid]) // 2], np.argsort(pub[mid])[-1]):
-            print("  op %d cta %d per warp (enter / LUT done / first block / lookups done / rows done), us:" % (mid, c))
-            for w in range(20):
-                cb = seq.warp_trace[mid, c, :, 5].min()
-                print("    w%02d %s   clock64 rel. to first arrival: arrive bar A %6d, released %6d, before weight wait %6d" % (w, "  ".join("%7.2f" % v for v in wt_[mid, c, w, :5]), seq.warp_trace[mid, c, w, 5] - cb, seq.warp_trace[mid, c, w, 6] - cb, seq.warp_trace[mid, c, w, 7] - cb))
+            base = wt_[mid, c, :, 0].min()
+            print("  op %d cta %d per warp, SM cycles since the first warp entered the op (0 = not stamped):" % (mid, c))
+            print("        " + " ".join("%9s" % n for n in names) + "   | next op enter")
+            for w in range(wt_.shape[2]):
+                nxt = wt_[mid + 1, c, w, 0] - base if mid + 1 < L else 0
+                print("    w%02d " % w + " ".join("%9d" % (v - base if v else 0) for v in wt_[mid, c, w, :12]) + "   | %9d" % nxt)
         order = np.argsort(ent[mid])
         print("  op %d timeline (us after launch), 6 CTAs:" % mid)
         for c in order[:: max(1, len(order) // 6)][:6]:
