@@ -423,9 +423,53 @@ def test_prefill_tcgen05_tile_matches_oracle(lib, oracle, cfg, N):
         tb.gemv(wt, N, dx, out2)
         torch.cuda.synchronize()
         assert torch.equal(out, out2)
-        os.environ["TMAC_B200_PREFILL"] = "0"
+        tb.debug_set("prefill", 0)                     # tile disabled: the GEMV kernel per activation row
+        out3 = torch.zeros_like(out)
+        tb.qgemm_lut(wt, N, q, ls, lb, out3)
+        assert tb.last_launch()["batch"] >= 0, "the tile was supposed to be disabled"
+        torch.cuda.synchronize()
+        g3 = out3.cpu().numpy()
+        assert np.abs(g3 - Co).max() <= TIGHT_TOL * np.abs(Co).max()
+        assert np.abs(g3 - got).max() <= 2 * TIGHT_TOL * np.abs(Co).max()
     finally:
-        os.environ.pop("TMAC_B200_PREFILL", None)
+        tb.debug_set("prefill", 1)
+        wt.free()
+
+
+# BASELINE.md 3.4 shapes at FULL size (the launch decomposition depends on Mout / K): every row against the oracle.
+LLAMA = [(4096, 4096), (11008, 4096), (4096, 11008)]
+QWEN2 = [(3584, 3584), (512, 3584), (18944, 3584), (3584, 18944)]
+BITNET = [(3200, 3200), (8640, 3200), (3200, 8640)]
+FULL_CASES = ([(m, k, 2, True, False) for m, k in LLAMA] + [(m, k, 4, False, False) for m, k in LLAMA] + [(m, k, 4, True, False) for m, k in LLAMA + QWEN2] +
+              [(m, k, 2, False, True) for m, k in BITNET])
+
+
+@pytest.mark.parametrize("mout,k,bits,zp,one_scale", FULL_CASES,
+                         ids=["%dx%d_w%d%s" % (m, k, b, "_bitnet" if o else ("_zp" if z else "_sym")) for m, k, b, z, o in FULL_CASES])
+def test_full_size_shapes_every_row(lib, oracle, mout, k, bits, zp, one_scale):
+    cfg = T.Config(mout, k, bits, zero_point=zp, one_scale=one_scale).resolved()
+    w, sc, z, x = T.make_problem(cfg, seed=7)
+    A, S = T.pack_reference_layout(w, sc, z, cfg)
+    wt = tb.upload_plain(kc(cfg), w, sc, z)
+    try:
+        nag = cfg.K // cfg.act_group_size
+        dx = torch.from_numpy(x).cuda()
+        q = torch.zeros((1, cfg.K // 4, 16), dtype=torch.int8, device="cuda")
+        ls = torch.zeros((1, nag), device="cuda"); lb = torch.zeros_like(ls)
+        two = torch.zeros((1, cfg.Mout), device="cuda"); one = torch.zeros_like(two)
+        tb.preprocessor(cfg.K, 1, cfg.act_group_size, dx, ls, lb, q)
+        tb.qgemm_lut(wt, 1, q, ls, lb, two)            # the two reference calls
+        tb.gemv(wt, 1, dx, one)                        # the one-call form (fused LUT where the grouping allows)
+        torch.cuda.synchronize()
+        qo, lso, lbo = oracle.preprocessor(x, cfg.act_group_size)
+        Co = oracle.qgemm(cfg, A, S, qo, lso, lbo)
+        assert np.array_equal(q.cpu().numpy(), qo)
+        for got in (two.cpu().numpy(), one.cpu().numpy()):
+            if one_scale:
+                assert np.array_equal(got.view(np.uint32), Co.view(np.uint32)), "int32 path must be bit exact"
+            else:
+                assert np.abs(got - Co).max() <= TIGHT_TOL * np.abs(Co).max()
+    finally:
         wt.free()
 
 
