@@ -162,6 +162,34 @@ def cpu_arm(budget_s, nbuf=4):
             "sample": "%d GEMVs %dx%d W2 g128 zp over %d distinct weight buffers, preprocessor included, %.1f s" % (n, MOUT, K, nbuf, el)}
 
 
+def parity_check(w, sc, z, xs, out_chain, out_seq, layers_checked=(0, LAYERS // 2, LAYERS - 1)):
+    """the numbers above come from outputs that match the CPU reference (oracle/_ref when built, else the
+    oracle port) -- used here as the CHECKER only.  Launch chain: layer i with its own input x[i].  Sequence kernel
+    (dependent chain): layer i with the GPU's own previous output as input.  All rows, tolerance 1e-3 of max|C| (north_star)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import tmac_oracle as T
+    lib = T.load_ref() or T.load_oracle()
+    cfg = T.Config(MOUT, K, BITS, group_size=GS, act_group_size=AGS, zero_point=ZP).resolved()
+    A, S = T.pack_reference_layout(w, sc, z, cfg)
+
+    def ref(xrow):
+        q, ls, lb = lib.preprocessor(xrow[None], AGS)
+        return lib.qgemm(cfg, A, S, q, ls, lb)[0]
+    worst = {}
+    for i in layers_checked:
+        r = ref(xs[i])
+        e = float(np.abs(out_chain[i] - r).max() / np.abs(r).max())
+        worst["launch_chain"] = max(worst.get("launch_chain", 0.0), e)
+        assert e <= 1e-3, "launch chain layer %d: rel err %.3g" % (i, e)
+        if out_seq is not None:
+            xin = xs[0] if i == 0 else out_seq[i - 1][:K]
+            r = ref(xin)
+            e = float(np.abs(out_seq[i] - r).max() / np.abs(r).max())
+            worst["sequence_dependent_chain"] = max(worst.get("sequence_dependent_chain", 0.0), e)
+            assert e <= 1e-3, "sequence kernel layer %d: rel err %.3g" % (i, e)
+    return {"checker": lib.kind, "layers": list(layers_checked), "rows": MOUT, "max_rel_err": worst, "tolerance": 1e-3}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -281,6 +309,24 @@ def main():
         g_grouped = lib.tmac_b200_graph_end(); tb.check(g_grouped, "graph_end")
     kernels_per_step = LAYERS
 
+    # ---- the same chain as ONE persistent launch (decode sequence kernel, tmac_b200_seq_*): op i+1 reads its input from
+    #      op i's output (first K rows) -- a TRUE data dependency carried through HBM -- and, for comparison, with the
+    #      independent inputs of the launch chain above.  Both write every layer's output.
+    out_seq = torch.zeros((LAYERS, MOUT), device="cuda")
+    seqs = {}
+    try:
+        for name, chained in (("dependent", True), ("independent", False)):
+            sq = tb.Sequence()
+            for i, wt in enumerate(layers):
+                if chained and i > 0:
+                    sq.add(wt, in_op=i - 1, in_offset=0, out=out_seq[i])
+                else:
+                    sq.add(wt, x=x[i], out=out_seq[i])
+            sq.build()
+            seqs[name] = sq
+    except Exception as ex:
+        seqs = {"error": str(ex)[:160]}
+
     def run_steps(graph, n):
         if args.eager:
             for _ in range(n):
@@ -322,9 +368,55 @@ def main():
     while time.time() < t_end:
         timed(g_step, args.steps, True)
     clocks = sampler.stop() if rank == 0 else None
+    gather_check = None
+    if world > 1:      # every rank's slice of the gathered tensor must equal its own outputs bit for bit (the gather moves bytes)
+        okt = torch.tensor([1 if torch.equal(gathered[rank], out) else 0], device="cuda", dtype=torch.int32)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        gather_check = bool(okt.item())
+        if not gather_check:
+            raise SystemExit("bench.py: gathered outputs differ from the ranks' own outputs")
     ms_per_step = ms / args.steps
     bytes_step = LAYERS * algorithmic_bytes()
     value = world * bytes_step / (ms_per_step * 1e-3) / 1e9
+    out_launch_chain = out.clone()
+    submission = "one tmac_b200_gemv launch per layer (LUT build fused), %d launches captured in one CUDA graph with programmatic-dependent-launch edges" % LAYERS
+
+    def timed_seq(sq, steps):
+        for _ in range(3):
+            sq.launch()
+        sq.status()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                sq.launch()
+            e1.record(stream)
+        torch.cuda.synchronize()
+        sq.status()
+        t = e0.elapsed_time(e1) / steps
+        if world > 1:
+            tt = torch.tensor([t], device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX); t = float(tt.item())
+        return t
+
+    seq_report = None
+    if "error" in seqs:
+        seq_report = seqs
+    else:
+        ms_dep, ms_ind = timed_seq(seqs["dependent"], args.steps), timed_seq(seqs["independent"], args.steps)
+        seqs["dependent"].launch(); seqs["dependent"].status()       # leave the dependent chain's outputs in out_seq for the parity check
+        seq_report = {"what": "decode sequence kernel: the %d GEMVs of the step in ONE persistent launch (one CTA per SM, TMA weight ring across ops)" % LAYERS,
+                      "dependent_chain": {"ms_per_step": ms_dep, "GBps": world * bytes_step / (ms_dep * 1e-3) / 1e9, "us_per_gemv": ms_dep * 1e3 / LAYERS,
+                                          "dependency": "x[i+1] = first K outputs of GEMV i (true data dependency through HBM {value, epoch} words)"},
+                      "independent_inputs": {"ms_per_step": ms_ind, "GBps": world * bytes_step / (ms_ind * 1e-3) / 1e9, "us_per_gemv": ms_ind * 1e3 / LAYERS},
+                      "info": seqs["dependent"].info()}
+        if ms_dep < ms_per_step and world == 1:      # the dependent chain in one launch beats the chain of launches: it is the step
+            ms_per_step = ms_dep
+            value = world * bytes_step / (ms_per_step * 1e-3) / 1e9
+            launches["n"] = args.steps
+            submission = "ONE persistent launch per step (decode sequence kernel); GEMV i+1 consumes GEMV i's output"
 
     timed(g_two, 3, False)
     ms_two = timed(g_two, args.steps, False) / args.steps
@@ -338,12 +430,15 @@ def main():
              else "gemv3_kernel<PB=2,SYM,QCH=8,AGQ=4>")
     roofline = {"bound": "hbm", "kernel": kname, "launch": lone_cfg, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src, "us_per_launch": t_gemv * 1e6,
+                "submission": submission, "sequence_kernel": seq_report,
                 "two_call_step": {"what": "preprocessor + qgemm_lut as two launches per layer (the reference's init/compute split)",
                                   "ms_per_step": ms_two, "GBps": bytes_step / (ms_two * 1e-3) / 1e9}, "algorithmic_bytes_per_launch": algorithmic_bytes(), "traffic": None}
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp):       # not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
         try:
-            roofline["traffic"] = json.load(open(tp)).get("gemv_kernel_dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            roofline["traffic"] = tj.get("gemv_kernel_dram_bytes_per_launch")
+            roofline["traffic_source"] = "static: " + str(tj.get("source", "profiles/traffic.json (ncu --set full capture)"))
         except Exception:
             pass
 
@@ -388,7 +483,7 @@ def main():
         return {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int8 LUT / int32 dp4a / fp32 scale", "data": "synthetic", "config": workload_config(world),
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches["n"], "roofline": roofline,
+                "clocks": clocks, "gathered_equals_rank_outputs": gather_check, "e2e": e2e, "gpu_launches": launches["n"], "roofline": roofline,
                 "cpu_baseline": cpu_, "tokens_per_s": extras_}
 
     if (world > 1 or force_sharded) and not args.no_extras:   # all ranks: the model's linears row-sharded over the ranks
@@ -413,6 +508,11 @@ def main():
             extras = {"error": str(ex)[:200]}
         if world == 1:
             cpu = cpu_arm(12.0)
+            try:
+                cpu["parity_check"] = parity_check(w, sc, z, x.cpu().numpy(), out_launch_chain.cpu().numpy(),
+                                                   out_seq.cpu().numpy() if (seq_report and "error" not in seq_report) else None)
+            except AssertionError as ex:
+                raise SystemExit("bench.py: GPU outputs disagree with the CPU reference: %s" % ex)
 
     if rank == 0:
         print(json.dumps(headline(extras, cpu)), flush=True)
