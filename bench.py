@@ -212,7 +212,8 @@ def workload_config(gpus):
     return {"workload": "Llama-2-7B ffn up/gate shape W2A16 GEMV: out=%d K=%d batch=1, W2 g128 zero-point, act_group 64, "
                         "%d distinct layers per step per GPU" % (MOUT, K, LAYERS),
             "layers_per_step": LAYERS, "l2_policy": "inputs larger than L2 (%.0f MB of weights per step per GPU)" % (LAYERS * algorithmic_bytes() / 1e6),
-            "parallelism": "rows sharded: %d x %d rows, one NCCL all_gather of the step's outputs" % (gpus, MOUT) if gpus > 1 else "single GPU"}
+            "parallelism": ("%d ranks x %d rows per layer; the all-gather of every layer's output is fused into the GEMV epilogue "
+                            "(peer stores over NVLink, no collective launch)" % (gpus, MOUT)) if gpus > 1 else "single GPU"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -264,13 +265,25 @@ def main():
         qlut = torch.zeros((LAYERS, K // 4, 16), dtype=torch.int8, device="cuda")
         ls = torch.zeros((LAYERS, nag), device="cuda"); lb = torch.zeros_like(ls)
         out = torch.zeros((LAYERS, MOUT), device="cuda")
-        gathered = torch.zeros((world, LAYERS, MOUT), device="cuda") if world > 1 else None
+        gathered, sv, nccl_gathered = None, None, None
+    if world > 1:
+        # the step's all-gather is fused into the GEMV epilogues: every rank's [world][LAYERS][MOUT] buffer is mapped by every
+        # other rank (cudaIpc) and each launch stores its finished rows into all of them over NVLink (tmac_b200_peer_outputs)
+        sv = tb.SharedVector(world * LAYERS * MOUT, dist, rank, world)
+        gathered = sv.local.view(world, LAYERS, MOUT)
+        out = gathered[rank]
+        with torch.cuda.stream(stream):
+            nccl_gathered = torch.zeros((world, LAYERS, MOUT), device="cuda")
 
     def fused_step_calls(_unused=True):
         for i, wt in enumerate(layers):           # the reference-facing plugin call: init + compute in one (fused LUT build)
             if PREFETCH_NEXT:
                 lib.tmac_b200_hint_next_weights(layers[(i + 1) % LAYERS].handle)
+            if sv is not None:
+                tb.peer_outputs([sv.peer_ptr(q) + 4 * (rank * LAYERS + i) * MOUT for q in range(world) if q != rank])
             tb.gemv(wt, 1, x[i], out[i])
+        if sv is not None:
+            sv.barrier()                          # one flag exchange per step: every rank's rows of this step are in place everywhere
 
     def step_calls(with_pre=True):
         for i, wt in enumerate(layers):
@@ -343,8 +356,8 @@ def main():
             e0.record(stream)
             for _ in range(steps):
                 run_steps(graph, 1)
-                if collective and world > 1:
-                    dist.all_gather_into_tensor(gathered.view(-1), out.view(-1))
+                if collective == "nccl" and world > 1:
+                    dist.all_gather_into_tensor(nccl_gathered.view(-1), out.reshape(-1))
             e1.record(stream)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -369,12 +382,23 @@ def main():
         timed(g_step, args.steps, True)
     clocks = sampler.stop() if rank == 0 else None
     gather_check = None
-    if world > 1:      # every rank's slice of the gathered tensor must equal its own outputs bit for bit (the gather moves bytes)
-        okt = torch.tensor([1 if torch.equal(gathered[rank], out) else 0], device="cuda", dtype=torch.int32)
+    nccl_step = None
+    if world > 1:
+        # the fused gather must have produced the same tensor on every rank, and the same bytes as an NCCL all-gather of the
+        # ranks' own outputs
+        torch.cuda.synchronize(); dist.barrier()
+        with torch.cuda.stream(stream):
+            dist.all_gather_into_tensor(nccl_gathered.view(-1), out.reshape(-1))
+        torch.cuda.synchronize()
+        okt = torch.tensor([1 if torch.equal(gathered, nccl_gathered) else 0], device="cuda", dtype=torch.int32)
         dist.all_reduce(okt, op=dist.ReduceOp.MIN)
         gather_check = bool(okt.item())
         if not gather_check:
-            raise SystemExit("bench.py: gathered outputs differ from the ranks' own outputs")
+            raise SystemExit("bench.py: the fused gather differs from an NCCL all-gather of the ranks' outputs")
+        timed(g_step, 3, "nccl")
+        ms_nccl = timed(g_step, args.steps, "nccl") / args.steps
+        nccl_step = {"what": "same step followed by one ncclAllGather of the step's outputs (round-1 form)", "ms_per_step": ms_nccl,
+                     "GBps": world * LAYERS * algorithmic_bytes() / (ms_nccl * 1e-3) / 1e9}
     ms_per_step = ms / args.steps
     bytes_step = LAYERS * algorithmic_bytes()
     value = world * bytes_step / (ms_per_step * 1e-3) / 1e9
@@ -483,7 +507,7 @@ def main():
         return {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int8 LUT / int32 dp4a / fp32 scale", "data": "synthetic", "config": workload_config(world),
-                "clocks": clocks, "gathered_equals_rank_outputs": gather_check, "e2e": e2e, "gpu_launches": launches["n"], "roofline": roofline,
+                "clocks": clocks, "fused_gather_equals_nccl_all_gather": gather_check, "nccl_all_gather_step": nccl_step, "e2e": e2e, "gpu_launches": launches["n"], "roofline": roofline,
                 "cpu_baseline": cpu_, "tokens_per_s": extras_}
 
     if (world > 1 or force_sharded) and not args.no_extras:   # all ranks: the model's linears row-sharded over the ranks
@@ -522,9 +546,10 @@ def main():
 
 def tokens_per_second_sharded(tb, lib, torch, dist, stream, rank, world):
     """Matmul-only decode tokens/s with every quantised linear ROW-SHARDED over the ranks (whole reference
-    tiles per rank, remainders spread; every rank runs its own preprocessor) and one NCCL all-gather per fused group
-    (q/k/v, o, gate/up, down = 4 per layer), the token step captured in one CUDA graph when NCCL capture works, else
-    eager launches (stated).  Strong scaling: the model is fixed, per-rank weights = 1/world.  Runs on ALL ranks."""
+    tiles per rank, remainders spread; every rank runs its own LUT build).  No collective launch: every GEMV stores its
+    finished rows into every rank's output vector from its epilogue (tmac_b200_peer_outputs) and each fused group
+    (q/k/v, o, gate/up, down = 4 per layer) ends with one flag exchange (tmac_b200_peer_barrier), the token step captured in
+    one CUDA graph.  Strong scaling: the model is fixed, per-rank weights = 1/world.  Runs on ALL ranks."""
     sys.path.insert(0, os.path.join(ROOT, "t-mac_b200"))
     from shard import row_partition
     models = {
@@ -541,32 +566,29 @@ def tokens_per_second_sharded(tb, lib, torch, dist, stream, rank, world):
     res = {}
     for name, m in models.items():
         handles, plan, local_bytes, err = [], [], 0, None
+        sv = None
         try:
+            sv = tb.SharedVector(max(cnt * mout for (_, mout, _, cnt) in m["shapes"]), dist, rank, world)
             for (tag, mout, k, cnt) in m["shapes"]:
                 bits = m["bits"]
                 bm = next(b for b in ((192, 384, 576, 768) if bits == 3 else (256, 128, 512, 1024, 320, 640)) if (mout * bits) % b == 0)
-                tile_rows = bm // bits
-                parts = row_partition(mout, tile_rows, world)
+                parts = row_partition(mout, bm // bits, world)
                 row0, rows = parts[rank]
-                mx = max(r for _, r in parts)
                 ags = k if m["os"] else 64
                 with torch.cuda.stream(stream):
                     xb = torch.randn((1, k), device="cuda")
                     q = torch.zeros((1, k // 4, 16), dtype=torch.int8, device="cuda")
                     l1 = torch.zeros((1, k // ags), device="cuda"); l2 = torch.zeros_like(l1)
-                    o = torch.zeros((cnt, mx), device="cuda")
-                    gathered = torch.zeros((world, cnt, mx), device="cuda")
                 hs = []
                 if rows > 0:
                     w, sc, z = synth(7, mout, k, bits, 128, m["zp"], m["os"])
                     cfg = tb.make_kcfg(rows, k, bits, bm, 16, 128, ags, m["zp"], m["os"])
-                    ng = k // 128
                     base = tb.upload_plain(cfg, np.ascontiguousarray(w[row0:row0 + rows]), sc if m["os"] else np.ascontiguousarray(sc[row0:row0 + rows]),
                                            None if z is None else np.ascontiguousarray(z[row0:row0 + rows]))
                     hs = [base] + [tb.clone(base) for _ in range(m["L"] * cnt - 1)]
                     handles += hs
                     local_bytes += m["L"] * cnt * base.nbytes
-                plan.append((hs, cnt, k, ags, xb, q, l1, l2, o, gathered, rows))
+                plan.append((hs, cnt, mout, k, ags, xb, q, l1, l2, row0, rows))
         except Exception as ex:
             err = str(ex)[:160]
         if not all_ok(err is None):
@@ -577,70 +599,52 @@ def tokens_per_second_sharded(tb, lib, torch, dist, stream, rank, world):
 
         def token():
             for layer in range(m["L"]):
-                for (hs, cnt, k, ags, xb, q, l1, l2, o, gathered, rows) in plan:
+                for (hs, cnt, mout, k, ags, xb, q, l1, l2, row0, rows) in plan:
                     if rows > 0:
-                        if cnt == 1 and not m["os"]:
-                            tb.gemv(hs[layer], 1, xb, o[0, :rows])
-                        else:
-                            tb.preprocessor(k, 1, ags, xb, l1, l2, q)
-                            if cnt == 1:
-                                tb.qgemm_lut(hs[layer], 1, q, l1, l2, o[0, :rows])
+                        if m["os"]:
+                            tb.preprocessor(k, 1, ags, xb, l1, l2, q)          # one LUT per fused group (shared input)
+                        for c in range(cnt):
+                            tb.peer_outputs([sv.peer_ptr(p_) + 4 * (c * mout + row0) for p_ in range(world) if p_ != rank])
+                            dst = sv.local[c * mout + row0: c * mout + row0 + rows]
+                            if m["os"]:
+                                tb.qgemm_lut(hs[layer * cnt + c], 1, q, l1, l2, dst)
                             else:
-                                tb.qgemm_lut_grouped(hs[layer * cnt:(layer + 1) * cnt], 1, [q] * cnt, [l1] * cnt, [l2] * cnt,
-                                                     [o[c, :rows] for c in range(cnt)])
-                    dist.all_gather_into_tensor(gathered.view(-1), o.view(-1))      # the group's output vector on every rank
+                                tb.gemv(hs[layer * cnt + c], 1, xb, dst)      # LUT built inside the GEMV
+                    sv.barrier()                                               # the group's output vector is whole on every rank
 
-        graph, mode = None, "eager launches (NCCL capture failed)"
+        ok, mode = True, "one CUDA graph per token (library launches only: peer stores + one flag exchange per fused group)"
         try:
             with torch.cuda.stream(stream):
                 token()
             torch.cuda.synchronize()
-            eager_ok = True
+            tb.check(lib.tmac_b200_graph_begin(), "graph_begin")
+            token()
+            g = lib.tmac_b200_graph_end(); tb.check(g, "graph_end")
         except Exception as ex:
-            eager_ok, err = False, str(ex)[:160]
-        if not all_ok(eager_ok):
+            ok, err = False, str(ex)[:160]
+        if not all_ok(ok):
             res[name] = {"error": err or "another rank failed"}
             for h in handles:
                 h.free()
             continue
-        try:
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=stream):
-                token()
-            cap_ok = True
-        except Exception:
-            cap_ok = False
-            try:
-                torch.cuda.synchronize()
-            except Exception:
-                pass
-        if all_ok(cap_ok):
-            mode = "one CUDA graph per token (library launches + NCCL all-gathers)"
-            run = graph.replay
-        else:
-            graph = None
-            run = token
         n = 10
-        with torch.cuda.stream(stream):
-            for _ in range(2):
-                run()
-            torch.cuda.synchronize()
-            dist.barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            for _ in range(n):
-                run()
-            e1.record(stream)
+        tb.check(lib.tmac_b200_graph_launch(g, 2), "warm")
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream); tb.check(lib.tmac_b200_graph_launch(g, n), "run"); e1.record(stream)
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1) / n * 1e-3], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         sec = float(t.item())
         tot = torch.tensor([float(local_bytes)], device="cuda"); dist.all_reduce(tot)
-        res[name] = {"tokens_per_s_matmul_only": 1.0 / sec, "ms_per_token": sec * 1e3, "ranks": world, "collectives_per_token": m["L"] * len(plan),
+        res[name] = {"tokens_per_s_matmul_only": 1.0 / sec, "ms_per_token": sec * 1e3, "ranks": world, "nccl_launches_per_token": 0,
+                     "flag_exchanges_per_token": m["L"] * len(plan),
                      "resident_weight_GB_total": float(tot.item()) / 1e9, "weight_stream_GBps_total": float(tot.item()) / sec / 1e9, "step": mode}
-        del graph
+        lib.tmac_b200_graph_free(g)
         for h in handles:
             h.free()
+        sv.close(dist)
     return res
 
 

@@ -157,6 +157,24 @@ TMAC_B200_API int tmac_b200_qgemm_lut_grouped(const int64_t *handles, int count,
 /* Fused convenience (llama_cpp_init + llama_cpp_compute of the whole tensor in one call,
  * workspaces owned by the library): C [N][M] = qgemm_lut(preprocessor(B)). */
 TMAC_B200_API int tmac_b200_gemv(int64_t handle, int N, int dtype, const void *B, void *C);
+/* ---- multi-GPU row sharding without a collective launch ------------------------------------------------
+ * The reference spreads a mat-vec over threads by rows: tiles are independent given the replicated activation row
+ * (3rdparty/llama.cpp/ggml/src/ggml.c:12636-12691).  Over GPUs the same partition makes the "all-gather" of the output vector
+ * every rank storing its finished rows into every rank's vector: tmac_b200_peer_outputs arms the NEXT N = 1 launch
+ * (tmac_b200_gemv / tmac_b200_qgemm_lut) to store its rows, besides C, at ptrs[q] + the same index -- device pointers into peer
+ * memory, each already offset to this shard's first row.  The stores ride NVLink inside the GEMV's epilogue; a consumer on a
+ * peer may read them after the producing launch has completed and the ranks have synchronised.  One-shot, 0..7 peers. */
+TMAC_B200_API int tmac_b200_peer_outputs(void *const *ptrs, int count);
+/* The flag / barrier per fused group: one tiny launch after which, in stream order, every launch this rank AND its peers
+ * enqueued before their matching call has completed (so the peers' rows stored by tmac_b200_peer_outputs are in place).
+ * flags: (world + 1) x uint32 inside this rank's ipc allocation, zero-initialised; peer_flags[q]: rank q's array mapped here. */
+TMAC_B200_API int tmac_b200_peer_barrier(void *flags, void *const *peer_flags, int rank, int world);
+/* Device allocations other processes of the node can map (cudaIpc*): alloc writes a 64-byte handle to send to the peers. */
+TMAC_B200_API void *tmac_b200_ipc_alloc(size_t bytes, void *handle64);
+TMAC_B200_API void *tmac_b200_ipc_open(const void *handle64);
+TMAC_B200_API int tmac_b200_ipc_close(void *peer_ptr);
+TMAC_B200_API int tmac_b200_ipc_free(void *ptr);
+
 /* ---- decode sequences: a chain of (dependent) GEMVs in ONE persistent launch ------------------------------------------
  * The reference executes a token step as ggml's graph loop: one mul_mat node after the other on a persistent thread pool
  * (3rdparty/llama.cpp/ggml/src/ggml.c:12562-12706 per node; llama_cpp_init + llama_cpp_compute per node,

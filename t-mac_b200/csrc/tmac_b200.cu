@@ -94,6 +94,7 @@ struct Context {
     int seq_grid = 0;                    // decode sequences: grid override (tests: CTA-boundary placements); 0 = one CTA per SM
     int use_prefill16 = 0;               // DRAFT fp16-operand prefill tile (tmac_prefill16.cuh), opt-in until validated on hardware
     int use_prefill = 1, prefill_min_n = 32;   // N >= prefill_min_n: tcgen05 int8 tile (W2 g128 act64)                   // tmac_b200_gemv builds the LUT inside the GEMV when the grouping allows
+    int npeer = 0; void *peer_out[7] = {};   // one-shot: peer output vectors of the next N = 1 launch (tmac_b200_peer_outputs)
     int64_t next_hint = 0;               // one-shot: tensor whose blocks the next launch prefetches into L2
     std::map<int64_t, Resident> res;
     int64_t next_handle = 1;
@@ -284,6 +285,12 @@ int launch_gemv3(const Resident &R, int row_begin, int row_end, int N, const int
     const int agq = int_path ? 0 : std::min(L.act_group_size, L.ck) / 16;
     p.zp = L.zp; p.one_scale = L.one_scale; p.sd = L.sd; p.out_f16 = out_f16;
     p.blk_bytes = (int)L.blk; p.scale0 = L.scale0; p.rsb_stride = L.rsb_stride;
+    if (g.npeer) {
+        if (N != 1 || batch) { g.npeer = 0; return fail("peer outputs: N = 1, single-tensor launches only"); }
+        p.npeer = g.npeer;
+        for (int q = 0; q < g.npeer; ++q) p.Cpeer[q] = g.peer_out[q];
+        g.npeer = 0;
+    }
     p.pdl_late = (g.pdl_late >= 0) ? g.pdl_late : (fused_act ? 0 : 1);   // measured: fused launches prefer the early trigger
     const int nb = batch ? batch->n : 0;
     if (batch) { p.nbatch = nb; p.Wv = batch->W; p.qlutv = batch->q; p.lsv = batch->ls; p.lbv = batch->lb; p.Cv = batch->C; }
@@ -1091,6 +1098,74 @@ int tmac_b200_gemv(int64_t handle, int N, int dtype, const void *B, void *C) {
         CUDA_OK(cudaStreamSynchronize(g.stream()));
         if (kind_c == 0) std::memcpy(C, g.h_out.p, cb);
     }
+    return 0;
+}
+
+// ---- multi-GPU row sharding without a collective launch --------------------------------------------------
+// Rows shard naturally (ref:ggml.c:12636-12691: tiles are independent given the replicated activation row), so the
+// "all-gather" of a sharded GEMV is every rank storing its finished rows into every rank's output vector.  The next
+// N = 1 launch (tmac_b200_gemv / tmac_b200_qgemm_lut) stores its rows, besides C, at ptrs[q] + the same index as C --
+// device pointers into PEER memory (cudaIpcOpenMemHandle), each already offset to this shard's first row.  One-shot.
+int tmac_b200_peer_outputs(void *const *ptrs, int count) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    if (count < 0 || count > 7 || (count && !ptrs)) return fail("peer_outputs: 0..7 peers");
+    g.npeer = count;
+    for (int q = 0; q < count; ++q) g.peer_out[q] = ptrs[q];
+    return 0;
+}
+// One tiny launch: all launches this rank enqueued before it are complete, and so are the peers' up to their matching call --
+// the flag / barrier per fused group of a row-sharded model (peer stores into `flags` of every rank; see peer_barrier_kernel).
+// flags: this rank's (world + 1) x u32 array inside an ipc allocation; peer_flags[q]: rank q's array as mapped here.
+int tmac_b200_peer_barrier(void *flags, void *const *peer_flags, int rank, int world) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    if (!flags || !peer_flags || world < 1 || world > 8 || rank < 0 || rank >= world) return fail("peer_barrier: bad arguments");
+    // the pointer table lives in device memory (stable under graph capture): cached per (flags) key
+    static std::map<void *, void *> tables;
+    void *&dt = tables[flags];
+    if (!dt) {
+        if (cudaMalloc(&dt, 10 * sizeof(void *)) != cudaSuccess) { cudaGetLastError(); dt = nullptr; return fail("peer_barrier: out of device memory"); }
+        void *host[9] = {};
+        for (int q = 0; q < world; ++q) host[q] = peer_flags[q];
+        CUDA_OK(cudaMemcpy(dt, host, sizeof host, cudaMemcpyHostToDevice));
+    }
+    peer_barrier_kernel<<<1, 32, 0, g.stream()>>>((unsigned *)flags, (unsigned *const *)dt, rank, world, (int *)((void **)dt + 8));
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// Device allocations that other processes of the node can map: alloc returns the pointer and a 64-byte handle to send to the
+// peers; open maps a peer's allocation (peer access is enabled on demand); close / free undo them.
+void *tmac_b200_ipc_alloc(size_t bytes, void *handle64) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (ensure_init()) return nullptr;
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); fail("ipc_alloc: out of device memory"); return nullptr; }
+    cudaMemset(p, 0, bytes);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    if (cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle64, p) != cudaSuccess) { cudaGetLastError(); cudaFree(p); fail("cudaIpcGetMemHandle failed"); return nullptr; }
+    return p;
+}
+void *tmac_b200_ipc_open(const void *handle64) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (ensure_init()) return nullptr;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, sizeof h);
+    void *p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { cudaGetLastError(); fail(std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); return nullptr; }
+    return p;
+}
+int tmac_b200_ipc_close(void *peer_ptr) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    CUDA_OK(cudaIpcCloseMemHandle(peer_ptr));
+    return 0;
+}
+int tmac_b200_ipc_free(void *ptr) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g.inited) cudaStreamSynchronize(g.stream());
+    CUDA_OK(cudaFree(ptr));
     return 0;
 }
 

@@ -257,6 +257,10 @@ struct Gemv3Params {
     size_t rsb_stride;
     float scale0;
     long long *trace;
+    // multi-GPU row sharding: the finished rows are also stored straight into the peers' output vectors (P2P over NVLink),
+    // Cpeer[q] already offset to this shard's first row; N = 1 only
+    int npeer;
+    void *Cpeer[7];
 };
 #ifdef TMAC_ENABLE_TRACE
 __device__ __forceinline__ long long globaltimer_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
@@ -557,6 +561,10 @@ __global__ void __launch_bounds__(kG3MaxWarps * 32, MINB) gemv3_kernel(const Gem
             const size_t o = (size_t)n * p.ldc + (size_t)(row - p.c_row0);
             if (p.out_f16) reinterpret_cast<__half *>(Cb)[o] = __float2half_rn(out);
             else reinterpret_cast<float *>(Cb)[o] = out;
+            for (int q = 0; q < p.npeer; ++q) {      // the all-gather, fused into the epilogue: one store per peer and row
+                if (p.out_f16) reinterpret_cast<__half *>(p.Cpeer[q])[o] = __float2half_rn(out);
+                else reinterpret_cast<float *>(p.Cpeer[q])[o] = out;
+            }
         }
     }
     if (tid == 0) TMAC_TRACE(7);
@@ -698,6 +706,32 @@ __global__ void __launch_bounds__(kPreThreads) preprocessor_kernel(const TIn *B,
         lut_biases[(size_t)n * nag + a_begin + a] = bias;
         lut_scales[(size_t)n * nag + a_begin + a] = __fdiv_rn(__int_as_float(smax[a]), 127.0f);
     }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// peer_barrier_kernel: "every rank's launches before this point have completed" as a stream-ordered fact on every rank,
+// without a collective library call.  flags[0..world) are written by the peers (slot q by rank q), flags[world] is this
+// rank's own barrier count.  One block; thread q handles peer q.  Stores issued by EARLIER kernels of this stream
+// (e.g. the GEMV epilogues' peer stores) are complete when this kernel starts, so publishing the count after them
+// orders them before any peer's wake-up.  Bounded wait; *err != 0 if a peer never arrived.
+// ------------------------------------------------------------------------------------------
+static __global__ void peer_barrier_kernel(unsigned *flags, unsigned *const *peer_flags, int rank, int world, int *err) {
+    __shared__ unsigned s_epoch;
+    if (threadIdx.x == 0) { s_epoch = flags[world] + 1u; flags[world] = s_epoch; }
+    __syncthreads();
+    const unsigned epoch = s_epoch;
+    const int q = threadIdx.x;
+    if (q >= world || q == rank) return;
+    __threadfence_system();
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(peer_flags[q] + rank), "r"(epoch) : "memory");
+    unsigned v;
+    int spins = 0;
+    do {
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + q) : "memory");
+    } while ((int)(v - epoch) < 0 && ++spins < (1 << 22));
+    if ((int)(v - epoch) < 0) atomicExch(err, 1);
+    __threadfence_system();
 }
 
 }  // namespace tmac_b200

@@ -53,6 +53,7 @@ EXPORTS = [
     "tmac_b200_gguf_meta_number", "tmac_b200_gguf_meta_string", "tmac_b200_gguf_load_tensor",
     "tmac_b200_seq_create", "tmac_b200_seq_add_gemv", "tmac_b200_seq_build", "tmac_b200_seq_launch", "tmac_b200_seq_status",
     "tmac_b200_seq_info", "tmac_b200_seq_trace", "tmac_b200_seq_free",
+    "tmac_b200_peer_outputs", "tmac_b200_peer_barrier", "tmac_b200_ipc_alloc", "tmac_b200_ipc_open", "tmac_b200_ipc_close", "tmac_b200_ipc_free",
 ]
 
 _lib = None
@@ -106,6 +107,8 @@ def load() -> C.CDLL:
         "tmac_b200_gguf_load_tensor": (i64, [i64, i, C.POINTER(TensorExtra)]),
         "tmac_b200_seq_create": (i64, []), "tmac_b200_seq_add_gemv": (i, [i64, i64, vp, i, i, vp, i]),
         "tmac_b200_seq_build": (i, [i64]), "tmac_b200_seq_launch": (i, [i64]), "tmac_b200_seq_status": (i, [i64]),
+        "tmac_b200_peer_outputs": (i, [vp, i]), "tmac_b200_peer_barrier": (i, [vp, vp, i, i]), "tmac_b200_ipc_alloc": (vp, [sz, vp]), "tmac_b200_ipc_open": (vp, [vp]),
+        "tmac_b200_ipc_close": (i, [vp]), "tmac_b200_ipc_free": (i, [vp]),
         "tmac_b200_seq_info": (i, [i64, C.POINTER(C.c_int)]), "tmac_b200_seq_trace": (i, [i64, vp, sz]), "tmac_b200_seq_free": (i, [i64]),
     }
     for name, (res, args) in sig.items():
@@ -218,6 +221,72 @@ def gemv(wt: Weights, N, B, Cout, dtype=F32):
 
 def cbits(wt: Weights, N, qlut, out):
     check(load().tmac_b200_cbits(wt.handle, N, ptr(qlut), ptr(out)), "tmac_b200_cbits")
+
+
+def peer_outputs(ptrs) -> None:
+    """Arm the next N = 1 launch to store its rows into these peer-memory addresses too (tmac_b200_peer_outputs)."""
+    n = len(ptrs)
+    arr = (C.c_void_p * max(1, n))(*[int(p) for p in ptrs])
+    check(load().tmac_b200_peer_outputs(arr, n), "tmac_b200_peer_outputs")
+
+
+class _RawCuda:
+    """Device memory that is not owned by torch, exposed through __cuda_array_interface__ (torch.as_tensor wraps it)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class SharedVector:
+    """One float32 buffer per rank that every rank of the node can write (cudaIpc): `local` is this rank's buffer as a torch
+    tensor, `peer_ptr(q)` the address of rank q's buffer in this process.  Used for the all-gather fused into the GEMV
+    epilogue (tmac_b200_peer_outputs).  Collective: every rank must construct it."""
+
+    def __init__(self, nfloats: int, dist, rank: int, world: int):
+        import torch
+        lib = load()
+        nfloats += world + 1                    # + the barrier flags (tmac_b200_peer_barrier)
+        self.n, self.rank, self.world = nfloats, rank, world
+        h = (C.c_ubyte * 64)()
+        self.ptr = lib.tmac_b200_ipc_alloc(nfloats * 4, h)
+        if not self.ptr:
+            raise TMACError("tmac_b200_ipc_alloc failed: " + last_error())
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(h))
+        self.peers = {}
+        for q in range(world):
+            if q == rank:
+                continue
+            hb = (C.c_ubyte * 64).from_buffer_copy(handles[q])
+            pp = lib.tmac_b200_ipc_open(hb)
+            if not pp:
+                raise TMACError("tmac_b200_ipc_open failed: " + last_error())
+            self.peers[q] = pp
+        self._raw = _RawCuda(self.ptr, nfloats * 4)
+        self.local = torch.as_tensor(self._raw, device="cuda").view(torch.float32)[: nfloats - (world + 1)]
+        dist.barrier()
+
+    def peer_ptr(self, q: int) -> int:
+        return self.ptr if q == self.rank else self.peers[q]
+
+    def barrier(self):
+        """Stream-ordered barrier over the ranks (tmac_b200_peer_barrier); the last world + 1 floats of the buffer are its flags."""
+        off = 4 * (self.n - (self.world + 1))
+        arr = (C.c_void_p * 8)(*[self.peer_ptr(q) + off for q in range(self.world)] + [0] * (8 - self.world))
+        check(load().tmac_b200_peer_barrier(self.ptr + off, arr, self.rank, self.world), "tmac_b200_peer_barrier")
+
+    def close(self, dist=None):
+        lib = load()
+        if dist is not None:
+            dist.barrier()
+        for pp in self.peers.values():
+            lib.tmac_b200_ipc_close(pp)
+        self.peers = {}
+        if dist is not None:
+            dist.barrier()
+        if self.ptr:
+            lib.tmac_b200_ipc_free(self.ptr)
+            self.ptr = 0
 
 
 SEQ_WARPS = 19      # kSeqWarps (consumer warps per CTA of the sequence kernel)
