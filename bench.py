@@ -500,6 +500,41 @@ def main():
            "call": "tmac_b200_gemv(handle, 1, F32, host_x, host_out) per layer, synchronous: H2D copy of the activation row straight from the caller's "
                    "page-locked buffer + fused LUT/GEMV kernel storing the result into the caller's page-locked buffer + stream sync"}
     launches["n"] += 0
+    # ---- the same through the REFERENCE's own two hook symbols with host workspaces, as ggml calls them: task_init once, then
+    #      task_compute for the whole tensor (ref:ggml.c:12610-12630) or once per 64-row weight tile (ref:ggml.c:12662-12691,
+    #      172 tiles), driven by the C++ caller emulation tmac_b200_debug_ggml_mul_mat (no interpreter between the calls).
+    #      The weights are random bytes in the reference layout (every byte is a valid pair of LUT indices); parity of this
+    #      path is the test suite's job (test_ggml_caller_emulation_whole_tensor_and_per_tile).
+    try:
+        import ctypes as _C
+        rng = np.random.default_rng(3)
+        A_ref = rng.integers(0, 256, size=MOUT * K * BITS // 8, dtype=np.uint8)
+        S_ref = (np.abs(rng.standard_normal(MOUT * (K // GS) * 2)) * 0.01 + 1e-4).astype(np.float16).astype(np.float32)
+        kref = tb.make_kcfg(MOUT, K, BITS, 128, 16, GS, AGS, ZP, False)
+        tb.check(lib.tmac_b200_register_kcfg(_C.byref(kref)), "register_kcfg")
+        wt_ref = tb.upload_reference_layout(kref, A_ref, S_ref)
+        wdata = np.zeros(K * 4 + 2 * (K // AGS) * 4 + 64, np.uint8)
+        dst = np.zeros(MOUT, np.float32)
+        hx_np = hx.numpy()
+        ref_sym = {}
+        for label, per_tile, threads in (("whole_tensor", 0, 1), ("per_tile_1_thread", 1, 1), ("per_tile_4_threads", 1, min(4, os.cpu_count() or 1))):
+            def one(i):
+                tb.check(lib.tmac_b200_debug_ggml_mul_mat(A_ref.ctypes.data, S_ref.ctypes.data, hx_np[i % LAYERS].ctypes.data, wdata.ctypes.data,
+                                                          dst.ctypes.data, MOUT, K, BITS, 128 // BITS, per_tile, threads), "ggml emulation")
+            for i in range(3):
+                one(i)
+            t0 = time.perf_counter()
+            nrep = 40
+            for i in range(nrep):
+                one(i)
+            dt = (time.perf_counter() - t0) / nrep
+            ref_sym[label] = {"us_per_gemv": dt * 1e6, "GBps": algorithmic_bytes() / dt / 1e9}
+        ref_sym["note"] = ("ONE resident tensor (L2-warm weights): this measures the call path -- H2D of the row, LUT build, D2H of the LUT into the "
+                           "caller's workspace, GEMV, result into page-locked memory, per-tile row copies -- not the HBM stream")
+        e2e["reference_symbols"] = ref_sym
+        wt_ref.free()
+    except Exception as ex:
+        e2e["reference_symbols"] = {"error": str(ex)[:200]}
 
     extras = {}
     cpu = None

@@ -224,6 +224,14 @@ TMAC_B200_API void ggml_tmac_mul_mat_task_compute(void *src0, void *scales, void
                                                   void *lut_scales, void *lut_biases, void *dst,
                                                   int n, int k, int m, int bits);
 TMAC_B200_API void ggml_tmac_set_n_threads(int n_threads);
+#ifndef TMAC_B200_NO_GGML_DECLS
+/* Caller emulation (measurement / tests): ggml's T-MAC mul_mat branch for one activation row with HOST buffers --
+ * task_init once, then task_compute once for the whole tensor (per_tile = 0; ref:ggml.c:12610-12630) or once per weight tile
+ * of tile_rows rows from `threads` tile-stealing host threads (per_tile = 1; ref:ggml.c:12632-12703).  wdata: the op's
+ * workspace (ggml_tmac_mul_mat_get_wsize bytes). */
+TMAC_B200_API int tmac_b200_debug_ggml_mul_mat(void *src0_qweights, void *src0_scales, void *src1_row, void *wdata, void *dst,
+                                               int ne01, int ne00, int bits, int tile_rows, int per_tile, int threads);
+#endif
 TMAC_B200_API int ggml_tmac_get_type_bits(int ggml_type);           /* ggml-tmac.cpp:503-526 */
 #endif
 /* ggml-free forms of can_mul_mat / get_wsize / get_nbytes / transform_tensor */

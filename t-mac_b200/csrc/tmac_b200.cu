@@ -11,12 +11,16 @@
 #include "../../include/tmac_b200.h"
 
 #include <algorithm>
+#include <atomic>
+#include <functional>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <sys/mman.h>
 #include <map>
 #include <mutex>
+#include <shared_mutex>
 #include <set>
 #include <string>
 #include <vector>
@@ -77,6 +81,25 @@ struct Resident {
     void *reserved = nullptr;            // address range reserved (PROT_NONE, no memory) to serve as the host alias key
     size_t reserved_bytes = 0;
     float *host_scales = nullptr;        // scales in the reference's run-time order, owned here (tmac_tensor_extra::scales)
+    int64_t id = 0;                      // its handle
+};
+
+// A LUT that lives in CALLER host memory (the reference's workspace, ref:ggml.c:12566-12576) and its device-resident copy.
+// ggml writes the LUT once per mat-vec (task_init) and then calls task_compute once per weight tile with the same pointers
+// (ref:ggml.c:12662-12691): the copy is keyed by the host QLUT pointer AND compared with the bytes the call passes, so a caller that
+// rewrites the table is never served stale data, and the first tile call computes the whole tensor once (`res`), later tile
+// calls of the same (LUT bytes, tensor) copy their rows out.
+struct HostLut {
+    const void *hq = nullptr;
+    std::vector<unsigned char> copy;     // the bytes the device copy was made from: QLUT || LUT_Scales || LUT_Biases (empty = invalid)
+    size_t qb = 0, sb = 0;
+    int N = 0;
+    DevBuf dq, dls, dlb;
+    bool sym = false;
+    int64_t res_id = 0;                  // tensor whose full result `res` holds (0 = none)
+    int res_dtype = 0;
+    PinBuf res;                          // [N][Mout] in page-locked host memory, written by the kernel itself
+    uint64_t stamp = 0;
 };
 
 struct Context {
@@ -99,6 +122,8 @@ struct Context {
     std::map<int64_t, Resident> res;
     int64_t next_handle = 1;
     std::vector<tmac_b200_kcfg> kcfgs;
+    HostLut hluts[4];
+    uint64_t hlut_clock = 0;
     std::set<const void *> sym_qluts;    // device QLUT buffers last written by our preprocessor
     std::vector<std::pair<std::vector<const void *>, void *>> ptr_tables;   // grouped-launch pointer tables
     // workspaces
@@ -111,7 +136,7 @@ struct Context {
 };
 
 Context g;
-std::mutex g_mu;
+std::shared_mutex g_mu;     // exclusive for everything that launches or mutates; shared for the read-only tile fast path
 std::map<int64_t, GgufFile *> g_gguf;    // open GGUF files (tmac_b200_gguf_*)
 int64_t g_next_gguf = 1;
 
@@ -138,9 +163,33 @@ int64_t g_next_seq = 1;
 
 bool is_device_ptr(const void *p) {
     if (!p) return false;
+    // ggml calls in once per weight tile with pointers into the same few host buffers: remember which 4 KB pages were ORDINARY
+    // HOST memory (a page of host address space never becomes device memory; one that gets page-locked later is still valid to
+    // treat as pageable), so that cudaPointerGetAttributes (~0.5 us) is not paid 4 times per tile
+    static thread_local uintptr_t host_pages[64];
+    const uintptr_t page = (uintptr_t)p >> 12, slot = page & 63;
+    if (host_pages[slot] == page) return false;
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (a.type == cudaMemoryTypeUnregistered) host_pages[slot] = page;
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// The entry whose device copy was made from exactly these host bytes (memcmp of ~17 KB: ~0.1 us), or null.
+HostLut *hlut_find(const void *hq, const void *ls, const void *lb, size_t qb, size_t sb) {
+    for (HostLut &e : g.hluts)
+        if (e.hq == hq && e.qb == qb && e.sb == sb && e.copy.size() == qb + 2 * sb && !std::memcmp(e.copy.data(), hq, qb) &&
+            !std::memcmp(e.copy.data() + qb, ls, sb) && !std::memcmp(e.copy.data() + qb + sb, lb, sb)) { e.stamp = ++g.hlut_clock; return &e; }
+    return nullptr;
+}
+HostLut *hlut_slot(const void *hq) {     // the entry of this host pointer, else the least recently used one
+    HostLut *best = &g.hluts[0];
+    for (HostLut &e : g.hluts) {
+        if (e.hq == hq) { best = &e; break; }
+        if (e.stamp < best->stamp) best = &e;
+    }
+    best->hq = hq; best->copy.clear(); best->res_id = 0; best->stamp = ++g.hlut_clock;
+    return best;
 }
 
 // 0 = ordinary host memory, 1 = page-locked host memory the device can address (dev = its device alias), 2 = device / managed
@@ -479,6 +528,7 @@ int64_t register_resident(const tmac_b200_kcfg &cfg, const PlainWeights &P, cons
     R.host_a = (const unsigned char *)host_alias;
     R.host_a_bytes = alias_bytes;
     const int64_t h = g.next_handle++;
+    R.id = h;
     g.res[h] = R;
     return h;
 }
@@ -531,7 +581,7 @@ size_t esize(int dtype) { return dtype == TMAC_B200_F16 ? 2 : 4; }
 extern "C" {
 
 int tmac_b200_init(int device) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     if (!g.inited && device >= 0) {
         if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return fail("cudaSetDevice failed"); }
     }
@@ -539,7 +589,7 @@ int tmac_b200_init(int device) {
 }
 
 void tmac_b200_shutdown(void) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     if (!g.inited) return;
     cudaStreamSynchronize(g.stream());
     for (auto &kv : g_seqs) kv.second.release();
@@ -557,6 +607,11 @@ void tmac_b200_shutdown(void) {
     }
     g.res.clear();
     for (DevBuf *b : {&g.d_b, &g.d_qlut, &g.d_ls, &g.d_lb, &g.d_c, &g.d_cbits, &g.d_trace, &g.d_tiles}) { if (b->p) cudaFree(b->p); b->p = nullptr; b->cap = 0; }
+    for (HostLut &e : g.hluts) {
+        for (DevBuf *b : {&e.dq, &e.dls, &e.dlb}) { if (b->p) cudaFree(b->p); b->p = nullptr; b->cap = 0; }
+        if (e.res.p) cudaFreeHost(e.res.p);
+        e = HostLut();
+    }
     for (PinBuf *b : {&g.h_in, &g.h_out}) { if (b->p) cudaFreeHost(b->p); b->p = nullptr; b->cap = 0; }
     if (g.stage_ev) cudaEventDestroy(g.stage_ev);
     g.stage_ev = nullptr; g.stage_pending = false;
@@ -570,7 +625,7 @@ const char *tmac_b200_last_error(void) { return t_err.c_str(); }
 int tmac_b200_version(void) { return 100; }
 
 int tmac_b200_set_stream(void *stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     if (ensure_init()) return -1;
     g.user = (cudaStream_t)stream;
     g.use_user = stream != nullptr;
@@ -578,14 +633,14 @@ int tmac_b200_set_stream(void *stream) {
 }
 
 int tmac_b200_set_float_type(int dtype) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     if (dtype != TMAC_B200_F32 && dtype != TMAC_B200_F16) return fail("bad dtype");
     g.float_type = dtype;
     return 0;
 }
 
 int tmac_b200_register_kcfg(const tmac_b200_kcfg *cfg) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     if (!cfg) return fail("null kcfg");
     tmac_b200_kcfg c = *cfg;
     if (c.simd_n_in == 0) c.simd_n_in = 16;
@@ -599,12 +654,12 @@ int tmac_b200_register_kcfg(const tmac_b200_kcfg *cfg) {
 }
 
 void tmac_b200_clear_kcfg(void) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     g.kcfgs.clear();
 }
 
 int tmac_b200_find_kcfg(int m_times_bits, int k, int bits, tmac_b200_kcfg *out) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     const tmac_b200_kcfg *c = find_kcfg_locked(m_times_bits, k, bits);
     if (!c) return fail("no kcfg for m=" + std::to_string(m_times_bits) + " k=" + std::to_string(k) + " b=" + std::to_string(bits));
     if (out) *out = *c;
@@ -655,7 +710,7 @@ int tmac_b200_load_kcfg_file(const char *path) {
 }
 
 int64_t tmac_b200_upload_weights(const tmac_b200_kcfg *cfg_in, const void *A, const void *scales, int scales_dtype) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     if (ensure_init()) return -1;
     if (!cfg_in || !A || !scales) return fail("upload_weights: null argument");
     if (is_device_ptr(A)) return fail("upload_weights: A must be a host pointer (reference layout)");
@@ -679,7 +734,7 @@ int64_t tmac_b200_upload_weights(const tmac_b200_kcfg *cfg_in, const void *A, co
 
 int64_t tmac_b200_upload_plain_rows(const tmac_b200_kcfg *cfg_in, const uint8_t *w, const float *scales, const float *zeros,
                                     int row0, int rows) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     if (ensure_init()) return -1;
     if (!cfg_in || !w || !scales) return fail("upload_plain: null argument");
     tmac_b200_kcfg cfg = *cfg_in;
@@ -774,10 +829,11 @@ int64_t tmac_b200_debug_encode(const tmac_b200_kcfg *cfg_in, const void *A, cons
 }
 
 int tmac_b200_free_weights(int64_t handle) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     auto it = g.res.find(handle);
     if (it == g.res.end()) return fail("bad handle");
     cudaStreamSynchronize(g.stream());
+    for (HostLut &e : g.hluts) if (e.res_id == handle) e.res_id = 0;
     cudaFree(it->second.d);
     if (it->second.reserved) munmap(it->second.reserved, it->second.reserved_bytes);
     std::free(it->second.host_scales);
@@ -786,7 +842,7 @@ int tmac_b200_free_weights(int64_t handle) {
 }
 
 size_t tmac_b200_weights_nbytes(int64_t handle) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     auto it = g.res.find(handle);
     return it == g.res.end() ? 0 : it->second.L.total;
 }
@@ -794,7 +850,7 @@ size_t tmac_b200_weights_nbytes(int64_t handle) {
 // Second resident copy of the same tensor in its own HBM allocation (benchmarks rotate through
 // distinct buffers so that weights stream from HBM, not L2; multi-layer models with tied shapes).
 int64_t tmac_b200_clone_weights(int64_t handle) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     auto it = g.res.find(handle);
     if (it == g.res.end()) return fail("clone: bad handle");
     Resident R = it->second;
@@ -803,6 +859,7 @@ int64_t tmac_b200_clone_weights(int64_t handle) {
     if (cudaMalloc((void **)&R.d, R.L.total) != cudaSuccess) { cudaGetLastError(); return fail("out of device memory for clone"); }
     if (cudaMemcpy(R.d, it->second.d, R.L.total, cudaMemcpyDeviceToDevice) != cudaSuccess) { cudaFree(R.d); return fail("clone copy failed"); }
     const int64_t h = g.next_handle++;
+    R.id = h;
     g.res[h] = R;
     return h;
 }
@@ -811,13 +868,13 @@ int64_t tmac_b200_clone_weights(int64_t handle) {
 // sequence once eagerly first so that every workspace is allocated) and replay it. -------------
 
 int tmac_b200_graph_begin(void) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     if (ensure_init()) return -1;
     CUDA_OK(cudaStreamBeginCapture(g.stream(), cudaStreamCaptureModeThreadLocal));
     return 0;
 }
 int64_t tmac_b200_graph_end(void) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     cudaGraph_t graph = nullptr;
     CUDA_OK(cudaStreamEndCapture(g.stream(), &graph));
     cudaGraphExec_t exec = nullptr;
@@ -829,14 +886,14 @@ int64_t tmac_b200_graph_end(void) {
     return h;
 }
 int tmac_b200_graph_launch(int64_t graph, int times) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     auto it = g_graphs.find(graph);
     if (it == g_graphs.end()) return fail("graph_launch: bad handle");
     for (int i = 0; i < times; ++i) CUDA_OK(cudaGraphLaunch(it->second, g.stream()));
     return 0;
 }
 int tmac_b200_graph_free(int64_t graph) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     auto it = g_graphs.find(graph);
     if (it == g_graphs.end()) return fail("graph_free: bad handle");
     cudaGraphExecDestroy(it->second);
@@ -844,7 +901,7 @@ int tmac_b200_graph_free(int64_t graph) {
     return 0;
 }
 int tmac_b200_sync(void) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     if (!g.inited) return 0;
     CUDA_OK(cudaStreamSynchronize(g.stream()));
     return 0;
@@ -853,7 +910,7 @@ int tmac_b200_sync(void) {
 // Debug / reporting: {cluster size, warps per CTA, chunks per warp, min blocks variant, grid.x, PB, sym, batch}
 // of the last qgemm_lut launch.
 int tmac_b200_debug_last_launch(int *out8) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     if (!out8) return fail("null");
     std::memcpy(out8, g.last_launch, sizeof g.last_launch);
     return 0;
@@ -863,14 +920,14 @@ int tmac_b200_debug_last_launch(int *out8) {
 // blocks into L2 (cp.async.bulk.prefetch.L2) while it computes, so that the HBM stream of launch
 // i+1 overlaps launch i.  Ignored unless the tensor has the same stream geometry.
 int tmac_b200_hint_next_weights(int64_t handle) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     g.next_hint = handle;
     return 0;
 }
 
 // Debug: per-CTA clock64 stamps of the last gemv3 launch ([ctas][8]); returns #ctas or -1.
 int tmac_b200_debug_trace(long long *dst, int cap_ctas) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     if (!g.trace || !g.d_trace.p) return fail("trace disabled (TMAC_B200_TRACE=1)");
     CUDA_OK(cudaStreamSynchronize(g.stream()));
     const int n = std::min(cap_ctas, g.trace_ctas * 8);   // ring of 8 launches x ctas
@@ -880,7 +937,7 @@ int tmac_b200_debug_trace(long long *dst, int cap_ctas) {
 
 // Tuning / A-B knobs at run time (same names as the TMAC_B200_* environment variables, lower case, without the prefix).
 int tmac_b200_debug_set(const char *key, int value) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     if (ensure_init()) return -1;
     const std::string k = key ? key : "";
     if (k == "seq_grid") g.seq_grid = value;
@@ -901,13 +958,13 @@ int tmac_b200_debug_set(const char *key, int value) {
 }
 
 int tmac_b200_set_lut_mode(int mode) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     g.lut_mode = mode;
     return 0;
 }
 
 int tmac_b200_preprocessor(int K, int N, int act_group_size, int dtype, const void *B, void *LUT_Scales, void *LUT_Biases, void *QLUT) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     if (ensure_init()) return -1;
     if (!B || !LUT_Scales || !LUT_Biases || !QLUT || N <= 0) return fail("preprocessor: null/empty argument");
     const int ags = (act_group_size <= 0 || act_group_size > K) ? K : act_group_size;
@@ -927,9 +984,11 @@ int tmac_b200_preprocessor(int K, int N, int act_group_size, int dtype, const vo
     float *dls = (float *)LUT_Scales, *dlb = (float *)LUT_Biases;
     int8_t *dq = (int8_t *)QLUT;
     const size_t qb = (size_t)N * K * 4, sb = (size_t)N * nag * 4;
-    if (!dev_out) {
-        if (g.d_qlut.ensure(qb) || g.d_ls.ensure(sb) || g.d_lb.ensure(sb)) return fail("out of device memory");
-        dls = (float *)g.d_ls.p; dlb = (float *)g.d_lb.p; dq = (int8_t *)g.d_qlut.p;
+    HostLut *hl = nullptr;
+    if (!dev_out) {          // the LUT goes to the caller's host workspace AND stays on the device for the compute calls that follow
+        hl = hlut_slot(QLUT);
+        if (hl->dq.ensure(qb) || hl->dls.ensure(sb) || hl->dlb.ensure(sb)) return fail("out of device memory");
+        dls = (float *)hl->dls.p; dlb = (float *)hl->dlb.p; dq = (int8_t *)hl->dq.p;
     }
     if (launch_preprocessor(K, N, ags, dtype, dB, dls, dlb, dq)) return -1;
     if (!dev_out) {
@@ -942,6 +1001,8 @@ int tmac_b200_preprocessor(int K, int N, int act_group_size, int dtype, const vo
         std::memcpy(QLUT, ho, qb);
         std::memcpy(LUT_Scales, ho + qb, sb);
         std::memcpy(LUT_Biases, ho + qb + sb, sb);
+        hl->copy.assign((const unsigned char *)ho, (const unsigned char *)ho + qb + 2 * sb);
+        hl->qb = qb; hl->sb = sb; hl->N = N; hl->sym = true; hl->res_id = 0;
     }
     return 0;
 }
@@ -959,19 +1020,46 @@ static int qgemm_impl(Resident &R, int row0, int rows, int N, int dtype, const v
     const int8_t *dq = (const int8_t *)QLUT;
     const float *dls = (const float *)LUT_Scales, *dlb = (const float *)LUT_Biases;
     bool sym;
+    HostLut *hl = nullptr;
     if (!dev_lut) {
-        sym = host_lut_symmetric((const int8_t *)QLUT, (size_t)N * L.K / 4);
-        stage_wait();
-        if (g.h_in.ensure(qb + 2 * sb)) return fail("out of pinned memory");
-        if (h2d(g.d_qlut, g.h_in, 0, QLUT, qb) || h2d(g.d_ls, g.h_in, qb, LUT_Scales, sb) || h2d(g.d_lb, g.h_in, qb + sb, LUT_Biases, sb)) return -1;
-        stage_mark();
-        dq = (const int8_t *)g.d_qlut.p; dls = (const float *)g.d_ls.p; dlb = (const float *)g.d_lb.p;
+        // device-resident copy keyed by (host pointer, content hash): written by the preprocessor call that filled this host
+        // workspace, or uploaded here once when the caller brings a table of its own
+        hl = hlut_find(QLUT, LUT_Scales, LUT_Biases, qb, sb);
+        if (!hl) {
+            hl = hlut_slot(QLUT);
+            stage_wait();
+            if (g.h_in.ensure(qb + 2 * sb)) return fail("out of pinned memory");
+            if (h2d(hl->dq, g.h_in, 0, QLUT, qb) || h2d(hl->dls, g.h_in, qb, LUT_Scales, sb) || h2d(hl->dlb, g.h_in, qb + sb, LUT_Biases, sb)) return -1;
+            stage_mark();
+            hl->copy.resize(qb + 2 * sb);
+            std::memcpy(hl->copy.data(), QLUT, qb); std::memcpy(hl->copy.data() + qb, LUT_Scales, sb); std::memcpy(hl->copy.data() + qb + sb, LUT_Biases, sb);
+            hl->qb = qb; hl->sb = sb; hl->N = N; hl->res_id = 0;
+            hl->sym = host_lut_symmetric((const int8_t *)QLUT, (size_t)N * L.K / 4);
+        }
+        sym = hl->sym;
+        dq = (const int8_t *)hl->dq.p; dls = (const float *)hl->dls.p; dlb = (const float *)hl->dlb.p;
     } else
         sym = g.sym_qluts.count(QLUT) != 0;
     if (g.lut_mode == 1) sym = false;
     if (g.lut_mode == 2) sym = true;
+    const size_t es = esize(dtype);
+    if (hl && !dev_c) {
+        // host LUT, host output (the reference's callers): the whole tensor is computed ONCE per (LUT bytes, tensor) straight
+        // into page-locked host memory; this call and the later tile calls of the same mat-vec copy their rows out
+        const bool hit = hl->res_id == R.id && hl->res_dtype == dtype && hl->N == N;
+        if (!hit) {
+            const size_t full = (size_t)N * L.Mout * es;
+            if (hl->res.ensure(full)) return fail("out of pinned memory");
+            if (launch_gemv(R, 0, L.Mout, N, dq, dls, dlb, hl->res.p, L.Mout, 0, dtype == TMAC_B200_F16, sym, nullptr)) return -1;
+            CUDA_OK(cudaStreamSynchronize(g.stream()));
+            hl->res_id = R.id; hl->res_dtype = dtype; hl->N = N;
+        }
+        for (int n = 0; n < N; ++n)
+            std::memcpy((char *)C + (size_t)n * rows * es, (const char *)hl->res.p + ((size_t)n * L.Mout + row0) * es, (size_t)rows * es);
+        return 0;
+    }
     void *dC = C;
-    const size_t cb = (size_t)N * rows * esize(dtype);
+    const size_t cb = (size_t)N * rows * es;
     if (!dev_c) {
         if (g.d_c.ensure(cb)) return fail("out of device memory");
         dC = g.d_c.p;
@@ -988,7 +1076,7 @@ static int qgemm_impl(Resident &R, int row0, int rows, int N, int dtype, const v
 
 int tmac_b200_qgemm_lut(int64_t handle, int row0, int rows, int N, int dtype, const void *QLUT, const void *LUT_Scales,
                         const void *LUT_Biases, void *C) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     if (ensure_init()) return -1;
     auto it = g.res.find(handle);
     if (it == g.res.end()) return fail("qgemm_lut: bad weight handle");
@@ -1001,7 +1089,7 @@ int tmac_b200_qgemm_lut(int64_t handle, int row0, int rows, int N, int dtype, co
 // QLUT[i], LUT_Scales[i], LUT_Biases[i], C[i] are per-problem device pointers (host arrays of pointers).
 int tmac_b200_qgemm_lut_grouped(const int64_t *handles, int count, int N, int dtype, const void *const *QLUT,
                                 const void *const *LUT_Scales, const void *const *LUT_Biases, void *const *C) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     if (ensure_init()) return -1;
     if (!handles || count <= 0 || count > 65535 || !QLUT || !LUT_Scales || !LUT_Biases || !C) return fail("grouped: bad arguments");
     std::vector<const Resident *> rs(count);
@@ -1047,7 +1135,7 @@ int tmac_b200_qgemm_lut_grouped(const int64_t *handles, int count, int N, int dt
 }
 
 int tmac_b200_gemv(int64_t handle, int N, int dtype, const void *B, void *C) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     if (ensure_init()) return -1;
     auto it = g.res.find(handle);
     if (it == g.res.end()) return fail("gemv: bad weight handle");
@@ -1107,7 +1195,7 @@ int tmac_b200_gemv(int64_t handle, int N, int dtype, const void *B, void *C) {
 // N = 1 launch (tmac_b200_gemv / tmac_b200_qgemm_lut) stores its rows, besides C, at ptrs[q] + the same index as C --
 // device pointers into PEER memory (cudaIpcOpenMemHandle), each already offset to this shard's first row.  One-shot.
 int tmac_b200_peer_outputs(void *const *ptrs, int count) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     if (ensure_init()) return -1;
     if (count < 0 || count > 7 || (count && !ptrs)) return fail("peer_outputs: 0..7 peers");
     g.npeer = count;
@@ -1118,7 +1206,7 @@ int tmac_b200_peer_outputs(void *const *ptrs, int count) {
 // the flag / barrier per fused group of a row-sharded model (peer stores into `flags` of every rank; see peer_barrier_kernel).
 // flags: this rank's (world + 1) x u32 array inside an ipc allocation; peer_flags[q]: rank q's array as mapped here.
 int tmac_b200_peer_barrier(void *flags, void *const *peer_flags, int rank, int world) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     if (ensure_init()) return -1;
     if (!flags || !peer_flags || world < 1 || world > 8 || rank < 0 || rank >= world) return fail("peer_barrier: bad arguments");
     // the pointer table lives in device memory (stable under graph capture): cached per (flags) key
@@ -1138,7 +1226,7 @@ int tmac_b200_peer_barrier(void *flags, void *const *peer_flags, int rank, int w
 // Device allocations that other processes of the node can map: alloc returns the pointer and a 64-byte handle to send to the
 // peers; open maps a peer's allocation (peer access is enabled on demand); close / free undo them.
 void *tmac_b200_ipc_alloc(size_t bytes, void *handle64) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     if (ensure_init()) return nullptr;
     void *p = nullptr;
     if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); fail("ipc_alloc: out of device memory"); return nullptr; }
@@ -1148,7 +1236,7 @@ void *tmac_b200_ipc_alloc(size_t bytes, void *handle64) {
     return p;
 }
 void *tmac_b200_ipc_open(const void *handle64) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     if (ensure_init()) return nullptr;
     cudaIpcMemHandle_t h;
     std::memcpy(&h, handle64, sizeof h);
@@ -1158,12 +1246,12 @@ void *tmac_b200_ipc_open(const void *handle64) {
     return p;
 }
 int tmac_b200_ipc_close(void *peer_ptr) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     CUDA_OK(cudaIpcCloseMemHandle(peer_ptr));
     return 0;
 }
 int tmac_b200_ipc_free(void *ptr) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     if (g.inited) cudaStreamSynchronize(g.stream());
     CUDA_OK(cudaFree(ptr));
     return 0;
@@ -1174,7 +1262,7 @@ int tmac_b200_ipc_free(void *ptr) {
 // (3rdparty/llama.cpp/ggml/src/ggml.c:12562-12706 per node); a sequence is that loop for the quantised linears.
 
 int64_t tmac_b200_seq_create(void) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     if (ensure_init()) return -1;
     const int64_t h = g_next_seq++;
     g_seqs[h];
@@ -1182,7 +1270,7 @@ int64_t tmac_b200_seq_create(void) {
 }
 
 int tmac_b200_seq_add_gemv(int64_t seq, int64_t handle, const void *x, int in_op, int in_offset, void *C, int dtype) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     auto it = g_seqs.find(seq);
     if (it == g_seqs.end()) return fail("seq_add_gemv: bad sequence");
     Sequence &S = it->second;
@@ -1204,7 +1292,7 @@ int tmac_b200_seq_add_gemv(int64_t seq, int64_t handle, const void *x, int in_op
 }
 
 int tmac_b200_seq_build(int64_t seq) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     auto it = g_seqs.find(seq);
     if (it == g_seqs.end()) return fail("seq_build: bad sequence");
     Sequence &S = it->second;
@@ -1347,7 +1435,7 @@ int tmac_b200_seq_build(int64_t seq) {
 }
 
 int tmac_b200_seq_launch(int64_t seq) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     auto it = g_seqs.find(seq);
     if (it == g_seqs.end()) return fail("seq_launch: bad sequence");
     Sequence &S = it->second;
@@ -1369,7 +1457,7 @@ int tmac_b200_seq_launch(int64_t seq) {
 
 /* Synchronises the stream and returns the sequence's error flag (0 = every wait completed). */
 int tmac_b200_seq_status(int64_t seq) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     auto it = g_seqs.find(seq);
     if (it == g_seqs.end() || !it->second.built) return fail("seq_status: bad sequence");
     CUDA_OK(cudaStreamSynchronize(g.stream()));
@@ -1381,7 +1469,7 @@ int tmac_b200_seq_status(int64_t seq) {
 
 /* info[8] = {grid, ring slots, slot bytes, shared memory bytes, ops, planes/word, quads/chunk, quads/act group} */
 int tmac_b200_seq_info(int64_t seq, int *out8) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     auto it = g_seqs.find(seq);
     if (it == g_seqs.end() || !it->second.built || !out8) return fail("seq_info: bad sequence");
     const Sequence &S = it->second;
@@ -1392,7 +1480,7 @@ int tmac_b200_seq_info(int64_t seq, int *out8) {
 
 /* Debug (knob "trace" set before seq_build): globaltimer stamps [ops][grid][8] of the last launch; returns grid. */
 int tmac_b200_seq_trace(int64_t seq, long long *dst, size_t cap_bytes) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     auto it = g_seqs.find(seq);
     if (it == g_seqs.end() || !it->second.built || !it->second.d_trace) return fail("seq_trace: tracing was not enabled when the sequence was built");
     CUDA_OK(cudaStreamSynchronize(g.stream()));
@@ -1402,7 +1490,7 @@ int tmac_b200_seq_trace(int64_t seq, long long *dst, size_t cap_bytes) {
 }
 
 int tmac_b200_seq_free(int64_t seq) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     auto it = g_seqs.find(seq);
     if (it == g_seqs.end()) return fail("seq_free: bad sequence");
     if (g.inited) cudaStreamSynchronize(g.stream());
@@ -1412,7 +1500,7 @@ int tmac_b200_seq_free(int64_t seq) {
 }
 
 int tmac_b200_cbits(int64_t handle, int N, const void *QLUT, int32_t *CBits) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     if (ensure_init()) return -1;
     auto it = g.res.find(handle);
     if (it == g.res.end()) return fail("cbits: bad weight handle");
@@ -1449,7 +1537,7 @@ int tmac_b200_cbits(int64_t handle, int N, const void *QLUT, int32_t *CBits) {
 int preprocessor_int8(int m, int k, int n, int b, void *B, void *LUT_Scales, void *LUT_Biases, void *QLUT) {
     int ags, dtype;
     {
-        std::lock_guard<std::mutex> lk(g_mu);
+        std::unique_lock<std::shared_mutex> lk(g_mu);
         const tmac_b200_kcfg *c = find_kcfg_locked(m, k, b);
         if (!c) return fail("preprocessor_int8: shape not configured (m=" + std::to_string(m) + ", k=" + std::to_string(k) + ", b=" + std::to_string(b) + ")");
         ags = c->act_group_size;
@@ -1460,7 +1548,28 @@ int preprocessor_int8(int m, int k, int n, int b, void *B, void *LUT_Scales, voi
 
 int qgemm_lut_int8(int m, int k, int n, int b, void *A, void *LUT, void *Scales, void *LUT_Scales, void *LUT_Biases, void *C) {
     (void)Scales;  // the resident copy carries the scales that were uploaded together with A
-    std::lock_guard<std::mutex> lk(g_mu);
+    if (g.inited && b >= 1 && b <= 4 && m > 0 && m % b == 0 && !is_device_ptr(LUT) && !is_device_ptr(C)) {
+        // read-only fast path (shared lock): a tile call of a mat-vec whose whole-tensor result is already in page-locked memory
+        // (computed by an earlier tile call with the same LUT bytes) only copies its rows -- ggml's workers do this concurrently
+        std::shared_lock<std::shared_mutex> rl(g_mu);
+        size_t off = 0;
+        Resident *R = find_by_alias(A, &off);
+        if (R && R->cfg.K == k && R->cfg.bits == b) {
+            const size_t tile_bytes = (size_t)(k / 4) * R->cfg.bm / 2;
+            const int row0 = (int)(off / tile_bytes) * (R->cfg.bm / b), rows = m / b;
+            const size_t qb = (size_t)n * k * 4, sb = (size_t)n * (k / R->L.act_group_size) * 4, es = esize(g.float_type);
+            if (off % tile_bytes == 0 && row0 + rows <= R->L.Mout)
+                for (HostLut &e : g.hluts)
+                    if (e.hq == LUT && e.res_id == R->id && e.res_dtype == g.float_type && e.N == n && e.qb == qb && e.sb == sb &&
+                        e.copy.size() == qb + 2 * sb && !std::memcmp(e.copy.data(), LUT, qb) && !std::memcmp(e.copy.data() + qb, LUT_Scales, sb) &&
+                        !std::memcmp(e.copy.data() + qb + sb, LUT_Biases, sb)) {
+                        for (int r = 0; r < n; ++r)
+                            std::memcpy((char *)C + (size_t)r * rows * es, (const char *)e.res.p + ((size_t)r * R->L.Mout + row0) * es, (size_t)rows * es);
+                        return 0;
+                    }
+        }
+    }
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     if (ensure_init()) return -1;
     if (b < 1 || b > 4 || m <= 0 || m % b) return fail("qgemm_lut_int8: bad m/b");
     size_t off = 0;
@@ -1494,6 +1603,62 @@ void ggml_tmac_mul_mat_task_compute(void *src0, void *scales, void *qlut, void *
     if (qgemm_lut_int8(n * bits, k, m, bits, src0, qlut, scales, lut_scales, lut_biases, dst) != 0)
         fprintf(stderr, "ggml_tmac_mul_mat_task_compute: %s\n", tmac_b200_last_error());
 }
+// Caller emulation for measurements and tests: ggml_compute_forward_mul_mat's T-MAC branch (ref:ggml.c:12562-12706) for one
+// activation row, in C++ so that no interpreter overhead sits between the hook calls.  Phase 1: ggml_tmac_mul_mat_task_init
+// (one call).  Phase 2: per_tile = 0 -> one ggml_tmac_mul_mat_task_compute for the whole tensor (the TMAC_USE_TVM_THREADPOOL
+// branch, :12610-12630); per_tile = 1 -> one call per weight tile of `tile_rows` rows from `threads` host threads that steal
+// tiles through an atomic counter (:12632-12703).  All pointers are HOST pointers as in ggml.
+int tmac_b200_debug_ggml_mul_mat(void *src0_qweights, void *src0_scales, void *src1_row, void *wdata, void *dst, int ne01, int ne00,
+                                 int bits, int tile_rows, int per_tile, int threads) {
+    if (!src0_qweights || !src1_row || !wdata || !dst || ne01 <= 0 || ne00 <= 0 || bits < 1 || bits > 4 || tile_rows <= 0 || ne01 % tile_rows)
+        return fail("debug_ggml_mul_mat: bad arguments");
+    tmac_b200_kcfg c;
+    if (tmac_b200_find_kcfg(ne01 * bits, ne00, bits, &c)) return fail("debug_ggml_mul_mat: shape not configured");
+    // workspace layout of ggml.c:12566-12576: qlut (K * 4 bytes) || lut_scales || lut_biases
+    char *qlut = (char *)wdata;
+    float *ls = (float *)(qlut + (size_t)ne00 * 4), *lb = ls + ne00 / c.act_group_size;
+    ggml_tmac_mul_mat_task_init(src1_row, qlut, ls, lb, ne01, ne00, 1, bits);
+    if (!per_tile) {
+        ggml_tmac_mul_mat_task_compute(src0_qweights, src0_scales, qlut, ls, lb, dst, ne01, ne00, 1, bits);
+        return 0;
+    }
+    const int n_tiles = ne01 / tile_rows;
+    const size_t w_chunk = (size_t)ne00 * tile_rows * bits / 8;               // bytes of one tile in the permuted blob (:12636)
+    const size_t s_chunk = c.one_scale ? 0 : (size_t)tile_rows * (ne00 / c.group_size) * (c.zero_point ? 2 : 1);
+    // tile-stealing workers, parked between calls like ggml's thread pool (spawning threads per mat-vec would dominate)
+    struct Pool {
+        std::vector<std::thread> th;
+        std::atomic<int> gen{0}, done{0}, next{0}, stop{0};
+        std::function<void()> job;
+        ~Pool() { stop = 1; gen++; for (auto &t : th) t.join(); }
+    };
+    static Pool pool;
+    static std::mutex pool_mu;
+    std::lock_guard<std::mutex> pl(pool_mu);
+    const int extra = std::max(0, std::min(threads, 64) - 1);
+    pool.next = 0; pool.done = 0;
+    pool.job = [&, n_tiles, w_chunk, s_chunk]() {
+        for (int t = pool.next.fetch_add(1); t < n_tiles; t = pool.next.fetch_add(1))
+            ggml_tmac_mul_mat_task_compute((char *)src0_qweights + t * w_chunk, src0_scales ? (float *)src0_scales + t * s_chunk : nullptr, qlut, ls, lb,
+                                           (float *)dst + (size_t)t * tile_rows, tile_rows, ne00, 1, bits);
+    };
+    while ((int)pool.th.size() < extra)
+        pool.th.emplace_back([&p = pool, my = pool.gen.load()]() mutable {
+            for (;;) {
+                while (p.gen.load(std::memory_order_acquire) == my) std::this_thread::yield();
+                my = p.gen.load();
+                if (p.stop) return;
+                p.job();
+                p.done.fetch_add(1, std::memory_order_release);
+            }
+        });
+    const int nworkers = (int)pool.th.size();
+    pool.gen.fetch_add(1, std::memory_order_release);
+    pool.job();
+    while (pool.done.load(std::memory_order_acquire) < nworkers) std::this_thread::yield();
+    return 0;
+}
+
 void ggml_tmac_set_n_threads(int n_threads) { (void)n_threads; /* CPU thread pool size is irrelevant on the GPU */ }
 
 int ggml_tmac_get_type_bits(int type) {  // ggml-tmac.cpp:503-522; ids from ggml.h:359,391-396
@@ -1582,7 +1747,7 @@ int ggml_tmac_b200_transform_tensor_typed(void *data, int ggml_type, int ne00, i
             hs[((size_t)(r / rows_per_tile) * NG + gk) * rows_per_tile + r % rows_per_tile] = sc[(size_t)r * NG + gk];
     int64_t h;
     {
-        std::lock_guard<std::mutex> lk(g_mu);
+        std::unique_lock<std::shared_mutex> lk(g_mu);
         if (ensure_init()) { munmap(key, abytes); std::free(hs); return -1; }
         PlainWeights P;
         plain_from_w(w.data(), ne01, ne00, bits, 0, ne01, &P);
@@ -1646,13 +1811,13 @@ int64_t tmac_b200_gguf_open(const char *path) {
     if (!path) return fail("gguf_open: null path");
     GgufFile *f = new GgufFile();
     if (!f->open(path)) { const std::string e = f->error; delete f; return fail("gguf_open: " + e); }
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     const int64_t h = g_next_gguf++;
     g_gguf[h] = f;
     return h;
 }
 int tmac_b200_gguf_close(int64_t gguf) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     auto it = g_gguf.find(gguf);
     if (it == g_gguf.end()) return fail("gguf_close: bad handle");
     // the file is unmapped: weights uploaded from it stay resident, but their host alias keys (ranges inside the mapping)
@@ -1669,12 +1834,12 @@ static GgufFile *gguf_locked(int64_t gguf) {
     return it == g_gguf.end() ? nullptr : it->second;
 }
 int tmac_b200_gguf_tensor_count(int64_t gguf) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     GgufFile *f = gguf_locked(gguf);
     return f ? (int)f->tensors.size() : fail("gguf: bad handle");
 }
 int tmac_b200_gguf_tensor_info(int64_t gguf, int index, struct tmac_b200_gguf_tensor *out) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     GgufFile *f = gguf_locked(gguf);
     if (!f || !out) return fail("gguf: bad handle / null argument");
     if (index < 0 || index >= (int)f->tensors.size()) return fail("gguf: tensor index out of range");
@@ -1688,7 +1853,7 @@ int tmac_b200_gguf_tensor_info(int64_t gguf, int index, struct tmac_b200_gguf_te
     return 0;
 }
 int tmac_b200_gguf_find_tensor(int64_t gguf, const char *name) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     GgufFile *f = gguf_locked(gguf);
     if (!f || !name) return fail("gguf: bad handle / null argument");
     const int i = f->find(name);
@@ -1696,7 +1861,7 @@ int tmac_b200_gguf_find_tensor(int64_t gguf, const char *name) {
 }
 // Metadata: integers / bools / floats (as double) and strings.  Return 0, or -1 when the key is absent or of another kind.
 int tmac_b200_gguf_meta_number(int64_t gguf, const char *key, double *out) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     GgufFile *f = gguf_locked(gguf);
     if (!f || !key || !out) return fail("gguf: bad handle / null argument");
     auto it = f->meta.find(key);
@@ -1705,7 +1870,7 @@ int tmac_b200_gguf_meta_number(int64_t gguf, const char *key, double *out) {
     return 0;
 }
 int tmac_b200_gguf_meta_string(int64_t gguf, const char *key, char *dst, size_t cap) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     GgufFile *f = gguf_locked(gguf);
     if (!f || !key || !dst || !cap) return fail("gguf: bad handle / null argument");
     auto it = f->meta.find(key);
@@ -1718,7 +1883,7 @@ int tmac_b200_gguf_meta_string(int64_t gguf, const char *key, char *dst, size_t 
 int64_t tmac_b200_gguf_load_tensor(int64_t gguf, int index, struct tmac_tensor_extra_b200 *extra) {
     const uint8_t *data; int type, ne0, ne1; uint64_t nbytes;
     {
-        std::lock_guard<std::mutex> lk(g_mu);
+        std::unique_lock<std::shared_mutex> lk(g_mu);
         GgufFile *f = gguf_locked(gguf);
         if (!f) return fail("gguf: bad handle");
         if (index < 0 || index >= (int)f->tensors.size()) return fail("gguf: tensor index out of range");

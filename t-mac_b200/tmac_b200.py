@@ -53,7 +53,7 @@ EXPORTS = [
     "tmac_b200_gguf_meta_number", "tmac_b200_gguf_meta_string", "tmac_b200_gguf_load_tensor",
     "tmac_b200_seq_create", "tmac_b200_seq_add_gemv", "tmac_b200_seq_build", "tmac_b200_seq_launch", "tmac_b200_seq_status",
     "tmac_b200_seq_info", "tmac_b200_seq_trace", "tmac_b200_seq_free",
-    "tmac_b200_peer_outputs", "tmac_b200_peer_barrier", "tmac_b200_ipc_alloc", "tmac_b200_ipc_open", "tmac_b200_ipc_close", "tmac_b200_ipc_free",
+    "tmac_b200_debug_ggml_mul_mat", "tmac_b200_peer_outputs", "tmac_b200_peer_barrier", "tmac_b200_ipc_alloc", "tmac_b200_ipc_open", "tmac_b200_ipc_close", "tmac_b200_ipc_free",
 ]
 
 _lib = None
@@ -107,7 +107,7 @@ def load() -> C.CDLL:
         "tmac_b200_gguf_load_tensor": (i64, [i64, i, C.POINTER(TensorExtra)]),
         "tmac_b200_seq_create": (i64, []), "tmac_b200_seq_add_gemv": (i, [i64, i64, vp, i, i, vp, i]),
         "tmac_b200_seq_build": (i, [i64]), "tmac_b200_seq_launch": (i, [i64]), "tmac_b200_seq_status": (i, [i64]),
-        "tmac_b200_peer_outputs": (i, [vp, i]), "tmac_b200_peer_barrier": (i, [vp, vp, i, i]), "tmac_b200_ipc_alloc": (vp, [sz, vp]), "tmac_b200_ipc_open": (vp, [vp]),
+        "tmac_b200_debug_ggml_mul_mat": (i, [vp, vp, vp, vp, vp, i, i, i, i, i, i]), "tmac_b200_peer_outputs": (i, [vp, i]), "tmac_b200_peer_barrier": (i, [vp, vp, i, i]), "tmac_b200_ipc_alloc": (vp, [sz, vp]), "tmac_b200_ipc_open": (vp, [vp]),
         "tmac_b200_ipc_close": (i, [vp]), "tmac_b200_ipc_free": (i, [vp]),
         "tmac_b200_seq_info": (i, [i64, C.POINTER(C.c_int)]), "tmac_b200_seq_trace": (i, [i64, vp, sz]), "tmac_b200_seq_free": (i, [i64]),
     }

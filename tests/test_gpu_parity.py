@@ -213,6 +213,49 @@ def test_tile_calls_like_ggml(lib, oracle):
         wt.free()
 
 
+def test_ggml_caller_emulation_whole_tensor_and_per_tile(lib, oracle):
+    """ggml's T-MAC mul_mat branch (ref:ggml.c:12562-12706) emulated in C++ (tmac_b200_debug_ggml_mul_mat): task_init + one
+    task_compute for the whole tensor, and task_init + one task_compute per weight tile from 1 and 4 tile-stealing threads.
+    Host buffers throughout.  The LUT written to the host workspace is the oracle's byte for byte; outputs match the oracle; a
+    new activation row (same pointers, new bytes) and a caller-made LUT (same pointer, new bytes) are never served stale data."""
+    cfg = T.Config(1024, 2048, 2, bm=128, zero_point=True).resolved()
+    w, sc, z, x = T.make_problem(cfg, seed=33)
+    A, S = T.pack_reference_layout(w, sc, z, cfg)
+    k = kc(cfg)
+    tb.check(lib.tmac_b200_register_kcfg(C.byref(k)), "register")
+    wt = tb.upload_reference_layout(k, A, S)
+    try:
+        nag = cfg.K // cfg.act_group_size
+        wdata = np.zeros(cfg.K * 4 + 2 * nag * 4 + 64, np.uint8)
+        tile_rows = cfg.bm // cfg.bits
+        for trial, (per_tile, threads) in enumerate(((0, 1), (1, 1), (1, 4), (0, 1))):
+            xr = np.ascontiguousarray(x[0] * (1.0 + 0.25 * trial), np.float32)       # new bytes at the same addresses every trial
+            dst = np.full(cfg.Mout, 7.0, np.float32)
+            tb.check(lib.tmac_b200_debug_ggml_mul_mat(A.ctypes.data, S.ctypes.data, xr.ctypes.data, wdata.ctypes.data, dst.ctypes.data,
+                                                      cfg.Mout, cfg.K, cfg.bits, tile_rows, per_tile, threads), "ggml emulation")
+            qo, lso, lbo = oracle.preprocessor(xr[None], cfg.act_group_size)
+            Co = oracle.qgemm(cfg, A, S, qo, lso, lbo)[0]
+            assert np.array_equal(wdata[:cfg.K * 4].view(np.int8).reshape(1, -1, 16), qo), "host QLUT bytes"
+            assert np.abs(dst - Co).max() <= TIGHT_TOL * np.abs(Co).max(), (per_tile, threads)
+        # a caller-made (non-symmetric) LUT written over the same workspace: compute only, per tile
+        rng = np.random.default_rng(8)
+        q = rng.integers(-127, 128, size=(1, cfg.K // 4, 16)).astype(np.int8)
+        ls = np.abs(rng.standard_normal((1, nag))).astype(np.float32); lb = rng.standard_normal((1, nag)).astype(np.float32)
+        wdata[:cfg.K * 4] = q.view(np.uint8).ravel()
+        wdata[cfg.K * 4:cfg.K * 4 + nag * 4] = ls.view(np.uint8).ravel()
+        wdata[cfg.K * 4 + nag * 4:cfg.K * 4 + 2 * nag * 4] = lb.view(np.uint8).ravel()
+        Co = oracle.qgemm(cfg, A, S, q, ls, lb)[0]
+        dst = np.zeros(cfg.Mout, np.float32)
+        n_tile = cfg.Mout // tile_rows; w_chunk = A.size // n_tile; s_chunk = S.size // n_tile
+        base = wdata.ctypes.data
+        for t in range(n_tile):
+            lib.ggml_tmac_mul_mat_task_compute(A.ctypes.data + t * w_chunk, S.ctypes.data + 4 * t * s_chunk, base, base + cfg.K * 4, base + cfg.K * 4 + nag * 4,
+                                               dst.ctypes.data + 4 * t * tile_rows, tile_rows, cfg.K, 1, cfg.bits)
+        assert np.abs(dst - Co).max() <= TIGHT_TOL * np.abs(Co).max()
+    finally:
+        wt.free()
+
+
 def test_ggml_hook_transform_tensor_i2_blob(lib, oracle):
     """The load-time path of the llama.cpp fork: an I2 tensor blob `permuted weights || fp32 scales`
     (python/t_mac/model_utils.py:271, ggml-tmac.cpp:336-345) goes through ggml_tmac_b200_transform_tensor, then the
