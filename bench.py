@@ -755,11 +755,21 @@ def tokens_per_second(tb, lib, torch, stream):
         e1.record(stream); torch.cuda.synchronize()
         s = e0.elapsed_time(e1) / 3 * 1e-3
         ll = tb.last_launch()
-        mma_tops = 2.0 * NB * MOUT * (2 * K) / s / 1e12       # contraction length = 8 LUT entries per K-group = 2K
+        mma = 2.0 * NB * MOUT * (2 * K) / s / 1e12            # contraction length = 8 LUT entries per K-group = 2K
+        fp16_tile = ll["cluster"] == 16
+        nominal = 2250.0 if fp16_tile else 4500.0             # dense fp16 / int8 tensor peak, TFLOP/s (B200_PROFILING.md)
+        measured = None
+        try:
+            measured = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]) * (1.0 if fp16_tile else 2.0)
+        except Exception:
+            pass
         res["prefill_seq256_one_tensor_11008x4096_w2"] = {
-            "ms": s * 1e3, "tokens_per_s_this_tensor": NB / s, "dense_equivalent_TFLOPs": 2.0 * NB * MOUT * K / s / 1e12,
-            "int8_mma_TOPs": mma_tops, "tensor_pipe_utilisation": mma_tops / 4500.0,
-            "path": "tcgen05.mma kind::i8 tile (one-hot-signed LUT contraction)" if ll["batch"] < 0 else "GEMV kernel per activation row"}
+            "ms": s * 1e3, "what": "preprocessor + LUT tiling + tcgen05 GEMM, one call (tmac_b200_gemv, N = 256)",
+            "tokens_per_s_this_tensor": NB / s, "dense_equivalent_TFLOPs": 2.0 * NB * MOUT * K / s / 1e12,
+            "mma_TFLOPs": mma, "tensor_pipe_utilisation_vs_nominal": mma / nominal,
+            "tensor_pipe_utilisation_vs_measured_cublas_peak": (mma / measured) if measured else None,
+            "path": ("tcgen05.mma kind::f16 tile, scales folded into fp16 operands, fp32 accumulation in TMEM (LUT contraction, 8 entries per K-group)"
+                     if fp16_tile else "tcgen05.mma kind::i8 tile (one-hot-signed LUT contraction)") if ll["batch"] < 0 else "GEMV kernel per activation row"}
         wt.free()
     except Exception as ex:
         res["prefill_seq256_one_tensor_11008x4096_w2"] = {"error": str(ex)[:160]}

@@ -115,7 +115,8 @@ struct Context {
     int use_fused = 1;
     int seq_smem_kb = 200;               // decode sequences: shared-memory budget; the rest of the 228 KB stays L1 (descriptor / polling loads, spills)
     int seq_grid = 0;                    // decode sequences: grid override (tests: CTA-boundary placements); 0 = one CTA per SM
-    int use_prefill16 = 0;               // DRAFT fp16-operand prefill tile (tmac_prefill16.cuh), opt-in until validated on hardware
+    int use_prefill16 = 1;               // fp16-operand prefill tile for N >= 64 (tmac_prefill16.cuh); 0 = the exact int8 tile for every N >= prefill_min_n
+    int pf_streamk = 0;                  // stream-K over all SMs when a prefill call has fewer tiles than SMs (measured slower: B delivery from L2 is the bound)
     int use_prefill = 1, prefill_min_n = 32;   // N >= prefill_min_n: tcgen05 int8 tile (W2 g128 act64)                   // tmac_b200_gemv builds the LUT inside the GEMV when the grouping allows
     int npeer = 0; void *peer_out[7] = {};   // one-shot: peer output vectors of the next N = 1 launch (tmac_b200_peer_outputs)
     int64_t next_hint = 0;               // one-shot: tensor whose blocks the next launch prefetches into L2
@@ -127,7 +128,7 @@ struct Context {
     std::set<const void *> sym_qluts;    // device QLUT buffers last written by our preprocessor
     std::vector<std::pair<std::vector<const void *>, void *>> ptr_tables;   // grouped-launch pointer tables
     // workspaces
-    DevBuf d_b, d_qlut, d_ls, d_lb, d_c, d_cbits, d_trace, d_tiles;
+    DevBuf d_b, d_qlut, d_ls, d_lb, d_c, d_cbits, d_trace, d_tiles, d_pf_scratch, d_pf_flags;
     int trace = 0, trace_ctas = 0, trace_seq = 0;
     PinBuf h_in, h_out;
     cudaEvent_t stage_ev = nullptr;      // last H2D that read h_in
@@ -403,9 +404,9 @@ int launch_prefill(const Resident &R, int N, const int8_t *qlut, const float *ls
     if (!g.use_prefill || N < g.prefill_min_n || !sym) return 1;
     if (L.pb != 2 || L.qch != 8 || L.act_group_size != 64 || L.one_scale || L.ck != 128) return 1;
     const size_t rawsz = (L.blk + 127) & ~(size_t)127;
-    if (g.use_prefill16 && N >= 64) {   // DRAFT: scales folded into fp16 operands, fp32 accumulation over K (tmac_prefill16.cuh)
+    if (g.use_prefill16 && N >= 64) {   // fp path: scales folded into fp16 operands, fp32 accumulation over K in TMEM (tmac_prefill16.cuh)
         const int nmain = L.K / 64, nextra = (L.nchunk + 31) / 32, ntile16 = (N + kP16NT - 1) / kP16NT;
-        const size_t smem16 = (size_t)kP16Stages * (kP16ABytes + kP16BBytes) + 2 * rawsz + 256 * 16 + (2 * kP16Stages + 1) * 8 + 1024;
+        const size_t smem16 = (size_t)kP16NA * kP16SubA + (size_t)kP16NB * kP16SubB + 2 * rawsz + (2 * kP16NA + 2 * kP16NB + 2) * 8 + 1024;
         if (smem16 <= 227 * 1024) {
             if (g.d_tiles.ensure((size_t)ntile16 * (nmain + nextra) * kP16BBytes)) return fail("out of device memory (LUT tiles)");
             lut_tile16_kernel<<<dim3(nmain + nextra, ntile16), 256, 0, g.stream()>>>(qlut, ls, lb, (unsigned char *)g.d_tiles.p, N, L.K, nmain, nextra);
@@ -414,10 +415,23 @@ int launch_prefill(const Resident &R, int N, const int8_t *qlut, const float *ls
             q.W = R.d; q.C = C; q.N = N; q.K = L.K; q.Mout = L.Mout; q.ldc = ldc; q.out_f16 = out_f16;
             q.nchunk = L.nchunk; q.zp = L.zp; q.sd = L.sd; q.blk_bytes = (int)L.blk; q.nmain = nmain; q.nextra = nextra;
             q.rsb_stride = L.rsb_stride; q.tiles = (const unsigned char *)g.d_tiles.p;
+            q.nrsb = L.nrsb; q.ntiles = L.nrsb * ntile16;
+            // fewer tiles than SMs (e.g. 86 at N = 256): stream-K over all SMs, partial tiles through `scratch`
+            q.streamk = (g.pf_streamk && q.ntiles < g.sms && (long)q.ntiles * (nmain + nextra) >= 2L * g.sms) ? 1 : 0;
+            const int grid = q.streamk ? g.sms : q.ntiles;
+            if (q.streamk) {
+                const size_t sb = (size_t)grid * kP16NT * 128 * sizeof(float);
+                if (g.d_pf_scratch.ensure(sb)) return fail("out of device memory (stream-K scratch)");
+                if (g.d_pf_flags.cap < (size_t)grid * sizeof(int)) {
+                    if (g.d_pf_flags.ensure((size_t)grid * sizeof(int))) return fail("out of device memory (stream-K flags)");
+                    CUDA_OK(cudaMemsetAsync(g.d_pf_flags.p, 0, g.d_pf_flags.cap, g.stream()));
+                }
+                q.scratch = (float *)g.d_pf_scratch.p; q.flags = (int *)g.d_pf_flags.p;
+            }
             CUDA_OK(cudaFuncSetAttribute((const void *)prefill16_w2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
-            prefill16_w2_kernel<<<dim3(L.nrsb, ntile16), kP16Threads, smem16, g.stream()>>>(q);
+            prefill16_w2_kernel<<<dim3(grid), kP16Threads, smem16, g.stream()>>>(q);
             CUDA_OK(cudaGetLastError());
-            g.last_launch[0] = 16; g.last_launch[1] = kP16Threads / 32; g.last_launch[2] = L.nchunk; g.last_launch[3] = 1; g.last_launch[4] = L.nrsb;
+            g.last_launch[0] = 16; g.last_launch[1] = kP16Threads / 32; g.last_launch[2] = L.nchunk; g.last_launch[3] = q.streamk; g.last_launch[4] = grid;
             g.last_launch[5] = L.pb; g.last_launch[6] = 1; g.last_launch[7] = -N;
             return 0;
         }
@@ -606,7 +620,7 @@ void tmac_b200_shutdown(void) {
         std::free(kv.second.host_scales);
     }
     g.res.clear();
-    for (DevBuf *b : {&g.d_b, &g.d_qlut, &g.d_ls, &g.d_lb, &g.d_c, &g.d_cbits, &g.d_trace, &g.d_tiles}) { if (b->p) cudaFree(b->p); b->p = nullptr; b->cap = 0; }
+    for (DevBuf *b : {&g.d_b, &g.d_qlut, &g.d_ls, &g.d_lb, &g.d_c, &g.d_cbits, &g.d_trace, &g.d_tiles, &g.d_pf_scratch, &g.d_pf_flags}) { if (b->p) cudaFree(b->p); b->p = nullptr; b->cap = 0; }
     for (HostLut &e : g.hluts) {
         for (DevBuf *b : {&e.dq, &e.dls, &e.dlb}) { if (b->p) cudaFree(b->p); b->p = nullptr; b->cap = 0; }
         if (e.res.p) cudaFreeHost(e.res.p);
@@ -946,6 +960,7 @@ int tmac_b200_debug_set(const char *key, int value) {
     else if (k == "fused") g.use_fused = value;
     else if (k == "prefill") g.use_prefill = value;
     else if (k == "prefill16") g.use_prefill16 = value;
+    else if (k == "pf_streamk") g.pf_streamk = value;
     else if (k == "prefill_min_n") g.prefill_min_n = value;
     else if (k == "pdl") g.use_pdl = value;
     else if (k == "pdl_late") g.pdl_late = value;
