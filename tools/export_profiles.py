@@ -1,7 +1,6 @@
-"""Turns the artefacts a tools/round_run.sh run left in gpurun_out/ into the tracked evidence under profiles/:
-bench line, launch list, raw + summarised ncu metrics of the dominant kernel (lone launch, and the grouped launch when
-gpurun_out/r1_prof_grouped.ncu-rep exists), executed opcode mix per block, DRAM traffic per launch."""
-import collections
+"""Turns the artefacts a tools/round_run.sh run left in gpurun_out/ into the tracked evidence under profiles/ (round 2):
+bench line, launch list, summarised ncu metrics of the three dominant kernels (gemv3 launch chain, decode sequence kernel,
+fp16 prefill tile), a SASS excerpt proving the Blackwell instructions, DRAM traffic per launch."""
 import csv
 import json
 import os
@@ -11,65 +10,58 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'launch__grid_size', 'launch__block_size', 'launch__cluster_size',
-        'launch__registers_per_thread', 'launch__shared_mem_per_block_dynamic', 'launch__occupancy_limit_shared_mem', 'launch__occupancy_limit_registers',
-        'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active',
+        'launch__registers_per_thread', 'launch__shared_mem_per_block_dynamic', 'smsp__inst_executed.sum',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active', 'sm__warps_active.avg.pct_of_peak_sustained_active', 'lts__t_sector_hit_rate.pct',
-        'dram__bytes_read.sum.per_second'] + ['smsp__average_warps_issue_stalled_%s_per_issue_active.ratio' % k for k in
-        ('long_scoreboard', 'wait', 'short_scoreboard', 'barrier', 'math_pipe_throttle', 'not_selected', 'dispatch_stall')]
+        'dram__bytes_read.sum.per_second', 'sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed',
+        'sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
+        'l1tex__data_pipe_tc_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'sm__cycles_active.avg', 'sm__cycles_elapsed.avg'] + \
+       ['smsp__average_warps_issue_stalled_%s_per_issue_active.ratio' % k for k in
+        ('long_scoreboard', 'wait', 'short_scoreboard', 'barrier', 'math_pipe_throttle', 'not_selected', 'dispatch_stall', 'sleeping')]
 UNIT = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
 
 
-def page(rep, which):
-    out = subprocess.run(["ncu", "-i", rep, "--page", which, "--csv"], capture_output=True, text=True).stdout
-    return list(csv.reader(out.splitlines()))
+def raw(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    return dict(zip(rows[0], rows[2])), dict(zip(rows[0], rows[1]))
 
 
-def summary(rep, note):
-    rows = page(rep, "raw")
-    d, u = dict(zip(rows[0], rows[2])), dict(zip(rows[0], rows[1]))
+def summary(rep, note, dst):
+    d, u = raw(rep)
     lines = ["kernel: " + d.get('Kernel Name', '?'), note] + ["%-90s %s %s" % (k, d[k], u[k]) for k in KEYS if k in d]
-    return rows, d, u, "\n".join(lines) + "\n"
-
-
-def mix(rep, blocks, title):
-    rows = page(rep, "source")
-    hi = [i for i, r in enumerate(rows) if "Source" in r][0]
-    si, ei = rows[hi].index("Source"), rows[hi].index("Instructions Executed")
-    c, tot = collections.Counter(), 0
-    for r in rows[hi + 1:]:
-        try:
-            n = int(r[ei])
-        except (ValueError, IndexError):
-            continue
-        toks = r[si].split()
-        c[toks[1] if toks[0].startswith('@') else toks[0]] += n
-        tot += n
-    lines = [title, "executed warp-instructions per (super-block, chunk) block of 256 lookups per lane (total %d / %d blocks = %.1f):" % (tot, blocks, tot / blocks)]
-    return "\n".join(lines + ["  %-22s %8.1f" % (op, n / blocks) for op, n in c.most_common(24)]) + "\n"
+    open(os.path.join(P, dst), "w").write("\n".join(lines) + "\n")
+    return d, u
 
 
 def main():
-    shutil.copy(os.path.join(G, "r1_bench.json"), os.path.join(P, "r1_bench.json"))
-    shutil.copy(os.path.join(G, "r1_launches.csv"), os.path.join(P, "r1_launches.csv"))
-    rows, d, u, txt = summary(os.path.join(G, "r1_prof_gemv3_nopf.ncu-rep"),
-                              "(one lone launch, no next-tensor L2 prefetch, cold cache, serialised by ncu: --set full --clock-control none)")
-    open(os.path.join(P, "r1_gemv3_ncu_summary.txt"), "w").write(txt)
-    with open(os.path.join(P, "r1_gemv3_ncu_raw.csv"), "w", newline="") as f:
-        csv.writer(f).writerows(rows)
+    shutil.copy(os.path.join(G, "r2_bench.json"), os.path.join(P, "r2_bench.json"))
+    shutil.copy(os.path.join(G, "r2_launches.csv"), os.path.join(P, "r2_launches.csv"))
+    for extra in ("r2_bench_n2.json", "r2_bench_n8.json", "r2_sanitizer.txt", "r2_pf16.txt"):
+        if os.path.exists(os.path.join(G, extra)):
+            shutil.copy(os.path.join(G, extra), os.path.join(P, extra))
+    d, u = summary(os.path.join(G, "r2_prof_gemv3.ncu-rep"), "(one launch of the chain of bench.py --eager: fused LUT build, cold cache, serialised by ncu: --set full --clock-control none)",
+                   "r2_gemv3_ncu_summary.txt")
     traffic = float(d['dram__bytes_read.sum']) * UNIT[u['dram__bytes_read.sum']] + float(d['dram__bytes_write.sum']) * UNIT[u['dram__bytes_write.sum']]
-    json.dump({"gemv_kernel_dram_bytes_per_launch": traffic, "source": "ncu --set full, r1_gemv3_ncu_raw.csv (lone launch, no next-tensor prefetch)",
-               "algorithmic_bytes_per_launch": 12741632}, open(os.path.join(P, "traffic.json"), "w"), indent=1)
-    text = ""
-    grouped = os.path.join(G, "r1_prof_grouped.ncu-rep")
-    if os.path.exists(grouped):
-        _, _, _, t2 = summary(grouped, "(ONE grouped launch = 32 GEMVs of the bench workload, serialised by ncu: --set full --clock-control none; 64-register variant)")
-        open(os.path.join(P, "r1_gemv3_grouped_ncu_summary.txt"), "w").write(t2)
-        text += mix(grouped, 32 * 2752, "gemv3_kernel<2,sym,8,4,minb4> grouped launch (32 GEMVs), ncu --page source:") + "\n"
-    text += mix(os.path.join(G, "r1_prof_gemv3.ncu-rep"), 2752,
-                "gemv3_kernel<2,sym,8,4,minb3,fused> lone launch (4 CTAs x 8 warps per super-block, LUT built in the kernel), ncu --page source:")
-    text += "\nALU pipe: PRMT, LOP3, SHF, IADD3, ISETP, VIADD, LEA, MOV, SEL ...; FMA pipe: IDP (DP4A), IMAD*, FFMA/FADD/FMUL.\n"
-    open(os.path.join(P, "r1_gemv3_opcode_mix.txt"), "w").write(text)
-    print(txt)
+    # profiles/traffic.json is maintained by hand from these captures (see its `source`): the chain launch also prefetches the next tensor
+    summary(os.path.join(G, "r2_prof_seq.ncu-rep"), "(one persistent launch = 32 GEMVs 11008x4096 W2, dependent chain, tools/seq_bench.py; --set full --clock-control none)",
+            "r2_seq_ncu_summary.txt")
+    summary(os.path.join(G, "r2_prof_pf16.ncu-rep"), "(prefill tile, N = 256 tokens x 11008x4096 W2 g128 zp, tools/pf_one.py 256 1 0; --set full --clock-control none)",
+            "r2_prefill16_ncu_summary.txt")
+    # SASS excerpt: the Blackwell-only mnemonics of the in-tree library
+    so = os.path.join(ROOT, "t-mac_b200", "libtmac_b200.so")
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout.splitlines()
+    pats = ("UTCHMMA", "UTCIMMA", "UTCBAR", "LDTM", "UBLKCP", "UBLKPF", "SYNCS", "IDP.4A", "PRMT", "UTCATOM", "ACQBULK", "NANOSLEEP", "ST.E.64.STRONG.SYS", "STG.E.STRONG.SYS", "CCTL")
+    out = ["cuobjdump -sass t-mac_b200/libtmac_b200.so: occurrences of Blackwell / hot-path mnemonics, then the first 3 lines of each", ""]
+    for pt in pats:
+        hits = [l.strip() for l in sass if pt in l]
+        out.append("%-22s x %d" % (pt, len(hits)))
+    out.append("")
+    for pt in pats:
+        for l in [l.strip() for l in sass if pt in l][:3]:
+            out.append(l[:150])
+    open(os.path.join(P, "r2_sass_excerpt.txt"), "w").write("\n".join(out) + "\n")
+    print("profiles/ updated; gemv3 traffic per launch = %.0f B" % traffic)
 
 
 if __name__ == "__main__":
