@@ -738,6 +738,18 @@ def tokens_per_second(tb, lib, torch, stream):
         lib.tmac_b200_graph_free(g)
         for h in handles:
             h.free()
+    # Full decode step: the same linears inside the real per-layer op order with torch fp32 RMSNorm / RoPE / attention over
+    # a 512-position KV cache / SiLU*mul / residuals, one CUDA graph per token (t-mac_b200/decode_harness.py).
+    try:
+        from decode_harness import DecodeModel
+        for name, kw in (("llama2_7b_w2_g128_zp", dict(layers=32, hidden=4096, ffn=11008, heads=32, bits=2, zero_point=True)),):
+            m = DecodeModel(ctx=512, **kw)
+            m.capture(stream)
+            res[name]["tokens_per_s_full_step"] = m.tokens_per_s(stream, n=10)
+            res[name]["full_step"] = "quantised linears through the library + torch fp32 norm / rope / attention (ctx 512) / activation, CUDA graph"
+            m.free()
+    except Exception as ex:
+        res["decode_harness_error"] = str(ex)[:200]
     # Prefill-shaped call (BASELINE config 4: Llama-2-7B W2, seq 256): N >= 32 takes the tcgen05 kind::i8 tile
     # (tmac_prefill.cuh): preprocessor + LUT tiling + GEMM.  Tensor-pipe utilisation = int8 MMA rate / 4500 TOP/s (dense peak).
     try:
