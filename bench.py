@@ -328,7 +328,8 @@ def main():
     out_seq = torch.zeros((LAYERS, MOUT), device="cuda")
     seqs = {}
     try:
-        for name, chained in (("dependent", True), ("independent", False)):
+        for name, chained in (("dependent", True), ("independent", False), ("dependent_streamk", True)):
+            tb.debug_set("seq_impl", 0 if name.endswith("streamk") else 2)     # 2 = resident chain where the sequence qualifies
             sq = tb.Sequence()
             for i, wt in enumerate(layers):
                 if chained and i > 0:
@@ -339,6 +340,7 @@ def main():
             seqs[name] = sq
     except Exception as ex:
         seqs = {"error": str(ex)[:160]}
+    tb.debug_set("seq_impl", 2)
 
     def run_steps(graph, n):
         if args.eager:
@@ -429,18 +431,22 @@ def main():
     if "error" in seqs:
         seq_report = seqs
     else:
-        ms_dep, ms_ind = timed_seq(seqs["dependent"], args.steps), timed_seq(seqs["independent"], args.steps)
+        ms_dep, ms_ind, ms_sk = timed_seq(seqs["dependent"], args.steps), timed_seq(seqs["independent"], args.steps), timed_seq(seqs["dependent_streamk"], args.steps)
         seqs["dependent"].launch(); seqs["dependent"].status()       # leave the dependent chain's outputs in out_seq for the parity check
-        seq_report = {"what": "decode sequence kernel: the %d GEMVs of the step in ONE persistent launch (one CTA per SM, TMA weight ring across ops)" % LAYERS,
+        resident = seqs["dependent"].info()["ring_slots"] < 0
+        seq_kind = ("resident chain kernel (tmac_chain.cuh): gemv3's clusters kept resident, inputs arrive as {value, epoch} words, next tensor's blocks requested before the lookups"
+                    if resident else "stream-K sequence kernel (tmac_seq.cuh): one CTA per SM, TMA weight ring across ops")
+        seq_report = {"what": "the %d GEMVs of the step in ONE persistent launch -- %s" % (LAYERS, seq_kind),
                       "dependent_chain": {"ms_per_step": ms_dep, "GBps": world * bytes_step / (ms_dep * 1e-3) / 1e9, "us_per_gemv": ms_dep * 1e3 / LAYERS,
                                           "dependency": "x[i+1] = first K outputs of GEMV i (true data dependency through HBM {value, epoch} words)"},
                       "independent_inputs": {"ms_per_step": ms_ind, "GBps": world * bytes_step / (ms_ind * 1e-3) / 1e9, "us_per_gemv": ms_ind * 1e3 / LAYERS},
+                      "streamk_sequence_kernel_dependent_chain": {"ms_per_step": ms_sk, "us_per_gemv": ms_sk * 1e3 / LAYERS, "what": "same chain through tmac_seq.cuh (the fallback for sequences the resident chain does not take)"},
                       "info": seqs["dependent"].info()}
         if ms_dep < ms_per_step and world == 1:      # the dependent chain in one launch beats the chain of launches: it is the step
             ms_per_step = ms_dep
             value = world * bytes_step / (ms_per_step * 1e-3) / 1e9
             launches["n"] = args.steps
-            submission = "ONE persistent launch per step (decode sequence kernel); GEMV i+1 consumes GEMV i's output"
+            submission = "ONE persistent launch per step (%s); GEMV i+1 consumes GEMV i's output" % seq_kind.split(":")[0]
 
     timed(g_two, 3, False)
     ms_two = timed(g_two, args.steps, False) / args.steps
@@ -450,8 +456,7 @@ def main():
     t_gemv = ms_g / args.steps / LAYERS * 1e-3
     peak, peak_src = measured_peak()
     achieved = algorithmic_bytes() / t_gemv / 1e9
-    kname = ("gemv4_kernel<PB=2,SYM,QCH=8,AGQ=4> (stream-K grid, one CTA per SM)" if lone_cfg["cluster"] == 0
-             else "gemv3_kernel<PB=2,SYM,QCH=8,AGQ=4>")
+    kname = "gemv3_kernel<PB=2,SYM,QCH=8,AGQ=4>"
     roofline = {"bound": "hbm", "kernel": kname, "launch": lone_cfg, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src, "us_per_launch": t_gemv * 1e6,
                 "submission": submission, "sequence_kernel": seq_report,

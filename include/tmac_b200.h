@@ -191,7 +191,11 @@ TMAC_B200_API int tmac_b200_seq_add_gemv(int64_t seq, int64_t handle, const void
 TMAC_B200_API int tmac_b200_seq_build(int64_t seq);     /* allocates the device tables; no more ops afterwards */
 TMAC_B200_API int tmac_b200_seq_launch(int64_t seq);    /* asynchronous, on the current stream; capturable in a CUDA graph */
 TMAC_B200_API int tmac_b200_seq_status(int64_t seq);    /* synchronises; 0 = ok, -1 = a bounded wait inside the kernel expired */
-/* info[8] = {grid, ring slots, slot bytes, shared-memory bytes, ops, planes/word, quads/chunk, quads/activation group} */
+/* Two kernels serve a sequence (tmac_b200_debug_set("seq_impl", 0 | 1 | 2), default 2): the resident gemv3 chain (tmac_chain.cuh: gemv3's
+ * decomposition kept resident, one grid barrier per op; needs one weight format, fp32 16-byte aligned inputs, in_offset % 4 == 0) when the
+ * sequence qualifies, else the stream-K sequence kernel (tmac_seq.cuh).
+ * info[8] = {grid, ring slots (-8 = resident chain, clusters of 8), slot bytes, shared-memory bytes, ops, planes/word, quads/chunk,
+ * quads/activation group} */
 TMAC_B200_API int tmac_b200_seq_info(int64_t seq, int *out8);
 /* Debug (tmac_b200_debug_set("trace", 1) before seq_build): globaltimer stamps [ops][grid][16] of the last launch:
  * 0 op entered, 1 own LUT work done, 2 first block resident, 3/5/4 lookups done (first / middle / last warp), 6 CTA sums read,

@@ -29,6 +29,7 @@
 #include "tmac_prefill.cuh"
 #include "tmac_prefill16.cuh"
 #include "tmac_seq.cuh"
+#include "tmac_chain.cuh"
 #include "tmac_layout.h"
 #include "tmac_gguf.h"
 
@@ -113,6 +114,7 @@ struct Context {
     int cs_override = 0, wpc_override = 0, pdl_late = -1, minb_override = 0, nbuf_override = 0;
     int last_launch[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int use_fused = 1;
+    int seq_impl = 2;                    // decode sequences: 0 = stream-K sequence kernel (tmac_seq.cuh), 1 = resident gemv3 chain (tmac_chain.cuh), 2 = chain when the sequence qualifies
     int seq_smem_kb = 200;               // decode sequences: shared-memory budget; the rest of the 228 KB stays L1 (descriptor / polling loads, spills)
     int seq_grid = 0;                    // decode sequences: grid override (tests: CTA-boundary placements); 0 = one CTA per SM
     int use_prefill16 = 1;               // fp16-operand prefill tile for N >= 64 (tmac_prefill16.cuh); 0 = the exact int8 tile for every N >= prefill_min_n
@@ -130,6 +132,7 @@ struct Context {
     // workspaces
     DevBuf d_b, d_qlut, d_ls, d_lb, d_c, d_cbits, d_trace, d_tiles, d_pf_scratch, d_pf_flags;
     int trace = 0, trace_ctas = 0, trace_seq = 0;
+    int chain_flags = 40;                // resident chain (tmac_chain.cuh): 32 data-flow inputs instead of a grid barrier | 8 next op's block requested before the lookups
     PinBuf h_in, h_out;
     cudaEvent_t stage_ev = nullptr;      // last H2D that read h_in
     bool stage_pending = false;
@@ -153,9 +156,14 @@ struct Sequence {
     seq_fn fn = nullptr;
     size_t smem = 0;
     SeqParams params{};
+    int impl = 0;                         // 1: chain_kernel
+    chain_fn cfn = nullptr;
+    ChainParams cparams{};
+    void *d_cops = nullptr, *d_bar = nullptr, *d_cint = nullptr;
     void *d_ops = nullptr, *d_ctas = nullptr, *d_lut = nullptr, *d_y = nullptr, *d_xchg = nullptr, *d_epochs = nullptr, *d_err = nullptr, *d_trace = nullptr;
     void release() {
-        for (void *q : {d_ops, d_ctas, d_lut, d_y, d_xchg, d_epochs, d_err, d_trace}) if (q) cudaFree(q);
+        for (void *q : {d_ops, d_ctas, d_lut, d_y, d_xchg, d_epochs, d_err, d_trace, d_cops, d_bar, d_cint}) if (q) cudaFree(q);
+        d_cops = d_bar = d_cint = nullptr;
         d_ops = d_ctas = d_lut = d_y = d_xchg = d_epochs = d_err = d_trace = nullptr; built = false;
     }
 };
@@ -956,7 +964,9 @@ int tmac_b200_debug_set(const char *key, int value) {
     const std::string k = key ? key : "";
     if (k == "seq_grid") g.seq_grid = value;
     else if (k == "seq_smem_kb") g.seq_smem_kb = value;
+    else if (k == "seq_impl") g.seq_impl = value;
     else if (k == "trace") g.trace = value;
+    else if (k == "chain_flags") g.chain_flags = value;
     else if (k == "fused") g.use_fused = value;
     else if (k == "prefill") g.use_prefill = value;
     else if (k == "prefill16") g.use_prefill16 = value;
@@ -1306,6 +1316,77 @@ int tmac_b200_seq_add_gemv(int64_t seq, int64_t handle, const void *x, int in_op
     return (int)S.ops.size() - 1;
 }
 
+// Resident gemv3 chain (tmac_chain.cuh): 1 = built, 0 = the sequence does not qualify (caller falls back), -1 = error.
+static int seq_build_chain(Sequence &S) {
+    const int n = (int)S.ops.size();
+    std::vector<ChainOp> ops(n);
+    std::vector<size_t> coff(n, (size_t)-1), lloff(n, 0);
+    size_t ctot = 0, max_blk = 0, lltot = 0;
+    int max_nrsb = 0, pb = 0, qch = 0, agq = 0, bits = 0, rsbsz = 0;
+    for (int i = 0; i < n; ++i) {
+        const Resident &R = g.res.find(S.ops[i].handle)->second;
+        const StreamLayout &L = R.L;
+        if ((L.one_scale && L.act_group_size == L.K) || L.act_group_size > L.ck) return 0;
+        const int a = std::min(L.act_group_size, L.ck) / 16;
+        if (i == 0) { pb = L.pb; qch = L.qch; agq = a; bits = L.bits; rsbsz = L.rsb; }
+        else if (pb != L.pb || qch != L.qch || agq != a || bits != L.bits) return 0;
+        if (S.ops[i].x_ext) { if ((uintptr_t)S.ops[i].x_ext % 16) return 0; }
+        else if (S.ops[i].in_off % ((g.chain_flags & 32) ? 2 : 4) || S.ops[S.ops[i].in_op].out_f16) return 0;    // float4 loads (16-byte word pairs in data-flow mode) of an fp32 producer
+        max_blk = std::max(max_blk, (L.blk + 127) & ~(size_t)127);
+        max_nrsb = std::max(max_nrsb, L.nrsb);
+        if (!S.ops[i].C) { coff[i] = ctot; ctot += ((size_t)L.nrsb * L.rsb * sizeof(float) + 255) & ~(size_t)255; }
+        lloff[i] = lltot; lltot += ((size_t)L.nrsb * L.rsb * sizeof(uint2) + 255) & ~(size_t)255;
+    }
+    chain_fn fn = pick_chain(pb, qch, agq);
+    if (!fn) return 0;
+    const int grid = max_nrsb * kChainCS;
+    const size_t smem = (size_t)(kChainCS + kChainWarps) * rsbsz * 4 + (size_t)kChainWarps * (2 * max_blk + (size_t)qch * 4 * 8) + kChainWarps * 16 + 32;
+    if (smem > 48 * 1024 && cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    {   // every cluster must be resident at once: the grid barrier spins
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kChainWarps * 32); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = kChainCS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, (const void *)fn, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+        if (nc < max_nrsb) return 0;
+    }
+    if (cudaMalloc(&S.d_cops, n * sizeof(ChainOp)) != cudaSuccess || cudaMalloc(&S.d_bar, 256) != cudaSuccess ||
+        cudaMalloc(&S.d_epochs, grid * sizeof(unsigned)) != cudaSuccess || cudaMalloc(&S.d_err, sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&S.d_cint, std::max<size_t>(ctot, 256)) != cudaSuccess || cudaMalloc(&S.d_y, lltot) != cudaSuccess) { cudaGetLastError(); S.release(); return fail("seq_build: out of device memory"); }
+    CUDA_OK(cudaMemset(S.d_y, 0, lltot));     // epoch 0 never matches: launches publish epochs >= 1
+    CUDA_OK(cudaMemset(S.d_bar, 0, 256)); CUDA_OK(cudaMemset(S.d_epochs, 0, grid * sizeof(unsigned))); CUDA_OK(cudaMemset(S.d_err, 0, sizeof(int)));
+    for (int i = 0; i < n; ++i) {
+        const StreamLayout &L = g.res.find(S.ops[i].handle)->second.L;
+        ChainOp &o = ops[i];
+        o.W = g.res.find(S.ops[i].handle)->second.d;
+        o.C = S.ops[i].C ? S.ops[i].C : (void *)((char *)S.d_cint + coff[i]);
+        o.x = S.ops[i].x_ext ? (const float *)S.ops[i].x_ext : (const float *)ops[S.ops[i].in_op].C + S.ops[i].in_off;
+        o.rsb_stride = L.rsb_stride; o.K = L.K; o.Mout = L.Mout; o.nrsb = L.nrsb; o.nchunk = L.nchunk;
+        o.blk_bytes = (int)L.blk; o.bpw = (L.nchunk + kChainCS * kChainWarps - 1) / (kChainCS * kChainWarps);
+        o.zp = L.zp; o.one_scale = L.one_scale; o.sd = L.sd; o.out_f16 = S.ops[i].out_f16; o.scale0 = L.scale0;
+        o.in_op = S.ops[i].x_ext ? -1 : S.ops[i].in_op;
+        o.ll_out = (uint2 *)((char *)S.d_y + lloff[i]);
+        o.ll_in = S.ops[i].x_ext ? nullptr : (const uint2 *)((char *)S.d_y + lloff[S.ops[i].in_op]) + S.ops[i].in_off;
+    }
+    CUDA_OK(cudaMemcpy(S.d_cops, ops.data(), n * sizeof(ChainOp), cudaMemcpyHostToDevice));
+    S.cparams.ops = (const ChainOp *)S.d_cops; S.cparams.nops = n; S.cparams.max_blk = (int)max_blk;
+    S.cparams.bar = (unsigned *)S.d_bar; S.cparams.epochs = (unsigned *)S.d_epochs; S.cparams.err = (int *)S.d_err;
+    S.cparams.flags = g.chain_flags; S.cparams.trace = nullptr;
+    if (g.trace) {
+        const size_t tb = (size_t)n * grid * (16 + 16 * kSeqWarps) * sizeof(long long);    // same size as the stream-K kernel's trace (seq_trace copies that much)
+        if (cudaMalloc(&S.d_trace, tb) != cudaSuccess) { cudaGetLastError(); S.release(); return fail("seq_build: out of device memory (trace)"); }
+        cudaMemset(S.d_trace, 0, tb);
+        S.cparams.trace = (long long *)S.d_trace;
+    }
+    S.cfn = fn; S.impl = 1; S.grid = grid; S.smem = smem; S.pb = pb; S.qch = qch; S.agq = agq; S.bits = bits;
+    S.built = true;
+    return 1;
+}
+
 int tmac_b200_seq_build(int64_t seq) {
     std::unique_lock<std::shared_mutex> lk(g_mu);
     auto it = g_seqs.find(seq);
@@ -1313,6 +1394,12 @@ int tmac_b200_seq_build(int64_t seq) {
     Sequence &S = it->second;
     if (S.built) return 0;
     if (S.ops.empty()) return fail("seq_build: empty sequence");
+    for (auto &o : S.ops) if (g.res.find(o.handle) == g.res.end()) return fail("seq_build: a weight handle was freed");
+    if (g.seq_impl >= 1 && g.seq_grid == 0) {
+        const int rc = seq_build_chain(S);
+        if (rc != 0) return rc < 0 ? -1 : 0;
+        if (g.seq_impl == 1) return fail("seq_build: the sequence does not qualify for the resident chain kernel (fp path, one format, fp32 16-byte aligned inputs, clusters resident)");
+    }
     const int G = g.seq_grid > 0 ? std::min(g.seq_grid, g.sms) : g.sms;
     const int n = (int)S.ops.size();
     std::vector<SeqOp> ops(n);
@@ -1457,6 +1544,16 @@ int tmac_b200_seq_launch(int64_t seq) {
     if (!S.built) return fail("seq_launch: call tmac_b200_seq_build first");
     uint32_t wtx, wty;
     plane_weight_regs(S.bits, true, &wtx, &wty);
+    if (S.impl == 1) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(S.grid); cfg.blockDim = dim3(kChainWarps * 32); cfg.dynamicSmemBytes = S.smem; cfg.stream = g.stream();
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = kChainCS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        CUDA_OK(cudaLaunchKernelEx(&cfg, S.cfn, S.cparams, wtx, wty));
+        return 0;
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(S.grid, 1, 1);
     cfg.blockDim = dim3(kSeqThreads, 1, 1);
@@ -1488,7 +1585,7 @@ int tmac_b200_seq_info(int64_t seq, int *out8) {
     auto it = g_seqs.find(seq);
     if (it == g_seqs.end() || !it->second.built || !out8) return fail("seq_info: bad sequence");
     const Sequence &S = it->second;
-    const int v[8] = {S.grid, S.params.nslots, S.params.slot_bytes, (int)S.smem, (int)S.ops.size(), S.pb, S.qch, S.agq};
+    const int v[8] = {S.grid, S.impl == 1 ? -kChainCS : S.params.nslots, S.impl == 1 ? S.cparams.max_blk : S.params.slot_bytes, (int)S.smem, (int)S.ops.size(), S.pb, S.qch, S.agq};
     std::memcpy(out8, v, sizeof v);
     return 0;
 }

@@ -99,6 +99,9 @@ CHAINS = {
 }
 
 
+CHAIN_FLAGS = (0, 26, 40)     # resident chain variants (tmac_chain.cuh): plain grid barrier, tuned grid barrier, data flow
+CHAIN_DEFAULT = 40
+
 # the per-CTA reduction buffer grows with the number of row super-blocks one CTA touches: the 11008-row chain needs >= 7 CTAs
 CASES = [(n, g) for n in CHAINS for g in (0, 1, 2, 3, 7, 37) if not (n == "w4zp_k11008" and 0 < g < 7)]
 
@@ -111,17 +114,25 @@ def test_sequence_chain_matches_oracle(lib, oracle, name, grid):
     try:
         x0 = np.random.default_rng(5).standard_normal(cfgs[0].K).astype(np.float16).astype(np.float32)
         offsets = [0] + [2 * (i % 3) if cfgs[i].K + 4 <= cfgs[i - 1].Mout else 0 for i in range(1, len(cfgs))]
+        tb.debug_set("seq_impl", 0)                     # the stream-K sequence kernel
         info = run_chain(lib, oracle, chain, x0, offsets)
-        assert info["grid"] == (grid if grid else torch.cuda.get_device_properties(0).multi_processor_count)
+        assert info["grid"] == (grid if grid else torch.cuda.get_device_properties(0).multi_processor_count) and info["ring_slots"] > 0
+        if grid == 0:                                   # the resident gemv3 chain, where the sequence qualifies (else it falls back)
+            tb.debug_set("seq_impl", 2)
+            for flags in CHAIN_FLAGS:                   # grid-barrier form and data-flow form
+                tb.debug_set("chain_flags", flags)
+                info = run_chain(lib, oracle, chain, x0, offsets)
+                if info["ring_slots"] == -8:            # (it also needs every cluster resident: 11008 W4 rows = 172 clusters are too many)
+                    assert all(o % (2 if flags & 32 else 4) == 0 for o in offsets), info
     finally:
         for c in chain:
             c[3].free()
-        tb.debug_set("seq_grid", 0)
+        tb.debug_set("seq_grid", 0); tb.debug_set("seq_impl", 2); tb.debug_set("chain_flags", CHAIN_DEFAULT)
 
 
 def test_sequence_equals_single_launch_path_within_reassociation(lib, oracle):
-    """Same tensor through tmac_b200_gemv (gemv3, fused LUT) and through a one-op sequence: identical LUT bytes, so the
-    outputs differ only by fp32 re-association of the K split."""
+    """Same tensor through tmac_b200_gemv (gemv3, fused LUT) and through a one-op sequence (whichever kernel serves it): identical
+    LUT bytes, so the outputs differ at most by fp32 re-association of the K split."""
     cfg = T.Config(2048, 4096, 2, zero_point=True).resolved()
     w, sc, z, x = T.make_problem(cfg, seed=41)
     A, S = T.pack_reference_layout(w, sc, z, cfg)
@@ -174,14 +185,18 @@ def test_sequence_independent_inputs_and_long_chain(lib, oracle):
             wt.free()
 
 
-def test_sequence_full_size_llama_shape(lib, oracle):
+@pytest.mark.parametrize("impl,flags", [(0, 0), (1, 26), (1, 40)], ids=["streamk", "resident_chain_barrier", "resident_chain_flow"])
+def test_sequence_full_size_llama_shape(lib, oracle, impl, flags):
     """BASELINE shape 11008x4096 W2 g128 zp at full size, two chained ops (down-projection shape second)."""
     cfgs = [T.Config(11008, 4096, 2, zero_point=True).resolved(), T.Config(4096, 11008, 2, zero_point=True).resolved()]
     chain = build_chain(cfgs, seed=61)
+    tb.debug_set("seq_impl", impl); tb.debug_set("chain_flags", flags)
     try:
         x0 = np.random.default_rng(7).standard_normal(4096).astype(np.float16).astype(np.float32)
-        run_chain(lib, oracle, chain, x0, [0, 0])
+        info = run_chain(lib, oracle, chain, x0, [0, 0], launches=3)
+        assert (info["ring_slots"] == -8) == (impl == 1)
     finally:
+        tb.debug_set("seq_impl", 2); tb.debug_set("chain_flags", CHAIN_DEFAULT)
         for c in chain:
             c[3].free()
 

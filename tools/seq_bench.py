@@ -23,6 +23,8 @@ ap.add_argument("--bits", type=int, default=2)
 ap.add_argument("--mout", type=int, default=bench.MOUT)
 ap.add_argument("--k", type=int, default=bench.K)
 ap.add_argument("--smem", type=int, default=0)
+ap.add_argument("--impl", type=int, default=2, help="0 stream-K sequence kernel, 1 resident gemv3 chain, 2 auto")
+ap.add_argument("--flags", type=str, default="", help="comma list of chain_flags values to time (resident chain only)")
 args = ap.parse_args()
 
 lib = tb.load(); tb.check(lib.tmac_b200_init(0), "init")
@@ -31,6 +33,7 @@ if args.trace:
     tb.debug_set("trace", 1)
 if args.smem:
     tb.debug_set("seq_smem_kb", args.smem)
+tb.debug_set("seq_impl", args.impl)
 L = args.layers
 w, sc, z = bench.synth(100, args.mout, args.k, args.bits, 128, True, False)
 bm = 256 if (args.mout * args.bits) % 256 == 0 else 128
@@ -54,6 +57,49 @@ def timed(seq, reps):
     seq.status()
     return e0.elapsed_time(e1) / reps * 1e3
 
+
+def chain_trace(seq):
+    """Resident chain: globaltimer stamps of warp 0 of every CTA, [ops][grid][16] (tmac_chain.cuh)."""
+    seq.launch(); seq.status()
+    t = seq.trace().astype(np.float64) / 1e3
+    names = ["top->barrier seen", "syncthreads", "LUT slice", "block wait", "lookups", "red sync", "cluster sync", "store+fence+arrive (leaders)"]
+    ops = slice(2, None)
+    def fmt(a):
+        return "%.2f/%.2f/%.2f" % (np.median(a), np.percentile(a, 90), a.max())
+    flow = bool(t[ops, :, 1].max() == 0)          # data-flow mode: no barrier stamps
+    for k, nme in enumerate(names):
+        if flow and k < 2:
+            continue
+        a = t[ops, :, k + 1] - t[ops, :, k]
+        if k == 7:
+            a = a[:, ::8]
+        print("    %-30s median/p90/max us: %s" % (nme, fmt(a)))
+    end = np.where(t[:, :, 8] > 0, t[:, :, 8], t[:, :, 7])
+    per = np.diff(end.max(axis=1))
+    if flow:
+        print("    op period median %.2f us (data-flow mode: CTAs are not aligned per op)" % np.median(per))
+        return
+    print("    op period median %.2f us; last leader arrive -> CTAs see barrier: median %.2f max %.2f us; spread of 'lookups done' across CTAs %.2f us" % (
+        np.median(per), np.median(t[3:, :, 1] - end[2:-1].max(axis=1)[:, None]), (t[3:, :, 1] - end[2:-1].max(axis=1)[:, None]).max(),
+        np.median(t[ops, :, 5].max(axis=1) - t[ops, :, 5].min(axis=1))))
+
+
+for fl in [int(v) for v in args.flags.split(",") if v != ""]:
+    tb.debug_set("chain_flags", fl); tb.debug_set("seq_impl", 1)
+    seq = tb.Sequence()
+    for i, wt in enumerate(layers):
+        if i > 0:
+            seq.add(wt, in_op=i - 1, in_offset=0, out=out[i])
+        else:
+            seq.add(wt, x=x[i], out=out[i])
+    seq.build()
+    us = timed(seq, args.reps)
+    print("chain_flags %d dependent: %.2f us per GEMV  %s" % (fl, us / L, seq.info()), flush=True)
+    if args.trace:
+        chain_trace(seq)
+    seq.free()
+if args.flags:
+    sys.exit(0)
 
 for name, chained in (("independent inputs", False), ("dependent chain", True)):
     if chained and args.k > args.mout:
