@@ -132,7 +132,7 @@ struct Context {
     // workspaces
     DevBuf d_b, d_qlut, d_ls, d_lb, d_c, d_cbits, d_trace, d_tiles, d_pf_scratch, d_pf_flags;
     int trace = 0, trace_ctas = 0, trace_seq = 0;
-    int chain_flags = 40;                // resident chain (tmac_chain.cuh): 32 data-flow inputs instead of a grid barrier | 8 next op's block requested before the lookups
+    int chain_flags = 0;                 // resident chain (tmac_chain.cuh): bit 0 = grid-barrier form (comparison); default: data flow
     PinBuf h_in, h_out;
     cudaEvent_t stage_ev = nullptr;      // last H2D that read h_in
     bool stage_pending = false;
@@ -967,6 +967,7 @@ int tmac_b200_debug_set(const char *key, int value) {
     else if (k == "seq_impl") g.seq_impl = value;
     else if (k == "trace") g.trace = value;
     else if (k == "chain_flags") g.chain_flags = value;
+
     else if (k == "fused") g.use_fused = value;
     else if (k == "prefill") g.use_prefill = value;
     else if (k == "prefill16") g.use_prefill16 = value;
@@ -1331,7 +1332,7 @@ static int seq_build_chain(Sequence &S) {
         if (i == 0) { pb = L.pb; qch = L.qch; agq = a; bits = L.bits; rsbsz = L.rsb; }
         else if (pb != L.pb || qch != L.qch || agq != a || bits != L.bits) return 0;
         if (S.ops[i].x_ext) { if ((uintptr_t)S.ops[i].x_ext % 16) return 0; }
-        else if (S.ops[i].in_off % ((g.chain_flags & 32) ? 2 : 4) || S.ops[S.ops[i].in_op].out_f16) return 0;    // float4 loads (16-byte word pairs in data-flow mode) of an fp32 producer
+        else if (S.ops[i].in_off % ((g.chain_flags & kChainBarrier) ? 4 : 2) || S.ops[S.ops[i].in_op].out_f16) return 0;    // float4 loads (16-byte word pairs in data-flow mode) of an fp32 producer
         max_blk = std::max(max_blk, (L.blk + 127) & ~(size_t)127);
         max_nrsb = std::max(max_nrsb, L.nrsb);
         if (!S.ops[i].C) { coff[i] = ctot; ctot += ((size_t)L.nrsb * L.rsb * sizeof(float) + 255) & ~(size_t)255; }
@@ -1369,6 +1370,7 @@ static int seq_build_chain(Sequence &S) {
         o.blk_bytes = (int)L.blk; o.bpw = (L.nchunk + kChainCS * kChainWarps - 1) / (kChainCS * kChainWarps);
         o.zp = L.zp; o.one_scale = L.one_scale; o.sd = L.sd; o.out_f16 = S.ops[i].out_f16; o.scale0 = L.scale0;
         o.in_op = S.ops[i].x_ext ? -1 : S.ops[i].in_op;
+
         o.ll_out = (uint2 *)((char *)S.d_y + lloff[i]);
         o.ll_in = S.ops[i].x_ext ? nullptr : (const uint2 *)((char *)S.d_y + lloff[S.ops[i].in_op]) + S.ops[i].in_off;
     }
@@ -1376,6 +1378,7 @@ static int seq_build_chain(Sequence &S) {
     S.cparams.ops = (const ChainOp *)S.d_cops; S.cparams.nops = n; S.cparams.max_blk = (int)max_blk;
     S.cparams.bar = (unsigned *)S.d_bar; S.cparams.epochs = (unsigned *)S.d_epochs; S.cparams.err = (int *)S.d_err;
     S.cparams.flags = g.chain_flags; S.cparams.trace = nullptr;
+
     if (g.trace) {
         const size_t tb = (size_t)n * grid * (16 + 16 * kSeqWarps) * sizeof(long long);    // same size as the stream-K kernel's trace (seq_trace copies that much)
         if (cudaMalloc(&S.d_trace, tb) != cudaSuccess) { cudaGetLastError(); S.release(); return fail("seq_build: out of device memory (trace)"); }

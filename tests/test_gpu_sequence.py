@@ -95,12 +95,14 @@ CHAINS = {
     "w4zp_k11008": [T.Config(11008, 512, 4, zero_point=True), T.Config(320, 11008, 4, zero_point=True)],
     "w1": [T.Config(512, 2048, 1), T.Config(512, 512, 1)],
     "w3zp": [T.Config(384, 1024, 3, zero_point=True), T.Config(192, 384, 3, zero_point=True)],
+    "partial": [T.Config(1024, 512, 2, zero_point=True), T.Config(640, 512, 2, zero_point=True), T.Config(512, 256, 2, zero_point=True),
+                T.Config(256, 256, 2, zero_point=True)],      # later ops read only the leading rows of their producer
     "ragged": [T.Config(192, 512, 2, bm=128, zero_point=True), T.Config(320, 128, 2, bm=128, zero_point=True)],
 }
 
 
-CHAIN_FLAGS = (0, 26, 40)     # resident chain variants (tmac_chain.cuh): plain grid barrier, tuned grid barrier, data flow
-CHAIN_DEFAULT = 40
+CHAIN_FLAGS = (0, 1)           # resident chain (tmac_chain.cuh): data flow (default), grid-barrier form
+CHAIN_DEFAULT = 0
 
 # the per-CTA reduction buffer grows with the number of row super-blocks one CTA touches: the 11008-row chain needs >= 7 CTAs
 CASES = [(n, g) for n in CHAINS for g in (0, 1, 2, 3, 7, 37) if not (n == "w4zp_k11008" and 0 < g < 7)]
@@ -123,7 +125,7 @@ def test_sequence_chain_matches_oracle(lib, oracle, name, grid):
                 tb.debug_set("chain_flags", flags)
                 info = run_chain(lib, oracle, chain, x0, offsets)
                 if info["ring_slots"] == -8:            # (it also needs every cluster resident: 11008 W4 rows = 172 clusters are too many)
-                    assert all(o % (2 if flags & 32 else 4) == 0 for o in offsets), info
+                    assert all(o % (4 if flags & 1 else 2) == 0 for o in offsets), info
     finally:
         for c in chain:
             c[3].free()
@@ -185,7 +187,7 @@ def test_sequence_independent_inputs_and_long_chain(lib, oracle):
             wt.free()
 
 
-@pytest.mark.parametrize("impl,flags", [(0, 0), (1, 26), (1, 40)], ids=["streamk", "resident_chain_barrier", "resident_chain_flow"])
+@pytest.mark.parametrize("impl,flags", [(0, 0), (1, 0), (1, 1)], ids=["streamk", "resident_chain", "resident_chain_grid_barrier"])
 def test_sequence_full_size_llama_shape(lib, oracle, impl, flags):
     """BASELINE shape 11008x4096 W2 g128 zp at full size, two chained ops (down-projection shape second)."""
     cfgs = [T.Config(11008, 4096, 2, zero_point=True).resolved(), T.Config(4096, 11008, 2, zero_point=True).resolved()]

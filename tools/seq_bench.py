@@ -24,7 +24,8 @@ ap.add_argument("--mout", type=int, default=bench.MOUT)
 ap.add_argument("--k", type=int, default=bench.K)
 ap.add_argument("--smem", type=int, default=0)
 ap.add_argument("--impl", type=int, default=2, help="0 stream-K sequence kernel, 1 resident gemv3 chain, 2 auto")
-ap.add_argument("--flags", type=str, default="", help="comma list of chain_flags values to time (resident chain only)")
+ap.add_argument("--dump", type=str, default="", help="save the raw chain trace [ops][grid][16] (ns) to this .npy")
+ap.add_argument("--flags", type=str, default="", help="comma list of chain_flags values to time (resident chain only): 0 data flow, 1 grid-barrier form")
 args = ap.parse_args()
 
 lib = tb.load(); tb.check(lib.tmac_b200_init(0), "init")
@@ -61,8 +62,11 @@ def timed(seq, reps):
 def chain_trace(seq):
     """Resident chain: globaltimer stamps of warp 0 of every CTA, [ops][grid][16] (tmac_chain.cuh)."""
     seq.launch(); seq.status()
-    t = seq.trace().astype(np.float64) / 1e3
-    names = ["top->barrier seen", "syncthreads", "LUT slice", "block wait", "lookups", "red sync", "cluster sync", "store+fence+arrive (leaders)"]
+    raw = seq.trace()
+    if args.dump:
+        np.save(args.dump, raw)
+    t = raw.astype(np.float64) / 1e3
+    names = ["top->barrier seen", "syncthreads", "input wait + LUT slice", "block wait", "lookups", "red sync", "CTA sums + send (barrier form: cluster sync)", "leader: partials landed, sum, publish"]
     ops = slice(2, None)
     def fmt(a):
         return "%.2f/%.2f/%.2f" % (np.median(a), np.percentile(a, 90), a.max())
