@@ -154,6 +154,11 @@ TMAC_B200_API int tmac_b200_qgemm_lut(int64_t handle, int row0, int rows, int N,
 TMAC_B200_API int tmac_b200_qgemm_lut_grouped(const int64_t *handles, int count, int N, int dtype,
                                               const void *const *QLUT, const void *const *LUT_Scales,
                                               const void *const *LUT_Biases, void *const *C);
+/* The one-call form of a fused group (q/k/v, gate/up: tensors of one geometry applied to the SAME activation rows, the
+ * sharing the reference's graph has between ggml_tmac_mul_mat_task_init and the task_compute calls of one op,
+ * 3rdparty/llama.cpp/ggml/src/ggml.c:12570-12600): ONE launch, the LUT built inside it.  B [N][K] and C[i] [N][Mout]
+ * are device pointers. */
+TMAC_B200_API int tmac_b200_gemv_grouped(const int64_t *handles, int count, int N, int dtype, const void *B, void *const *C);
 /* Fused convenience (llama_cpp_init + llama_cpp_compute of the whole tensor in one call,
  * workspaces owned by the library): C [N][M] = qgemm_lut(preprocessor(B)). */
 TMAC_B200_API int tmac_b200_gemv(int64_t handle, int N, int dtype, const void *B, void *C);

@@ -276,9 +276,12 @@ template <int PB, int MINB> gemv3_fn pick3_fused_qa(int qch, int agq) {
         case 8 * 16 + 8: return gemv3_kernel<PB, true, 8, 8, MINB, true>;
         case 8 * 16 + 4: return gemv3_kernel<PB, true, 8, 4, MINB, true>;
         case 8 * 16 + 2: return gemv3_kernel<PB, true, 8, 2, MINB, true>;
+        case 8 * 16 + 0: return gemv3_kernel<PB, true, 8, 0, MINB, true>;     // integer path (one activation group = K)
         case 4 * 16 + 4: return gemv3_kernel<PB, true, 4, 4, MINB, true>;
         case 4 * 16 + 2: return gemv3_kernel<PB, true, 4, 2, MINB, true>;
+        case 4 * 16 + 0: return gemv3_kernel<PB, true, 4, 0, MINB, true>;
         case 2 * 16 + 2: return gemv3_kernel<PB, true, 2, 2, MINB, true>;
+        case 2 * 16 + 0: return gemv3_kernel<PB, true, 2, 0, MINB, true>;
     }
     return nullptr;
 }
@@ -381,7 +384,8 @@ int launch_gemv3(const Resident &R, int row_begin, int row_end, int N, const int
     p.nbuf = (p.bpw > 1) ? 2 : 1;
     if (g.nbuf_override > 0) p.nbuf = std::min(p.nbuf, g.nbuf_override);
     const size_t wregion = std::max((size_t)p.wpc * (p.nbuf * L.blk + (size_t)L.qch * 4 * (sym ? 8 : 16)), (size_t)p.wpc * L.rsb * 4);
-    const size_t smem = (size_t)p.cs * L.rsb * 4 + ((wregion + 15) & ~(size_t)15) + (size_t)p.wpc * 16;   // + warp-private mbarriers
+    size_t smem = (size_t)p.cs * L.rsb * 4 + ((wregion + 15) & ~(size_t)15) + (size_t)p.wpc * 16;   // + warp-private mbarriers
+    if (fused_act && int_path) { p.ioff = (int)smem; smem += (size_t)(L.K / 32 + kG3MaxWarps + 4 + 8) * 4; }   // row scan: block sums, warp maxima, bias, cluster maxima
     if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     uint32_t wtx, wty;
     plane_weight_regs(L.bits, sym, &wtx, &wty);
@@ -1160,6 +1164,50 @@ int tmac_b200_qgemm_lut_grouped(const int64_t *handles, int count, int N, int dt
     return launch_gemv3(*rs[0], 0, L.Mout, N, nullptr, nullptr, nullptr, nullptr, L.Mout, 0, dtype == TMAC_B200_F16, sym, &bp);
 }
 
+/* q/k/v or gate/up in ONE launch with the LUT built inside it: `count` tensors of one geometry applied to the SAME activation
+ * rows B [N][K] (device), outputs C[i] [N][Mout] (device).  The one-call form of preprocessor + tmac_b200_qgemm_lut_grouped. */
+int tmac_b200_gemv_grouped(const int64_t *handles, int count, int N, int dtype, const void *B, void *const *C) {
+    std::unique_lock<std::shared_mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    if (!handles || count <= 0 || count > 65535 || !B || !C || N <= 0) return fail("gemv_grouped: bad arguments");
+    if (!is_device_ptr(B)) return fail("gemv_grouped: device pointers only");
+    std::vector<const Resident *> rs(count);
+    for (int i = 0; i < count; ++i) {
+        auto it = g.res.find(handles[i]);
+        if (it == g.res.end()) return fail("gemv_grouped: bad weight handle");
+        rs[i] = &it->second;
+        const StreamLayout &a = rs[0]->L, &b = rs[i]->L;
+        if (a.Mout != b.Mout || a.K != b.K || a.bits != b.bits || a.blk != b.blk || a.nchunk != b.nchunk || a.zp != b.zp ||
+            a.one_scale != b.one_scale || a.sd != b.sd || a.act_group_size != b.act_group_size || a.scale0 != b.scale0)
+            return fail("gemv_grouped: all tensors must share one geometry");
+        if (!is_device_ptr(C[i])) return fail("gemv_grouped: device pointers only");
+    }
+    const StreamLayout &L = rs[0]->L;
+    const bool int_path = L.one_scale && L.act_group_size == L.K;
+    if (!(int_path || L.act_group_size <= L.ck)) return fail("gemv_grouped: the activation group must lie inside a chunk (or be the whole row)");
+    std::vector<const void *> tab(5 * (size_t)count, nullptr);
+    for (int i = 0; i < count; ++i) { tab[i] = rs[i]->d; tab[4 * count + i] = C[i]; }
+    void *dtab = nullptr;
+    for (auto &e : g.ptr_tables)
+        if (e.first == tab) { dtab = e.second; break; }
+    if (!dtab) {
+        if (cudaMalloc(&dtab, tab.size() * sizeof(void *)) != cudaSuccess) { cudaGetLastError(); return fail("out of device memory (pointer table)"); }
+        CUDA_OK(cudaMemcpy(dtab, tab.data(), tab.size() * sizeof(void *), cudaMemcpyHostToDevice));
+        if (g.ptr_tables.size() >= 256) {
+            cudaStreamSynchronize(g.stream());
+            cudaFree(g.ptr_tables.front().second);
+            g.ptr_tables.erase(g.ptr_tables.begin());
+        }
+        g.ptr_tables.emplace_back(tab, dtab);
+    }
+    const void **dt = (const void **)dtab;
+    BatchPtrs bp;
+    bp.n = count;
+    bp.W = (const unsigned char *const *)dt; bp.q = (const int8_t *const *)(dt + count);
+    bp.ls = (const float *const *)(dt + 2 * count); bp.lb = (const float *const *)(dt + 3 * count); bp.C = (void *const *)(dt + 4 * count);
+    return launch_gemv3(*rs[0], 0, L.Mout, N, nullptr, nullptr, nullptr, nullptr, L.Mout, 0, dtype == TMAC_B200_F16, true, &bp, B, dtype == TMAC_B200_F16);
+}
+
 int tmac_b200_gemv(int64_t handle, int N, int dtype, const void *B, void *C) {
     std::unique_lock<std::shared_mutex> lk(g_mu);
     if (ensure_init()) return -1;
@@ -1176,7 +1224,7 @@ int tmac_b200_gemv(int64_t handle, int N, int dtype, const void *B, void *C) {
     const bool dev_b = kind_b == 2, dev_c = kind_c == 2;
     const bool int_path = L.one_scale && L.act_group_size == L.K;
     const bool prefill_shape = g.use_prefill && N >= g.prefill_min_n && L.pb == 2 && L.qch == 8 && L.act_group_size == 64 && !L.one_scale;
-    const bool can_fuse = g.use_fused && !int_path && L.act_group_size <= L.ck && g.lut_mode != 1 && !prefill_shape;
+    const bool can_fuse = g.use_fused && (int_path || L.act_group_size <= L.ck) && g.lut_mode != 1 && !prefill_shape;
     auto launch_compute = [&](const void *dB, void *dC) -> int {
         if (can_fuse)   // one launch: the GEMV builds each chunk's LUT slice itself (bit-identical tables)
             return launch_gemv3(R, 0, L.Mout, N, nullptr, nullptr, nullptr, dC, L.Mout, 0, dtype == TMAC_B200_F16, true, nullptr, dB,
@@ -1358,8 +1406,10 @@ static int seq_build_chain(Sequence &S) {
     if (cudaMalloc(&S.d_cops, n * sizeof(ChainOp)) != cudaSuccess || cudaMalloc(&S.d_bar, 256) != cudaSuccess ||
         cudaMalloc(&S.d_epochs, grid * sizeof(unsigned)) != cudaSuccess || cudaMalloc(&S.d_err, sizeof(int)) != cudaSuccess ||
         cudaMalloc(&S.d_cint, std::max<size_t>(ctot, 256)) != cudaSuccess || cudaMalloc(&S.d_y, lltot) != cudaSuccess) { cudaGetLastError(); S.release(); return fail("seq_build: out of device memory"); }
-    CUDA_OK(cudaMemset(S.d_y, 0, lltot));     // epoch 0 never matches: launches publish epochs >= 1
-    CUDA_OK(cudaMemset(S.d_bar, 0, 256)); CUDA_OK(cudaMemset(S.d_epochs, 0, grid * sizeof(unsigned))); CUDA_OK(cudaMemset(S.d_err, 0, sizeof(int)));
+    // (on the library's stream: the legacy default stream does not order against a non-blocking stream)
+    CUDA_OK(cudaMemsetAsync(S.d_y, 0, lltot, g.stream()));     // epoch 0 never matches: launches publish epochs >= 1
+    CUDA_OK(cudaMemsetAsync(S.d_bar, 0, 256, g.stream())); CUDA_OK(cudaMemsetAsync(S.d_epochs, 0, grid * sizeof(unsigned), g.stream()));
+    CUDA_OK(cudaMemsetAsync(S.d_err, 0, sizeof(int), g.stream()));
     for (int i = 0; i < n; ++i) {
         const StreamLayout &L = g.res.find(S.ops[i].handle)->second.L;
         ChainOp &o = ops[i];
@@ -1374,7 +1424,8 @@ static int seq_build_chain(Sequence &S) {
         o.ll_out = (uint2 *)((char *)S.d_y + lloff[i]);
         o.ll_in = S.ops[i].x_ext ? nullptr : (const uint2 *)((char *)S.d_y + lloff[S.ops[i].in_op]) + S.ops[i].in_off;
     }
-    CUDA_OK(cudaMemcpy(S.d_cops, ops.data(), n * sizeof(ChainOp), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpyAsync(S.d_cops, ops.data(), n * sizeof(ChainOp), cudaMemcpyHostToDevice, g.stream()));
+    CUDA_OK(cudaStreamSynchronize(g.stream()));
     S.cparams.ops = (const ChainOp *)S.d_cops; S.cparams.nops = n; S.cparams.max_blk = (int)max_blk;
     S.cparams.bar = (unsigned *)S.d_bar; S.cparams.epochs = (unsigned *)S.d_epochs; S.cparams.err = (int *)S.d_err;
     S.cparams.flags = g.chain_flags; S.cparams.trace = nullptr;
@@ -1382,7 +1433,7 @@ static int seq_build_chain(Sequence &S) {
     if (g.trace) {
         const size_t tb = (size_t)n * grid * (16 + 16 * kSeqWarps) * sizeof(long long);    // same size as the stream-K kernel's trace (seq_trace copies that much)
         if (cudaMalloc(&S.d_trace, tb) != cudaSuccess) { cudaGetLastError(); S.release(); return fail("seq_build: out of device memory (trace)"); }
-        cudaMemset(S.d_trace, 0, tb);
+        cudaMemsetAsync(S.d_trace, 0, tb, g.stream());
         S.cparams.trace = (long long *)S.d_trace;
     }
     S.cfn = fn; S.impl = 1; S.grid = grid; S.smem = smem; S.pb = pb; S.qch = qch; S.agq = agq; S.bits = bits;
@@ -1457,13 +1508,13 @@ int tmac_b200_seq_build(int64_t seq) {
         cudaMalloc(&S.d_err, sizeof(int)) != cudaSuccess) { cudaGetLastError(); S.release(); return fail("seq_build: out of device memory"); }
     if (g.trace) {
         if (cudaMalloc(&S.d_trace, (size_t)n * G * (16 + 16 * kSeqWarps) * sizeof(long long)) != cudaSuccess) { cudaGetLastError(); S.release(); return fail("seq_build: out of device memory (trace)"); }
-        cudaMemset(S.d_trace, 0, (size_t)n * G * (16 + 16 * kSeqWarps) * sizeof(long long));
+        cudaMemsetAsync(S.d_trace, 0, (size_t)n * G * (16 + 16 * kSeqWarps) * sizeof(long long), g.stream());
     }
-    CUDA_OK(cudaMemset(S.d_y, 0, ytot));
-    CUDA_OK(cudaMemset(S.d_lut, 0, std::max<size_t>(ltot, 256)));
-    CUDA_OK(cudaMemset(S.d_xchg, 0, xper * n));
-    CUDA_OK(cudaMemset(S.d_epochs, 0, G * sizeof(unsigned)));
-    CUDA_OK(cudaMemset(S.d_err, 0, sizeof(int)));
+    CUDA_OK(cudaMemsetAsync(S.d_y, 0, ytot, g.stream()));
+    CUDA_OK(cudaMemsetAsync(S.d_lut, 0, std::max<size_t>(ltot, 256), g.stream()));
+    CUDA_OK(cudaMemsetAsync(S.d_xchg, 0, xper * n, g.stream()));
+    CUDA_OK(cudaMemsetAsync(S.d_epochs, 0, G * sizeof(unsigned), g.stream()));
+    CUDA_OK(cudaMemsetAsync(S.d_err, 0, sizeof(int), g.stream()));
     for (int i = 0; i < n; ++i) {
         const Resident &R = g.res.find(S.ops[i].handle)->second;
         const StreamLayout &L = R.L;

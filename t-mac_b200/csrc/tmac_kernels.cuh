@@ -254,6 +254,7 @@ struct Gemv3Params {
     // fused LUT construction (FUSED instantiations): activations [N][K] f32 or f16 instead of qlut / lut_scales / lut_biases
     const void *act;
     int act_f16;
+    int ioff;                      // fused integer path (activation group = K): byte offset of the row-scan scratch in shared memory
     size_t rsb_stride;
     float scale0;
     long long *trace;
@@ -330,8 +331,11 @@ constexpr int kG3MaxWarps = 8;
 // best for a single launch per tensor) or 4 (64 registers, more CTAs in flight; best for grouped launches).
 // FUSED = build the LUT slice of each chunk inside the GEMV from the activation row (same fp32 operation
 // order as preprocessor_kernel / lut_ctor.cc, so QLUT bytes, LUT scales and LUT biases are bit-identical to
-// the two-kernel path) instead of reading QLUT / LUT_Scales / LUT_Biases.  Requires AGQ > 0 (activation
-// group inside a chunk) and SYM.
+// the two-kernel path) instead of reading QLUT / LUT_Scales / LUT_Biases.  Requires SYM.  AGQ > 0: activation
+// group inside a chunk, scale and bias per chunk by warp shuffles.  AGQ == 0 (integer path, ONE activation group
+// = the whole row, BitNet): every CTA scans the row once (K * 4 bytes, L2-resident) for the row-wide abs-sum
+// maximum -- cheaper than a cluster-wide exchange, which costs a rendezvous -- and the cluster leader also forms
+// the row's LUT bias in the reference's order (addv tree per 32 activations, serial over the blocks).
 template <int PB, bool SYM, int QCH, int AGQ, int MINB, bool FUSED = false>
 __global__ void __launch_bounds__(kG3MaxWarps * 32, MINB) gemv3_kernel(const Gemv3Params p, const uint32_t wtx, const uint32_t wty) {
     constexpr int RW = 8 / PB;
@@ -368,7 +372,11 @@ __global__ void __launch_bounds__(kG3MaxWarps * 32, MINB) gemv3_kernel(const Gem
     const int8_t *qb = p.qlut;
     const float *lsb = p.lut_scales, *lbb = p.lut_biases;
     void *Cb = p.C;
-    if (p.nbatch > 0) { const int z = blockIdx.z; Wb = p.Wv[z]; qb = p.qlutv[z]; lsb = p.lsv[z]; lbb = p.lbv[z]; Cb = p.Cv[z]; }
+    if (p.nbatch > 0) {
+        const int z = blockIdx.z;
+        Wb = p.Wv[z]; Cb = p.Cv[z];
+        if (!FUSED) { qb = p.qlutv[z]; lsb = p.lsv[z]; lbb = p.lbv[z]; }   // fused: the tensors of the group share the activation rows
+    }
     const unsigned char *rsb_base = Wb + (size_t)rsb * p.rsb_stride;
     const int nag = p.K / p.ags;
 
@@ -392,6 +400,100 @@ __global__ void __launch_bounds__(kG3MaxWarps * 32, MINB) gemv3_kernel(const Gem
     int iacc[RW];
 #pragma unroll
     for (int i = 0; i < RW; ++i) { cacc[i] = 0.f; iacc[i] = 0; }
+    float row_scale = 0.f, row_ts = 0.f;          // fused integer path: LUT scale of the row and its reciprocal
+    float *iscr = reinterpret_cast<float *>(smem + p.ioff);   // [K/32] block sums (leader) | [8] warp maxima | [1] bias
+    bool scan_split = false;                      // fused integer path: the cluster splits the row scan (else every CTA scans the row)
+    if (FUSED && INT_PATH) {
+        // Row-wide LUT scale and bias (lut_ctor.cc:232-260 partial_max over the whole row, :157 bias) without a preprocessor launch.
+        // Short rows (one round of four 16-byte loads per thread covers the row, K = 3200): every CTA scans the whole row itself,
+        // no exchange.  Long rows (K = 8640): that is 200 CTAs x 34 KB of reads on the same few L2 lines, several serial rounds;
+        // the cluster splits the row instead, maxima go to every peer and the block sums of LUT[0] to the last rank through
+        // distributed shared memory, one cluster barrier (measured: 4.55 / 5.31 us per 3200x3200 GEMV whole-row / split,
+        // 10.7 / 9.8 us per 3200x8640).  The last rank's last warp (idle or lightest: warps beyond the last chunk have no block)
+        // forms the bias serially; the leader needs it only in the epilogue.
+        const int nblk = p.K >> 5, ngrp = p.K >> 2, nth = WPC * 32;
+        float *wmax = iscr + nblk, *bias_out = wmax + kG3MaxWarps, *cmax = bias_out + 4;
+        scan_split = p.cs > 1 && ngrp > 4 * nth;
+        const bool bias_cta = rank == p.cs - 1;
+        auto load_group = [&](int gi, float &b0, float &b1, float &b2, float &b3) {
+            const size_t k0 = (size_t)n * p.K + (size_t)gi * 4;
+            if (p.act_f16) {
+                const uint2 h = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const __half *>(p.act) + k0));
+                const float2 f01 = __half22float2(*reinterpret_cast<const __half2 *>(&h.x)), f23 = __half22float2(*reinterpret_cast<const __half2 *>(&h.y));
+                b0 = f01.x; b1 = f01.y; b2 = f23.x; b3 = f23.y;
+            } else {
+                const float4 f = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p.act) + k0));
+                b0 = f.x; b1 = f.y; b2 = f.z; b3 = f.w;
+            }
+        };
+        // K-groups [gbeg, gend): LUT[0] = -LUT[15] of every group (:133-155), _mm256_addv_ps tree per block of 32 activations = 8
+        // lanes (lut_ctor.cc:24-31, as in the fp path below), block sums -> the bias CTA; returns the abs-sum maximum (:242-256)
+        auto scan = [&](int gbeg, int gend, bool want_max, bool remote) {
+            float mm = 0.f;
+            for (int g0 = gbeg + warp * 32; g0 < gend; g0 += nth) {   // lane = K-group (coalesced 16-byte loads)
+                const int gi = g0 + lane;
+                float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+                if (gi < gend) load_group(gi, b0, b1, b2, b3);
+                if (want_max) mm = fmaxf(mm, __fadd_rn(__fadd_rn(fabsf(b0), fabsf(b1)), __fadd_rn(fabsf(b2), fabsf(b3))));
+                float v = -__fadd_rn(__fadd_rn(__fadd_rn(b0, b1), b2), b3);
+                v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 4));
+                v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 2));
+                v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 1));
+                if ((lane & 7) == 0 && gi < gend) {
+                    if (remote) st_cluster_f32(iscr + (gi >> 3), p.cs - 1, v); else iscr[gi >> 3] = v;
+                }
+            }
+            return mm;
+        };
+        float m = 0.f;
+        if (scan_split) {
+            const int per = ((nblk + p.cs - 1) / p.cs) * 8;      // K-groups per CTA, whole blocks
+            cluster_wait();                                      // phase 1 ("every CTA of the cluster runs"): DSMEM may be written
+            m = scan(rank * per, min(ngrp, rank * per + per), true, true);
+        } else {
+            // four independent loads per thread in one round; every CTA starts at its own offset (the L2 serves a hot line one
+            // request at a time)
+            const int off = (int)(((long long)blockIdx.x * 160) % ngrp);
+            for (int g = tid; g < ngrp; g += 4 * nth) {
+                float b[4][4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int gj = g + j * nth;
+                    b[j][0] = b[j][1] = b[j][2] = b[j][3] = 0.f;
+                    if (gj < ngrp) { int gi = gj + off; if (gi >= ngrp) gi -= ngrp; load_group(gi, b[j][0], b[j][1], b[j][2], b[j][3]); }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) m = fmaxf(m, __fadd_rn(__fadd_rn(fabsf(b[j][0]), fabsf(b[j][1])), __fadd_rn(fabsf(b[j][2]), fabsf(b[j][3]))));
+            }
+            if (bias_cta) scan(0, ngrp, false, false);           // L1 hits
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) wmax[warp] = m;
+        __syncthreads();
+        m = wmax[0];
+        for (int w = 1; w < WPC; ++w) m = fmaxf(m, wmax[w]);
+        if (scan_split) {
+            if (tid < p.cs) st_cluster_f32(cmax + rank, tid, m);   // this CTA's maximum -> slot `rank` of every CTA of the cluster
+            cluster_sync_all();
+            m = cmax[0];
+            for (int r = 1; r < p.cs; ++r) m = fmaxf(m, cmax[r]);
+        }
+        row_scale = __fdiv_rn(m, 127.0f);
+        row_ts = (row_scale != 0.0f) ? __fdiv_rn(1.0f, row_scale) : 0.0f;
+        if (bias_cta && warp == WPC - 1) {
+            // serial over the blocks of the (single) activation group, from 0 (:157).  32 values per shared-memory round trip,
+            // the 32 shuffles of a round issued ahead of the dependent adds (fixed trip count); the tail is padded with +0.0,
+            // an exact no-op: an accumulator that starts at +0.0 is never -0.0
+            float bias = 0.0f;
+            for (int k0 = 0; k0 < nblk; k0 += 32) {
+                const float v = (k0 + lane < nblk) ? iscr[k0 + lane] : 0.f;
+#pragma unroll
+                for (int k = 0; k < 32; ++k) bias = __fadd_rn(bias, __shfl_sync(0xffffffffu, v, k));
+            }
+            if (lane == 0) *bias_out = bias;       // forwarded to the leader with the partial sums below
+        }
+    }
     const uint4 *qrow = reinterpret_cast<const uint4 *>(qb + (size_t)n * p.K * 4);
     const float *lsg = lsb + (size_t)n * nag, *lbg = lbb + (size_t)n * nag;
 
@@ -414,11 +516,15 @@ __global__ void __launch_bounds__(kG3MaxWarps * 32, MINB) gemv3_kernel(const Gem
                     b0 = f.x; b1 = f.y; b2 = f.z; b3 = f.w;
                 }
             }
-            float m = __fadd_rn(__fadd_rn(fabsf(b0), fabsf(b1)), __fadd_rn(fabsf(b2), fabsf(b3)));
+            float scale, ts;
+            if (INT_PATH) { scale = row_scale; ts = row_ts; }
+            else {
+                float m = __fadd_rn(__fadd_rn(fabsf(b0), fabsf(b1)), __fadd_rn(fabsf(b2), fabsf(b3)));
 #pragma unroll
-            for (int o = W / 2; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-            const float scale = __fdiv_rn(m, 127.0f);
-            const float ts = (scale != 0.0f) ? __fdiv_rn(1.0f, scale) : 0.0f;
+                for (int o = W / 2; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                scale = __fdiv_rn(m, 127.0f);
+                ts = (scale != 0.0f) ? __fdiv_rn(1.0f, scale) : 0.0f;
+            }
             float od[8];                                   // odd entries 1,3,...,15
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -439,18 +545,20 @@ __global__ void __launch_bounds__(kG3MaxWarps * 32, MINB) gemv3_kernel(const Gem
                 if (e < 4) lo |= (uint32_t)(q & 0xff) << (8 * e); else hi |= (uint32_t)(q & 0xff) << (8 * (e - 4));
             }
             if (lane < NG) reinterpret_cast<uint2 *>(tab)[lane] = make_uint2(lo, hi);
-            // LUT bias: _mm256_addv_ps tree per 8 groups (lut_ctor.cc:24-31), serial over the blocks of a group (:157)
-            float v = -od[7];                              // LUT[0] = -LUT[15]
-            v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 4));
-            v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 2));
-            v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 1));
+            if (!INT_PATH) {
+                // LUT bias: _mm256_addv_ps tree per 8 groups (lut_ctor.cc:24-31), serial over the blocks of a group (:157)
+                float v = -od[7];                          // LUT[0] = -LUT[15]
+                v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 4));
+                v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 2));
+                v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 1));
 #pragma unroll
-            for (int a = 0; a < NAG; ++a) {
-                lsv[a] = __shfl_sync(0xffffffffu, scale, a * W);
-                float bias = 0.f;
+                for (int a = 0; a < NAG; ++a) {
+                    lsv[a] = __shfl_sync(0xffffffffu, scale, a * W);
+                    float bias = 0.f;
 #pragma unroll
-                for (int k = 0; k < W / 8; ++k) bias = __fadd_rn(bias, __shfl_sync(0xffffffffu, v, a * W + 8 * k));
-                lbsum += bias;
+                    for (int k = 0; k < W / 8; ++k) bias = __fadd_rn(bias, __shfl_sync(0xffffffffu, v, a * W + 8 * k));
+                    lbsum += bias;
+                }
             }
         } else {
             if (lane < QCH * 4) {
@@ -526,7 +634,11 @@ __global__ void __launch_bounds__(kG3MaxWarps * 32, MINB) gemv3_kernel(const Gem
     __syncthreads();
     if (tid == 0) TMAC_TRACE(5);
     const int nthreads = WPC * 32;
-    if (p.cs > 1) cluster_wait();                 // every CTA of the cluster has started: its shared memory may be written
+    if (p.cs > 1 && !scan_split) cluster_wait();  // every CTA of the cluster has started: its shared memory may be written
+    if (FUSED && INT_PATH && p.cs > 1 && rank == p.cs - 1 && tid == (WPC - 1) * 32) {
+        float *bias_out = iscr + (p.K >> 5) + kG3MaxWarps;
+        st_cluster_f32(bias_out, 0, *bias_out);    // written by this thread after the row scan
+    }
     for (int t = tid; t < RSB; t += nthreads) {
         float fsum = 0.f; int isum = 0;
         for (int w = 0; w < WPC; ++w) {
@@ -553,8 +665,8 @@ __global__ void __launch_bounds__(kG3MaxWarps * 32, MINB) gemv3_kernel(const Gem
                 // C = ((sum_b alpha_b*CBits_b) * LUT_Scales[0] + LUT_Biases[0]*alpha_0) * Scales[0]
                 // (python/t_mac/ops/qgemm.py:160,171-174); isum = sum_b 2*alpha_b*CBits_b exactly.
                 const float cb = __fmul_rn((float)isum, 0.5f);
-                const float t1 = __fmul_rn(cb, __ldg(lsg));
-                const float t2 = __fmul_rn(__ldg(lbg), 0.5f);
+                const float t1 = __fmul_rn(cb, FUSED ? row_scale : __ldg(lsg));
+                const float t2 = __fmul_rn(FUSED ? iscr[(p.K >> 5) + kG3MaxWarps] : __ldg(lbg), 0.5f);
                 out = __fmul_rn(__fadd_rn(t1, t2), p.scale0);
             } else
                 out = fsum;

@@ -44,7 +44,7 @@ EXPORTS = [
     "tmac_b200_find_kcfg", "tmac_b200_clear_kcfg", "tmac_b200_upload_weights", "tmac_b200_upload_plain",
     "tmac_b200_upload_plain_rows", "tmac_b200_debug_encode", "tmac_b200_free_weights", "tmac_b200_clone_weights", "tmac_b200_hint_next_weights",
     "tmac_b200_graph_begin", "tmac_b200_graph_end", "tmac_b200_graph_launch", "tmac_b200_graph_free", "tmac_b200_sync", "tmac_b200_debug_trace", "tmac_b200_debug_last_launch", "tmac_b200_debug_set", "tmac_b200_weights_nbytes", "tmac_b200_preprocessor",
-    "tmac_b200_qgemm_lut", "tmac_b200_qgemm_lut_grouped", "tmac_b200_gemv", "tmac_b200_cbits", "qgemm_lut_int8", "preprocessor_int8",
+    "tmac_b200_qgemm_lut", "tmac_b200_qgemm_lut_grouped", "tmac_b200_gemv", "tmac_b200_gemv_grouped", "tmac_b200_cbits", "qgemm_lut_int8", "preprocessor_int8",
     "ggml_tmac_init", "ggml_tmac_free", "ggml_tmac_mul_mat_task_init", "ggml_tmac_mul_mat_task_compute",
     "ggml_tmac_set_n_threads", "ggml_tmac_get_type_bits", "ggml_tmac_b200_can_mul_mat",
     "ggml_tmac_b200_mul_mat_get_wsize", "ggml_tmac_b200_get_nbytes", "ggml_tmac_b200_transform_tensor",
@@ -85,6 +85,7 @@ def load() -> C.CDLL:
         "tmac_b200_preprocessor": (i, [i, i, i, i, vp, vp, vp, vp]),
         "tmac_b200_qgemm_lut": (i, [i64, i, i, i, i, vp, vp, vp, vp]),
         "tmac_b200_qgemm_lut_grouped": (i, [vp, i, i, i, vp, vp, vp, vp]),
+        "tmac_b200_gemv_grouped": (i, [vp, i, i, i, vp, vp]),
         "tmac_b200_gemv": (i, [i64, i, i, vp, vp]), "tmac_b200_cbits": (i, [i64, i, vp, vp]),
         "qgemm_lut_int8": (i, [i, i, i, i, vp, vp, vp, vp, vp, vp]),
         "preprocessor_int8": (i, [i, i, i, i, vp, vp, vp, vp]),
@@ -213,6 +214,14 @@ def qgemm_lut_grouped(wts, N, qluts, lut_scales, lut_biases, outs, dtype=F32):
         return (C.c_void_p * n)(*[ptr(x) for x in xs])
     check(load().tmac_b200_qgemm_lut_grouped(H, n, N, dtype, arr(qluts), arr(lut_scales), arr(lut_biases), arr(outs)),
           "tmac_b200_qgemm_lut_grouped")
+
+
+def gemv_grouped(wts, N, B, outs, dtype=F32):
+    """len(wts) tensors of one geometry applied to the same activation rows B in ONE launch, LUT built inside (device tensors)."""
+    n = len(wts)
+    H = (C.c_int64 * n)(*[w.handle for w in wts])
+    O = (C.c_void_p * n)(*[ptr(x) for x in outs])
+    check(load().tmac_b200_gemv_grouped(H, n, N, dtype, ptr(B), O), "tmac_b200_gemv_grouped")
 
 
 def gemv(wt: Weights, N, B, Cout, dtype=F32):

@@ -379,6 +379,80 @@ def test_fused_gemv_fp16_and_plain_upload(lib, oracle):
         wt.free()
 
 
+@pytest.mark.parametrize("K", [3200, 8640, 96], ids=["k3200", "k8640_half_chunks", "k96"])
+def test_fused_gemv_integer_path_row_wide_scale(lib, oracle, K):
+    """BitNet grouping (ONE activation group = the whole row, reference tools/run_pipeline.py:409-412): tmac_b200_gemv builds the
+    LUT inside the GEMV -- every CTA scans the row for the row-wide scale, the cluster leader forms the bias in the reference's
+    summation order -- and must equal the oracle bit for bit (int32 path), for N > 1, fp32 and fp16 activations, and equal the
+    two-call form."""
+    cfg = T.Config(640, K, 2, kfactor=8 if K % 64 else 16, one_scale=True).resolved()
+    N = 3
+    w, sc, z, x = T.make_problem(cfg, seed=12, N=N)
+    x = x.astype(np.float16).astype(np.float32)            # fp16-representable: the fp16 call sees the same values
+    x[1] *= 32.0; x[2, : K // 2] = 0.0                      # rows with different maxima; a row with a zero half
+    A, S = T.pack_reference_layout(w, sc, z, cfg)
+    wt = tb.upload_plain(kc(cfg), w, sc, z)
+    try:
+        qo, lso, lbo = oracle.preprocessor(x, cfg.act_group_size)
+        Co = oracle.qgemm(cfg, A, S, qo, lso, lbo)
+        dx = torch.from_numpy(x).cuda()
+        one = torch.zeros((N, cfg.Mout), device="cuda"); two = torch.zeros_like(one)
+        tb.gemv(wt, N, dx, one)
+        assert tb.last_launch()["batch"] >= 1
+        tb.debug_set("fused", 0)
+        tb.gemv(wt, N, dx, two)
+        tb.debug_set("fused", 1)
+        torch.cuda.synchronize()
+        assert np.array_equal(one.cpu().numpy().view(np.uint32), Co.view(np.uint32)), "fused integer path must be bit exact"
+        assert np.array_equal(two.cpu().numpy().view(np.uint32), Co.view(np.uint32))
+        h16 = torch.zeros((N, cfg.Mout), dtype=torch.float16, device="cuda")
+        tb.gemv(wt, N, dx.half(), h16, dtype=tb.F16)
+        torch.cuda.synchronize()
+        assert np.array_equal(h16.cpu().numpy(), Co.astype(np.float16)), "fp16 activations / outputs: same table, one rounding at the store"
+        zero = torch.zeros((1, K), device="cuda"); oz = torch.ones((1, cfg.Mout), device="cuda")
+        tb.gemv(wt, 1, zero, oz)                            # all-zero row: scale 0 -> table 0 (lut_ctor.cc:124)
+        assert float(oz.abs().max()) == 0.0
+    finally:
+        tb.debug_set("fused", 1)
+        wt.free()
+
+
+@pytest.mark.parametrize("cfg", [T.Config(512, 2048, 2, zero_point=True), T.Config(640, 3200, 2, one_scale=True), T.Config(384, 1024, 4)],
+                         ids=["w2zp", "bitnet", "w4"])
+def test_gemv_grouped_equals_single_launches(lib, oracle, cfg):
+    """tmac_b200_gemv_grouped (q/k/v, gate/up: one launch, shared activation rows, LUT built inside) against the oracle; on the
+    integer path also bit-identical to tmac_b200_gemv per tensor (the fp path's K split differs between the two launch shapes)."""
+    cfg = cfg.resolved()
+    N = 2
+    probs = [T.make_problem(cfg, seed=70 + i, N=N) for i in range(3)]
+    x = probs[0][3]
+    wts = [tb.upload_plain(kc(cfg), w, sc, z) for (w, sc, z, _) in probs]
+    try:
+        dx = torch.from_numpy(x).cuda()
+        outs = [torch.zeros((N, cfg.Mout), device="cuda") for _ in wts]
+        single = [torch.zeros((N, cfg.Mout), device="cuda") for _ in wts]
+        tb.gemv_grouped(wts, N, dx, outs)
+        assert tb.last_launch()["batch"] == 3
+        for wt, o in zip(wts, single):
+            tb.gemv(wt, N, dx, o)
+        torch.cuda.synchronize()
+        qo, lso, lbo = oracle.preprocessor(x, cfg.act_group_size)
+        for (w, sc, z, _), o, s1 in zip(probs, outs, single):
+            A, S = T.pack_reference_layout(w, sc, z, cfg)
+            Co = oracle.qgemm(cfg, A, S, qo, lso, lbo)
+            got = o.cpu().numpy()
+            if cfg.one_scale:                               # integer path: exact whatever the K split of the launch
+                assert np.array_equal(got.view(np.uint32), s1.cpu().numpy().view(np.uint32))
+                assert np.array_equal(got.view(np.uint32), Co.view(np.uint32))
+            else:
+                assert np.abs(got - Co).max() <= TIGHT_TOL * np.abs(Co).max()
+        with pytest.raises(tb.TMACError):
+            tb.gemv_grouped(wts, N, x, outs)               # host activation pointer
+    finally:
+        for wt in wts:
+            wt.free()
+
+
 def test_full_size_properties(lib, oracle):
     """BASELINE.json full size (W2 g128 zp, 11008 x 4096): size-independent properties + a row sample
     against the oracle.  (a) determinism, (b) linearity in the weight scales: doubling every
