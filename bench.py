@@ -431,6 +431,7 @@ def main():
         return t
 
     seq_report = None
+    step_is_sequence = False
     if "error" in seqs:
         seq_report = seqs
     else:
@@ -452,6 +453,7 @@ def main():
             value = world * bytes_step / (ms_per_step * 1e-3) / 1e9
             launches["n"] = args.steps
             submission = "ONE persistent launch per step (%s); GEMV i+1 consumes GEMV i's output" % seq_kind.split(":")[0]
+            step_is_sequence = resident
 
     timed(g_two, 3, False)
     ms_two = timed(g_two, args.steps, False) / args.steps
@@ -473,6 +475,23 @@ def main():
             tj = json.load(open(tp))
             roofline["traffic"] = tj.get("gemv_kernel_dram_bytes_per_launch")
             roofline["traffic_source"] = "static: " + str(tj.get("source", "profiles/traffic.json (ncu --set full capture)"))
+        except Exception:
+            pass
+
+    if step_is_sequence:
+        # the step IS one launch of the resident chain kernel: it is the dominant kernel.  One launch processes LAYERS GEMVs
+        # (LAYERS x the per-GEMV algorithmic bytes); its duration is the CUDA-event time of the step (one kernel per step).
+        roofline["gemv3_launch_chain_kernel"] = {"kernel": kname, "launch": lone_cfg, "achieved": achieved, "frac": achieved / peak, "us_per_launch": t_gemv * 1e6,
+                                                 "algorithmic_bytes_per_launch": algorithmic_bytes(), "traffic": roofline.get("traffic"), "traffic_source": roofline.get("traffic_source")}
+        a2 = bytes_step / (ms_per_step * 1e-3) / 1e9
+        roofline.update({"kernel": "chain_kernel<PB=2,QCH=8,AGQ=4> (tmac_chain.cuh; one persistent launch = %d GEMVs)" % LAYERS, "launch": seq_report["info"],
+                         "achieved": a2, "frac": a2 / peak, "us_per_launch": ms_per_step * 1e3, "algorithmic_bytes_per_launch": bytes_step, "traffic": None})
+        roofline.pop("traffic_source", None)
+        try:
+            tj = json.load(open(tp))
+            if tj.get("chain_kernel_dram_bytes_per_launch"):
+                roofline["traffic"] = tj["chain_kernel_dram_bytes_per_launch"]
+                roofline["traffic_source"] = "static: " + str(tj.get("chain_source", "profiles/traffic.json (ncu --set full capture)"))
         except Exception:
             pass
 

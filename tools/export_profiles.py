@@ -37,7 +37,7 @@ def summary(rep, note, dst):
 def main():
     shutil.copy(os.path.join(G, "r2_bench.json"), os.path.join(P, "r2_bench.json"))
     shutil.copy(os.path.join(G, "r2_launches.csv"), os.path.join(P, "r2_launches.csv"))
-    for extra in ("r2_bench_n2.json", "r2_bench_n8.json", "r2_sanitizer.txt", "r2_pf16.txt"):
+    for extra in ("r2_bench_n2.json", "r2_bench_n8.json", "r2_sanitizer.txt", "r2_sanitizer_late.txt", "r2_pf16.txt"):
         if os.path.exists(os.path.join(G, extra)):
             shutil.copy(os.path.join(G, extra), os.path.join(P, extra))
     d, u = summary(os.path.join(G, "r2_prof_gemv3.ncu-rep"), "(one launch of the chain of bench.py --eager: fused LUT build, cold cache, serialised by ncu: --set full --clock-control none)",
@@ -46,6 +46,9 @@ def main():
     # profiles/traffic.json is maintained by hand from these captures (see its `source`): the chain launch also prefetches the next tensor
     summary(os.path.join(G, "r2_prof_seq.ncu-rep"), "(one persistent launch = 32 GEMVs 11008x4096 W2, dependent chain, tools/seq_bench.py; --set full --clock-control none)",
             "r2_seq_ncu_summary.txt")
+    if os.path.exists(os.path.join(G, "r2_prof_chain.ncu-rep")):
+        summary(os.path.join(G, "r2_prof_chain.ncu-rep"), "(one persistent launch = 32 GEMVs 11008x4096 W2, dependent chain, resident chain kernel, tools/seq_bench.py --impl 1; --set full --clock-control none)",
+                "r2_chain_ncu_summary.txt")
     summary(os.path.join(G, "r2_prof_pf16.ncu-rep"), "(prefill tile, N = 256 tokens x 11008x4096 W2 g128 zp, tools/pf_one.py 256 1 0; --set full --clock-control none)",
             "r2_prefill16_ncu_summary.txt")
     # SASS excerpt: the Blackwell-only mnemonics of the in-tree library
