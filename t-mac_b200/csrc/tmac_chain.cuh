@@ -15,7 +15,7 @@
 //     of the way of the latency-critical words (requesting it earlier, across the hand-over, measured 1.3 us per op SLOWER:
 //     12.7 MB of bulk traffic queue in front of the words everybody waits for);
 //   * CTA placement is fixed for the whole chain (688 CTAs of 128 threads, all resident: 4 or 5 per SM).
-// Measured on the bench chain (32 x 11008x4096 W2, x[i+1] = first K outputs of op i): 5.55 us per GEMV against 6.35 for the
+// Measured on the bench chain (32 x 11008x4096 W2, x[i+1] = first K outputs of op i): 5.05 us per GEMV against 6.35 for the
 // launch chain and 8.0 for tmac_seq.cuh; flags bit 0 selects the grid-barrier form this kernel started as (7.0 us), kept for
 // comparison.  Per-phase stamps (ChainParams::trace) are read by tools/seq_bench.py --trace.
 // Same arithmetic as gemv3's fused path: LUT bytes identical to the preprocessor, fp32 sums in fixed (warp, then cluster rank)
@@ -56,8 +56,12 @@ struct ChainParams {
     long long *trace;                       // debug: [nops][grid][16] globaltimer stamps of thread 0, or NULL
 };
 
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait_acq() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// The split-phase barrier of the data-flow form guards only the RE-USE of shared-memory buffers (red, cl): the readers have
+// consumed their values before they arrive, the writers write after they have waited.  It carries no data, so it needs neither
+// release on the arrive side -- which ptxas turns into MEMBAR.ALL.GPU per thread and op (ncu: 15 % of the warp stall time of the
+// first version was `membar`; 5.40 -> 5.05 us per GEMV).  (barrier.cluster.wait has only the acquire form.)
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acq() { asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
 // partial sum -> the leader's shared memory, completion counted on the leader's mbarrier
 __device__ __forceinline__ void st_async_f32(float *local_ptr, uint64_t *local_bar, uint32_t rank, float v) {
     uint32_t ra, rb;
