@@ -329,16 +329,27 @@ def main():
     #      op i's output (first K rows) -- a TRUE data dependency carried through HBM -- and, for comparison, with the
     #      independent inputs of the launch chain above.  Both write every layer's output.
     out_seq = torch.zeros((LAYERS, MOUT), device="cuda")
+    sv2, gathered2, out_plain = None, None, None
+    if world > 1:
+        # row-sharded form of the sequence: every op also stores its rows into every rank's [world][LAYERS][MOUT] buffer from its
+        # epilogue (tmac_b200_seq_peer_outputs), one flag exchange per step; a second, peer-less copy of the sequence checks it
+        sv2 = tb.SharedVector(world * LAYERS * MOUT, dist, rank, world)
+        gathered2 = sv2.local.view(world, LAYERS, MOUT)
+        out_seq = gathered2[rank]
+        out_plain = torch.zeros((LAYERS, MOUT), device="cuda")
     seqs = {}
     try:
-        for name, chained in (("dependent", True), ("independent", False), ("dependent_streamk", True)):
+        for name, chained in (("dependent", True), ("independent", False), ("dependent_streamk", True)) + ((("dependent_plain", True),) if world > 1 else ()):
             tb.debug_set("seq_impl", 0 if name.endswith("streamk") else 2)     # 2 = resident chain where the sequence qualifies
             sq = tb.Sequence()
+            dst = out_plain if name == "dependent_plain" else out_seq
             for i, wt in enumerate(layers):
                 if chained and i > 0:
-                    sq.add(wt, in_op=i - 1, in_offset=0, out=out_seq[i])
+                    sq.add(wt, in_op=i - 1, in_offset=0, out=dst[i])
                 else:
-                    sq.add(wt, x=x[i], out=out_seq[i])
+                    sq.add(wt, x=x[i], out=dst[i])
+                if sv2 is not None and name == "dependent":
+                    sq.peer_outputs(i, [sv2.peer_ptr(q) + 4 * (rank * LAYERS + i) * MOUT for q in range(world) if q != rank])
             sq.build()
             seqs[name] = sq
     except Exception as ex:
@@ -410,9 +421,11 @@ def main():
     out_launch_chain = out.clone()
     submission = "one tmac_b200_gemv launch per layer (LUT build fused), %d launches captured in one CUDA graph with programmatic-dependent-launch edges" % LAYERS
 
-    def timed_seq(sq, steps):
+    def timed_seq(sq, steps, flags=None):
         for _ in range(3):
             sq.launch()
+            if flags is not None:
+                flags.barrier()
         sq.status()
         if world > 1:
             dist.barrier()
@@ -422,6 +435,8 @@ def main():
             e0.record(stream)
             for _ in range(steps):
                 sq.launch()
+                if flags is not None:
+                    flags.barrier()             # one flag exchange per step: every rank's rows of this step are in place everywhere
             e1.record(stream)
         torch.cuda.synchronize()
         sq.status()
@@ -435,8 +450,20 @@ def main():
     if "error" in seqs:
         seq_report = seqs
     else:
-        ms_dep, ms_ind, ms_sk = timed_seq(seqs["dependent"], args.steps), timed_seq(seqs["independent"], args.steps), timed_seq(seqs["dependent_streamk"], args.steps)
+        ms_dep, ms_ind, ms_sk = timed_seq(seqs["dependent"], args.steps, sv2), timed_seq(seqs["independent"], args.steps), timed_seq(seqs["dependent_streamk"], args.steps)
         seqs["dependent"].launch(); seqs["dependent"].status()       # the dependent chain's outputs for the parity check (host copy taken now)
+        seq_gather_ok = None
+        if world > 1:
+            # the sharded sequence must equal its peer-less copy bit for bit, and its fused gather an NCCL all-gather of the ranks' rows
+            sv2.barrier()
+            seqs["dependent_plain"].launch(); seqs["dependent_plain"].status()
+            torch.cuda.synchronize(); dist.barrier()
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(nccl_gathered.view(-1), out_seq.reshape(-1))
+            torch.cuda.synchronize()
+            okt = torch.tensor([1 if (torch.equal(gathered2, nccl_gathered) and torch.equal(out_plain, out_seq)) else 0], device="cuda", dtype=torch.int32)
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            seq_gather_ok = bool(okt.item())
         out_seq_host = out_seq.cpu().numpy()
         out_seq_nan_now = bool(np.isnan(out_seq_host).any())
         resident = seqs["dependent"].info()["ring_slots"] < 0
@@ -448,10 +475,13 @@ def main():
                       "independent_inputs": {"ms_per_step": ms_ind, "GBps": world * bytes_step / (ms_ind * 1e-3) / 1e9, "us_per_gemv": ms_ind * 1e3 / LAYERS},
                       "streamk_sequence_kernel_dependent_chain": {"ms_per_step": ms_sk, "us_per_gemv": ms_sk * 1e3 / LAYERS, "what": "same chain through tmac_seq.cuh (the fallback for sequences the resident chain does not take)"},
                       "info": seqs["dependent"].info()}
-        if ms_dep < ms_per_step and world == 1:      # the dependent chain in one launch beats the chain of launches: it is the step
+        if world > 1:
+            seq_report["sharded"] = {"what": "every op stores its rows into every rank's output buffer from its epilogue (tmac_b200_seq_peer_outputs) + one flag exchange per step; 0 NCCL launches",
+                                     "gather_equals_nccl_all_gather_and_peerless_sequence": seq_gather_ok}
+        if ms_dep < ms_per_step and (world == 1 or seq_gather_ok):      # the dependent chain in one launch beats the chain of launches: it is the step
             ms_per_step = ms_dep
             value = world * bytes_step / (ms_per_step * 1e-3) / 1e9
-            launches["n"] = args.steps
+            launches["n"] = args.steps * (2 if world > 1 else 1)       # + the flag exchange
             submission = "ONE persistent launch per step (%s); GEMV i+1 consumes GEMV i's output" % seq_kind.split(":")[0]
             step_is_sequence = resident
 

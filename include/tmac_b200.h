@@ -193,6 +193,11 @@ TMAC_B200_API int tmac_b200_ipc_free(void *ptr);
  *   (act_group_size <= 128).  Results equal tmac_b200_gemv up to fp32 re-association (different K split). */
 TMAC_B200_API int64_t tmac_b200_seq_create(void);
 TMAC_B200_API int tmac_b200_seq_add_gemv(int64_t seq, int64_t handle, const void *x, int in_op, int in_offset, void *C, int dtype);
+/* Row-sharded sequences (multi-GPU): op `op` also stores its finished rows at ptrs[q][row] for q < count <= 7 -- device
+ * pointers into peer memory (tmac_b200_ipc_open), each already offset to this shard's first row -- from the same epilogue that
+ * stores C; the all-gather of a sharded chain without a collective launch (pair with tmac_b200_peer_barrier after the launch).
+ * Call before tmac_b200_seq_build; needs the resident chain kernel (the build fails otherwise). */
+TMAC_B200_API int tmac_b200_seq_peer_outputs(int64_t seq, int op, void *const *ptrs, int count);
 TMAC_B200_API int tmac_b200_seq_build(int64_t seq);     /* allocates the device tables; no more ops afterwards */
 TMAC_B200_API int tmac_b200_seq_launch(int64_t seq);    /* asynchronous, on the current stream; capturable in a CUDA graph */
 TMAC_B200_API int tmac_b200_seq_status(int64_t seq);    /* synchronises; 0 = ok, -1 = a bounded wait inside the kernel expired */

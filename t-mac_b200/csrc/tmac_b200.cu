@@ -148,7 +148,7 @@ std::map<int64_t, cudaGraphExec_t> g_graphs;   // tmac_b200_graph_*
 int64_t g_next_graph = 1;
 
 // decode sequences (tmac_b200_seq_*)
-struct SeqOpHost { int64_t handle; const void *x_ext; int in_op, in_off; void *C; int out_f16; };
+struct SeqOpHost { int64_t handle; const void *x_ext; int in_op, in_off; void *C; int out_f16; int npeer = 0; void *peer[7] = {}; };
 struct Sequence {
     std::vector<SeqOpHost> ops;
     bool built = false;
@@ -1365,6 +1365,21 @@ int tmac_b200_seq_add_gemv(int64_t seq, int64_t handle, const void *x, int in_op
     return (int)S.ops.size() - 1;
 }
 
+/* Multi-GPU row sharding inside a sequence (as tmac_b200_peer_outputs for single launches): op `op` also stores its finished rows
+ * at ptrs[q][row] -- device pointers into PEER memory, each already offset to this shard's first row.  Before seq_build. */
+int tmac_b200_seq_peer_outputs(int64_t seq, int op, void *const *ptrs, int count) {
+    std::unique_lock<std::shared_mutex> lk(g_mu);
+    auto it = g_seqs.find(seq);
+    if (it == g_seqs.end()) return fail("seq_peer_outputs: bad sequence");
+    Sequence &S = it->second;
+    if (S.built) return fail("seq_peer_outputs: sequence already built");
+    if (op < 0 || op >= (int)S.ops.size() || count < 0 || count > 7 || (count && !ptrs)) return fail("seq_peer_outputs: bad op / 0..7 peers");
+    if (!S.ops[op].C) return fail("seq_peer_outputs: the op has no output vector");
+    S.ops[op].npeer = count;
+    for (int q = 0; q < count; ++q) S.ops[op].peer[q] = ptrs[q];
+    return 0;
+}
+
 // Resident gemv3 chain (tmac_chain.cuh): 1 = built, 0 = the sequence does not qualify (caller falls back), -1 = error.
 static int seq_build_chain(Sequence &S) {
     const int n = (int)S.ops.size();
@@ -1420,6 +1435,8 @@ static int seq_build_chain(Sequence &S) {
         o.blk_bytes = (int)L.blk; o.bpw = (L.nchunk + kChainCS * kChainWarps - 1) / (kChainCS * kChainWarps);
         o.zp = L.zp; o.one_scale = L.one_scale; o.sd = L.sd; o.out_f16 = S.ops[i].out_f16; o.scale0 = L.scale0;
         o.in_op = S.ops[i].x_ext ? -1 : S.ops[i].in_op;
+        o.npeer = S.ops[i].npeer; o.pad_ = 0;
+        for (int q = 0; q < 7; ++q) o.Cpeer[q] = q < S.ops[i].npeer ? S.ops[i].peer[q] : nullptr;
 
         o.ll_out = (uint2 *)((char *)S.d_y + lloff[i]);
         o.ll_in = S.ops[i].x_ext ? nullptr : (const uint2 *)((char *)S.d_y + lloff[S.ops[i].in_op]) + S.ops[i].in_off;
@@ -1454,6 +1471,7 @@ int tmac_b200_seq_build(int64_t seq) {
         if (rc != 0) return rc < 0 ? -1 : 0;
         if (g.seq_impl == 1) return fail("seq_build: the sequence does not qualify for the resident chain kernel (fp path, one format, fp32 16-byte aligned inputs, clusters resident)");
     }
+    for (auto &o : S.ops) if (o.npeer) return fail("seq_build: peer outputs need the resident chain kernel, and this sequence does not qualify for it");
     const int G = g.seq_grid > 0 ? std::min(g.seq_grid, g.sms) : g.sms;
     const int n = (int)S.ops.size();
     std::vector<SeqOp> ops(n);

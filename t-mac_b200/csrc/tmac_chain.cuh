@@ -43,6 +43,9 @@ struct ChainOp {
     int in_op;                              // producer op of x, or -1 (external input)
     uint2 *ll_out;                          // [rows] {value bits, epoch} words written next to C
     const uint2 *ll_in;                     // the producer's words, already offset (NULL: external input, plain loads)
+    // multi-GPU row sharding (as Gemv3Params::Cpeer): the finished rows are also stored straight into the peers' output vectors
+    int npeer, pad_;
+    void *Cpeer[7];
 };
 
 struct ChainParams {
@@ -298,6 +301,10 @@ __global__ void __launch_bounds__(kChainWarps * 32, 5) chain_kernel(const ChainP
                             seq_publish(o.ll_out + row, __float_as_uint(fsum), ep_out);
                             if (o.out_f16) reinterpret_cast<__half *>(o.C)[row] = __float2half_rn(fsum);
                             else reinterpret_cast<float *>(o.C)[row] = fsum;
+                            for (int q = 0; q < o.npeer; ++q) {      // the all-gather, fused into the epilogue: one store per peer and row
+                                if (o.out_f16) reinterpret_cast<__half *>(o.Cpeer[q])[row] = __float2half_rn(fsum);
+                                else reinterpret_cast<float *>(o.Cpeer[q])[row] = fsum;
+                            }
                         }
                     }
                     if (tr) tr[8] = chain_now();
@@ -323,6 +330,10 @@ __global__ void __launch_bounds__(kChainWarps * 32, 5) chain_kernel(const ChainP
                         if (row < o.Mout) {
                             if (o.out_f16) reinterpret_cast<__half *>(o.C)[row] = __float2half_rn(fsum);
                             else reinterpret_cast<float *>(o.C)[row] = fsum;
+                            for (int q = 0; q < o.npeer; ++q) {
+                                if (o.out_f16) reinterpret_cast<__half *>(o.Cpeer[q])[row] = __float2half_rn(fsum);
+                                else reinterpret_cast<float *>(o.Cpeer[q])[row] = fsum;
+                            }
                         }
                     }
                 __syncthreads();                                   // the release below is cumulative over the CTA's stores

@@ -52,7 +52,7 @@ EXPORTS = [
     "tmac_b200_default_kcfg", "tmac_b200_quantize_bitdistiller", "tmac_b200_quantize_bitnet", "tmac_b200_gguf_open", "tmac_b200_gguf_close", "tmac_b200_gguf_tensor_count", "tmac_b200_gguf_tensor_info", "tmac_b200_gguf_find_tensor",
     "tmac_b200_gguf_meta_number", "tmac_b200_gguf_meta_string", "tmac_b200_gguf_load_tensor",
     "tmac_b200_seq_create", "tmac_b200_seq_add_gemv", "tmac_b200_seq_build", "tmac_b200_seq_launch", "tmac_b200_seq_status",
-    "tmac_b200_seq_info", "tmac_b200_seq_trace", "tmac_b200_seq_free",
+    "tmac_b200_seq_info", "tmac_b200_seq_trace", "tmac_b200_seq_free", "tmac_b200_seq_peer_outputs",
     "tmac_b200_debug_ggml_mul_mat", "tmac_b200_peer_outputs", "tmac_b200_peer_barrier", "tmac_b200_ipc_alloc", "tmac_b200_ipc_open", "tmac_b200_ipc_close", "tmac_b200_ipc_free",
 ]
 
@@ -110,6 +110,7 @@ def load() -> C.CDLL:
         "tmac_b200_seq_build": (i, [i64]), "tmac_b200_seq_launch": (i, [i64]), "tmac_b200_seq_status": (i, [i64]),
         "tmac_b200_debug_ggml_mul_mat": (i, [vp, vp, vp, vp, vp, i, i, i, i, i, i]), "tmac_b200_peer_outputs": (i, [vp, i]), "tmac_b200_peer_barrier": (i, [vp, vp, i, i]), "tmac_b200_ipc_alloc": (vp, [sz, vp]), "tmac_b200_ipc_open": (vp, [vp]),
         "tmac_b200_ipc_close": (i, [vp]), "tmac_b200_ipc_free": (i, [vp]),
+        "tmac_b200_seq_peer_outputs": (i, [i64, i, vp, i]),
         "tmac_b200_seq_info": (i, [i64, C.POINTER(C.c_int)]), "tmac_b200_seq_trace": (i, [i64, vp, sz]), "tmac_b200_seq_free": (i, [i64]),
     }
     for name, (res, args) in sig.items():
@@ -315,6 +316,12 @@ class Sequence:
         check(rc, "tmac_b200_seq_add_gemv")
         self.nops += 1
         return rc
+
+    def peer_outputs(self, op: int, ptrs):
+        """Row sharding: op `op` also stores its rows at these peer addresses (ints, already offset to the shard's first row)."""
+        n = len(ptrs)
+        arr = (C.c_void_p * max(n, 1))(*ptrs)
+        check(load().tmac_b200_seq_peer_outputs(self.h, op, arr, n), "tmac_b200_seq_peer_outputs")
 
     def build(self):
         check(load().tmac_b200_seq_build(self.h), "tmac_b200_seq_build")
