@@ -69,6 +69,60 @@ def main():
             shard_wt.free()
         sv.close(dist)
     tb.debug_set("cs", 0); tb.debug_set("wpc", 0)
+
+    # ---- decode SEQUENCE with peer outputs (tmac_b200_seq_peer_outputs): every rank runs its own dependent chain (op 1 reads op 0's
+    #      rows) in one persistent launch and stores the rows of both ops into every rank's [world][2][Mout] buffer from the kernel's
+    #      epilogue; one flag exchange.  Gathered == an NCCL all-gather of the ranks' rows, == the peer-less sequence, and the oracle.
+    cfgs = [T.Config(1024, 1024, 2, zero_point=True).resolved(), T.Config(1024, 512, 2, zero_point=True).resolved()]
+    M = 1024
+    probs = [T.make_problem(c, seed=200 + 10 * rank + i) for i, c in enumerate(cfgs)]      # different weights on every rank
+    wts = [tb.upload_plain(tb.make_kcfg(c.Mout, c.K, c.bits, c.bm, c.kfactor, c.group_size, c.act_group_size, c.zero_point, c.one_scale), w, sc, z)
+           for c, (w, sc, z, _) in zip(cfgs, probs)]
+    sv = tb.SharedVector(world * 2 * M, dist, rank, world)
+    gathered = sv.local.view(world, 2, M)
+    mine = gathered[rank]
+    plain = torch.zeros((2, M), device="cuda")
+    dx = torch.from_numpy(probs[0][3][0]).cuda()
+    seqs = []
+    for dst, peers in ((mine, True), (plain, False)):
+        sq = tb.Sequence()
+        sq.add(wts[0], x=dx, out=dst[0])
+        sq.add(wts[1], in_op=0, in_offset=0, out=dst[1])
+        if peers:
+            for i in range(2):
+                sq.peer_outputs(i, [sv.peer_ptr(q) + 4 * (rank * 2 + i) * M for q in range(world) if q != rank])
+        sq.build()
+        assert sq.info()["ring_slots"] < 0, "the resident chain kernel must take this sequence"
+        seqs.append(sq)
+    for rep in range(2):
+        sv.local.zero_()
+        sv.barrier()
+        seqs[0].launch()
+        sv.barrier()
+        got = gathered.clone()
+        torch.cuda.synchronize()
+    seqs[0].status()
+    seqs[1].launch(); seqs[1].status()
+    ref = torch.zeros((world, 2, M), device="cuda")
+    dist.all_gather_into_tensor(ref.view(-1), plain.reshape(-1))
+    torch.cuda.synchronize()
+    assert torch.equal(got, ref), "rank %d: sequence gather != all-gather of the peer-less sequences" % rank
+    o = got[rank].cpu().numpy()
+    xin = probs[0][3][0]
+    for i, c in enumerate(cfgs):
+        w, sc, z, _ = probs[i]
+        A, S = T.pack_reference_layout(w, sc, z, c)
+        q, ls, lb = oracle.preprocessor(xin[None, :c.K], c.act_group_size)
+        Co = oracle.qgemm(c, A, S, q, ls, lb)[0]
+        assert np.abs(o[i] - Co).max() <= 2e-5 * np.abs(Co).max(), "rank %d op %d" % (rank, i)
+        xin = o[i]
+    if rank == 0:
+        print("OK sequence with peer outputs, world %d" % world, flush=True)
+    for sq in seqs:
+        sq.free()
+    for wt in wts:
+        wt.free()
+    sv.close(dist)
     dist.barrier()
     dist.destroy_process_group()
 
