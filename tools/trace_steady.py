@@ -33,8 +33,6 @@ nc = lib.tmac_b200_debug_trace(buf.ctypes.data, 8 * 4096)
 t = buf[:8 * nc].reshape(8, nc, 8).astype(np.float64)
 t0 = t[:, :, 0].min()
 names = ["entry", "copies issued", "pdl wait done", "lut+data ready", "loop done", "cta reduced", "cluster synced", "stored(leader)"]
-if tb.last_launch()["cluster"] == 0:   # gemv4 (stream-K): slot 6 = partial sums published, 7 = rows finished
-    names = ["entry", "copies issued", "pdl wait done", "lut+data ready", "loop done", "cta synced", "published", "finished"]
 FUSED = os.environ.get("TRACE_FUSED", "0") == "1"
 order = np.argsort(t[:, :, 0].min(axis=1))
 print("ctas per launch", nc, "; times in ns relative to the first CTA entry of the oldest launch in the ring")
