@@ -79,7 +79,9 @@ TMAC_B200_API int tmac_b200_sync(void);
  * holds blocks per CTA); batch < 0 = the tcgen05 prefill tile over -batch activation rows. */
 TMAC_B200_API int tmac_b200_debug_last_launch(int *out8);
 /* Tuning / A-B knobs at run time: key = a TMAC_B200_* environment variable name in lower case without the prefix
- * ("g4", "g4_grid", "fused", "prefill", "prefill_min_n", "pdl", "pdl_late", "cs", "wpc", "minb", "kernel"). */
+ * ("fused", "prefill", "prefill16", "pf_streamk", "prefill_min_n", "pdl", "pdl_late", "cs", "wpc", "minb", "nbuf", "trace";
+ * decode sequences: "seq_impl" 0 stream-K sequence kernel | 1 resident chain kernel | 2 chain when the sequence qualifies (default),
+ * "chain_flags" bit 0 = the chain kernel's grid-barrier form, "seq_grid", "seq_smem_kb"). */
 TMAC_B200_API int tmac_b200_debug_set(const char *key, int value);
 /* Debug (TMAC_B200_TRACE=1): per-CTA clock64 stamps [ctas][8] of the last qgemm_lut launch. */
 TMAC_B200_API int tmac_b200_debug_trace(long long *dst, int cap_ctas);
@@ -201,15 +203,18 @@ TMAC_B200_API int tmac_b200_seq_peer_outputs(int64_t seq, int op, void *const *p
 TMAC_B200_API int tmac_b200_seq_build(int64_t seq);     /* allocates the device tables; no more ops afterwards */
 TMAC_B200_API int tmac_b200_seq_launch(int64_t seq);    /* asynchronous, on the current stream; capturable in a CUDA graph */
 TMAC_B200_API int tmac_b200_seq_status(int64_t seq);    /* synchronises; 0 = ok, -1 = a bounded wait inside the kernel expired */
-/* Two kernels serve a sequence (tmac_b200_debug_set("seq_impl", 0 | 1 | 2), default 2): the resident gemv3 chain (tmac_chain.cuh: gemv3's
- * decomposition kept resident, one grid barrier per op; needs one weight format, fp32 16-byte aligned inputs, in_offset % 4 == 0) when the
- * sequence qualifies, else the stream-K sequence kernel (tmac_seq.cuh).
+/* Two kernels serve a sequence (tmac_b200_debug_set("seq_impl", 0 | 1 | 2), default 2): the resident chain kernel (tmac_chain.cuh: gemv3's
+ * decomposition kept resident, an op's inputs arrive as {value, epoch} words written by the producing clusters; needs the fp path, one weight
+ * format, fp32 producers, 16-byte aligned external inputs, even in_offset, and all clusters resident at once) when the sequence qualifies,
+ * else the stream-K sequence kernel (tmac_seq.cuh).
  * info[8] = {grid, ring slots (-8 = resident chain, clusters of 8), slot bytes, shared-memory bytes, ops, planes/word, quads/chunk,
  * quads/activation group} */
 TMAC_B200_API int tmac_b200_seq_info(int64_t seq, int *out8);
-/* Debug (tmac_b200_debug_set("trace", 1) before seq_build): globaltimer stamps [ops][grid][16] of the last launch:
+/* Debug (tmac_b200_debug_set("trace", 1) before seq_build): globaltimer stamps [ops][grid][16] of the last launch.  Stream-K kernel:
  * 0 op entered, 1 own LUT work done, 2 first block resident, 3/5/4 lookups done (first / middle / last warp), 6 CTA sums read,
- * 7 rows published, 8/9 producer thread enters / has requested the op.  Returns grid. */
+ * 7 rows published, 8/9 producer thread enters / has requested the op.  Resident chain kernel (thread 0 of every CTA): 0 op entered,
+ * 1/2 grid barrier seen / passed (barrier form only), 3 LUT slice built, 4 weight block resident, 5 lookups done, 6 CTA sums ready,
+ * 7 partial sums sent, 8 rows published (leaders).  Returns grid.  tools/seq_bench.py --trace prints both. */
 TMAC_B200_API int tmac_b200_seq_trace(int64_t seq, long long *dst, size_t cap_bytes);
 TMAC_B200_API int tmac_b200_seq_free(int64_t seq);
 /* Debug / parity gate G2: integer bit-plane sums CBits int32 [N][M*bits] in the reference
