@@ -355,6 +355,13 @@ def main():
     except Exception as ex:
         seqs = {"error": str(ex)[:160]}
     tb.debug_set("seq_impl", 2)
+    if world > 1:       # the timed sequence runs contain collectives: either every rank has its sequences or none uses them
+        okt = torch.tensor([0 if "error" in seqs else 1], device="cuda", dtype=torch.int32)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        if not bool(okt.item()) and "error" not in seqs:
+            for sq in seqs.values():
+                sq.free()
+            seqs = {"error": "another rank failed to build its sequences"}
 
     def run_steps(graph, n):
         if args.eager:
