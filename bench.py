@@ -11,12 +11,16 @@ larger than L2), each with its own activation row.  The step is captured once in
 replayed; time is CUDA events on the launching stream, max over ranks.
 
   value     = algorithmic bytes of all ranks / step time, inputs resident in HBM          [GB/s]
-              (step = one tmac_b200_gemv call per layer: LUT build fused into the GEMV launch)
-  roofline  = the dominant kernel (gemv_kernel) alone: algorithmic bytes per launch / its
-              average duration (graph of gemv launches only, same rotating buffers) vs the
-              measured HBM peak in MEASURED_PEAKS.json
+              (step = the faster of: one tmac_b200_gemv launch per layer in a CUDA graph, or the
+              decode sequence -- the layers as a DEPENDENT chain in one persistent launch;
+              roofline.submission says which)
+  roofline  = the dominant kernel of that step: algorithmic bytes per launch / its average
+              duration vs the measured HBM peak in MEASURED_PEAKS.json (chain_kernel: one launch =
+              all layers; the gemv3 launch-chain figures are kept beside it)
   e2e       = the same metric through the reference-facing call tmac_b200_gemv with HOST
-              activations/outputs (H2D + 2 kernels + D2H + sync per GEMV inside the timed region)
+              activations/outputs (H2D + kernel + result into page-locked memory + sync per GEMV
+              inside the timed region); e2e.sequence_step = the decode-loop form (host input row ->
+              one persistent launch -> all outputs to host)
   cpu_baseline = the reference's own AVX2 kernels (oracle/_ref, built from /root/reference) on the
               box's host cores, bounded sample of the same workload
   --impl reference : that CPU arm alone, same metric / config.
@@ -566,6 +570,35 @@ def main():
            "call": "tmac_b200_gemv(handle, 1, F32, host_x, host_out) per layer, synchronous: H2D copy of the activation row straight from the caller's "
                    "page-locked buffer + fused LUT/GEMV kernel storing the result into the caller's page-locked buffer + stream sync"}
     launches["n"] += 0
+    # ---- the decode-loop form of the same thing: the step's input row copied from page-locked host memory, the dependent chain as ONE
+    #      persistent launch (tmac_b200_seq_launch), every layer's output copied back to page-locked host memory, stream sync -- all inside
+    #      the timed region.  Reported beside the per-call figure (e2e.value stays the reference-facing per-op call).
+    if world == 1 and "error" not in seqs:
+        try:
+            sqd = seqs["dependent"]
+            hx0 = x[0].detach().cpu().pin_memory()
+            hseq = torch.zeros((LAYERS, MOUT)).pin_memory()
+
+            def seq_e2e_step():
+                with torch.cuda.stream(stream):
+                    x[0].copy_(hx0, non_blocking=True)
+                    sqd.launch()
+                    hseq.copy_(out_seq, non_blocking=True)
+                stream.synchronize()
+            for _ in range(3):
+                seq_e2e_step()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                seq_e2e_step()
+            seq_s = (time.perf_counter() - t0) / e2e_steps
+            sqd.status()
+            e2e["sequence_step"] = {"value": bytes_step / seq_s / 1e9, "unit": UNIT, "ms_per_step": seq_s * 1e3,
+                                    "h2d_bytes_per_step": K * 4, "d2h_bytes_per_step": LAYERS * MOUT * 4,
+                                    "equals_device_timed_outputs": bool(np.array_equal(hseq.numpy(), out_seq_host)),
+                                    "call": "copy of the step's input row from page-locked host memory + tmac_b200_seq_launch (the %d dependent GEMVs in one persistent "
+                                            "launch) + copy of all %d output rows to page-locked host memory + stream sync" % (LAYERS, LAYERS)}
+        except Exception as ex:
+            e2e["sequence_step"] = {"error": str(ex)[:200]}
     # ---- the same through the REFERENCE's own two hook symbols with host workspaces, as ggml calls them: task_init once, then
     #      task_compute for the whole tensor (ref:ggml.c:12610-12630) or once per 64-row weight tile (ref:ggml.c:12662-12691,
     #      172 tiles), driven by the C++ caller emulation tmac_b200_debug_ggml_mul_mat (no interpreter between the calls).
