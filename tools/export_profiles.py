@@ -54,7 +54,7 @@ def main():
     # SASS excerpt: the Blackwell-only mnemonics of the in-tree library
     so = os.path.join(ROOT, "t-mac_b200", "libtmac_b200.so")
     sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout.splitlines()
-    pats = ("UTCHMMA", "UTCIMMA", "UTCBAR", "LDTM", "UBLKCP", "UBLKPF", "SYNCS", "IDP.4A", "PRMT", "UTCATOM", "ACQBULK", "NANOSLEEP", "ST.E.64.STRONG.SYS", "STG.E.STRONG.SYS", "CCTL")
+    pats = ("UTCHMMA", "UTCIMMA", "UTCBAR", "LDTM", "UBLKCP", "UBLKPF", "SYNCS", "IDP.4A", "PRMT", "UTCATOM", "ACQBULK", "NANOSLEEP", "ST.E.64.STRONG.SYS", "STG.E.STRONG.SYS", "CCTL", "STAS", "UCGABAR_ARV", "UCGABAR_WAIT")
     out = ["cuobjdump -sass t-mac_b200/libtmac_b200.so: occurrences of Blackwell / hot-path mnemonics, then the first 3 lines of each", ""]
     for pt in pats:
         hits = [l.strip() for l in sass if pt in l]
